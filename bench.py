@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- detection hot path benchmark (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU decode+NMS on host cores
+
+A "step" is one pass of the hot path over one batch of 32 synthetic 640x640 frames per GPU
+(BASELINE.json configs[1]: YOLOv8n b32 640x640): batched letterbox pre-process of the frames +
+fused YoloLayer decode + NMS of the backbone's head tensors (+ the NCCL all-gather of the compact
+detections when N > 1).  The TensorRT backbone is not part of this path; its per-stride outputs are
+synthetic, seeded tensors resident in HBM (in the reference they are produced on the device by
+context.enqueue and handed to the plugin as device pointers, yolov8/yolov8_det.cpp:98).
+
+value = whole-job frames/s with inputs resident in HBM; e2e = the same step through
+DetectionPipeline.run with the frames coming from pinned HOST memory (H2D inside the timed region)
+and the compact detections copied back to the host (D2H inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 32
+NET = 640
+NC = 80
+STRIDES = (8, 16, 32)
+MAX_OUT = 1000
+CONF, IOU = 0.5, 0.45
+ALGO_BYTES_PER_IMAGE = (4 + NC) * sum((NET // s) ** 2 for s in STRIDES) * 4  # 2 822 400 B, SURVEY 8d
+METRIC = "end_to_end_fps_yolov8n_640_b32 (pre-process + fused decode + NMS); decode+NMS us/frame alongside"
+WORKLOAD = "YOLOv8n 640x640 b32/GPU: letterbox preprocess + YoloLayer decode + NMS, synthetic (SURVEY 8d), fp32 heads"
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed regions (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._pump, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, windows):
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.lines:
+            if not any(a <= ts <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # timed regions shorter than the sampling period: fall back to every sample taken
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU comparator: the reference's decode (restated, it only exists as a GPU kernel) + its host nms()
+# (oracle/ is test infrastructure; this leg and --impl reference are the only product-side users)
+# --------------------------------------------------------------------------------------------------
+def cpu_decode_nms_fps(heads_np, total_frames: int, threads: int):
+    """Run oracle decode+nms over `total_frames` frames (cycling through the batch) on `threads` host
+    threads (one frame per call; ctypes releases the GIL).  Returns (fps, kept_checksum)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from oracle import oracle as O
+
+    lib = O.load()
+    lib.oracle_yolov8_decode_nms_image.restype = C.c_int
+    B = heads_np[0].shape[0]
+    gh = (C.c_int * 3)(*[NET // s for s in STRIDES])
+    gw = (C.c_int * 3)(*[NET // s for s in STRIDES])
+    st = (C.c_int * 3)(*STRIDES)
+    kept = [0] * threads
+
+    def worker(tid):
+        scratch = np.zeros(1 + MAX_OUT * 90, np.float32)
+        res = np.zeros(MAX_OUT * 90, np.float32)
+        ptrs = (C.c_void_p * 3)()
+        for f in range(tid, total_frames, threads):
+            b = f % B
+            for l in range(3):
+                ptrs[l] = heads_np[l][b].ctypes.data
+            kept[tid] += lib.oracle_yolov8_decode_nms_image(ptrs, 3, gh, gw, st, NC, MAX_OUT, 90, C.c_float(0.1),
+                                                            C.c_float(CONF), C.c_float(IOU),
+                                                            scratch.ctypes.data_as(C.c_void_p),
+                                                            res.ctypes.data_as(C.c_void_p))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return total_frames / dt, sum(kept)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU-side decode+NMS on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from tensorrtx_b200 import synth
+
+    cores = host_cores()
+    heads = synth.yolov8_heads(BATCH, seed=0, nc=NC, net_w=NET, net_h=NET, strides=STRIDES)
+    frames_per_step = BATCH * max(1, cores // 8)  # bounded sample: ~0.1-0.2 s per step
+    for _ in range(args.warmup if args.warmup < 3 else 3):
+        cpu_decode_nms_fps(heads, frames_per_step, cores)
+    t0 = time.perf_counter()
+    kept = 0
+    for _ in range(args.steps):
+        _, k = cpu_decode_nms_fps(heads, frames_per_step, cores)
+        kept += k
+    dt = time.perf_counter() - t0
+    fps = frames_per_step * args.steps / dt
+    sample = f"{frames_per_step} frames/step x {args.steps} steps of the b32 synthetic set, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU decode (restated CalDetection, the reference has no CPU decode) + "
+                   "reference nms() restatement, oracle/trtx_oracle.c; pre-process not included"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "decode_nms_us_per_frame": 1e6 / fps, "kept_rows": kept,
+    }))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated to defeat the 126 MB L2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of CUDA graphs")
+    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+
+    from tensorrtx_b200 import _lib as L
+    from tensorrtx_b200 import synth
+    from tensorrtx_b200.pipeline import DetectionPipeline, gather
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    # ---- synthetic inputs: `sets` distinct batches so consecutive steps never hit L2-resident data ----
+    R = max(1, args.sets)
+    head_dtype = L.F32 if args.head_dtype == "f32" else L.F16
+    tdt = torch.float32 if head_dtype == L.F32 else torch.float16
+    heads_np0 = None
+    head_sets, frame_sets_host = [], []
+    for i in range(R):
+        hn = synth.yolov8_heads(BATCH, seed=1000 * rank + i, nc=NC, net_w=NET, net_h=NET, strides=STRIDES)
+        if i == 0:
+            heads_np0 = hn
+        head_sets.append([torch.from_numpy(h).to(dev).to(tdt).contiguous() for h in hn])
+        frame_sets_host.append(torch.from_numpy(synth.frames(BATCH, seed=77 + 1000 * rank + i, h=NET, w=NET)).pin_memory())
+    frame_sets_dev = [f.to(dev) for f in frame_sets_host]
+    head_bytes = sum(h.numel() * h.element_size() for h in head_sets[0])
+    assert head_dtype != L.F32 or head_bytes == BATCH * ALGO_BYTES_PER_IMAGE
+
+    pipe = DetectionPipeline(BATCH, NET, NET, NET, NET, NC, STRIDES, MAX_OUT, CONF, IOU, dev, head_dtype=head_dtype)
+    stream = torch.cuda.Stream(dev)
+    gathered = None
+
+    # device-resident step i: frames of set i (already in HBM) -> preprocess -> decode+NMS (-> all-gather)
+    pipes_dev = []
+    for i in range(R):
+        p = pipe if i == 0 else DetectionPipeline(BATCH, NET, NET, NET, NET, NC, STRIDES, MAX_OUT, CONF, IOU, dev,
+                                                  head_dtype=head_dtype)
+        p.frames_dev.copy_(frame_sets_dev[i])
+        pipes_dev.append(p)
+    del frame_sets_dev
+
+    with torch.cuda.stream(stream):
+        if args.no_graph:
+            dev_steps = [(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
+            e2e_steps = [(lambda p=p, f=f, h=h: p.run(f, h)) for p, f, h in zip(pipes_dev, frame_sets_host, head_sets)]
+        else:
+            dg = [p.capture(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
+            eg = [p.capture(lambda p=p, f=f, h=h: p.run(f, h)) for p, f, h in zip(pipes_dev, frame_sets_host, head_sets)]
+            dev_steps = [g.replay for g in dg]
+            e2e_steps = [g.replay for g in eg]
+
+        def step_dev(i):
+            dev_steps[i % R]()
+            if world > 1:
+                return gather(pipes_dev[i % R].fused.out, world)
+
+        def step_e2e(i):
+            e2e_steps[i % R]()
+            if world > 1:
+                return gather(pipes_dev[i % R].fused.out, world)
+
+        def timed(step, K, W):
+            for i in range(W):
+                step(i)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            e0.record(stream)
+            for i in range(K):
+                step(W + i)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            t1 = time.time()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, (t0, t1)
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        K, W = args.steps, args.warmup
+        ms_dev, win_dev = timed(step_dev, K, W)
+        ms_e2e, win_e2e = timed(step_e2e, K, W)
+
+        # ---- decode+NMS only (the "decode+NMS us/frame" half of the metric) and the scan kernel alone,
+        #      launched unfused with CUDA events around the scan kernel on its launching stream ----
+        fused = pipe.fused
+        for i in range(W):
+            fused.enqueue(BATCH, head_sets[i % R])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            fused.enqueue(BATCH, head_sets[(W + i) % R])
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms_decnms = e0.elapsed_time(e1) / K
+
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            h = head_sets[(W + i) % R]
+            ev[i][0].record(stream)
+            fused.enqueue_scan(BATCH, h)
+            ev[i][1].record(stream)
+            fused.enqueue_nms(BATCH, h)
+        torch.cuda.synchronize(dev)
+        scan_ms = [a.elapsed_time(b) for a, b in ev]
+        scan_ms_avg = sum(scan_ms) / len(scan_ms)
+        # back-to-back scan launches between two events (amortises the event overhead)
+        e0.record(stream)
+        for i in range(K):
+            fused.enqueue_scan(BATCH, head_sets[(W + i) % R])
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        scan_ms_b2b = e0.elapsed_time(e1) / K
+        if rank == 0:
+            sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback"
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak = 6650.0  # B200_PROFILING.md fallback
+    algo = head_bytes  # bytes one scan launch must read (all class + box rows of 32 images)
+    achieved = algo / (scan_ms_avg * 1e-3) / 1e9
+    fps = world * BATCH * K / (ms_dev * 1e-3)
+    fps_e2e = world * BATCH * K / (ms_e2e * 1e-3)
+    out = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if head_dtype == L.F32 else "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "net": [NET, NET],
+                   "num_classes": NC, "max_out": MAX_OUT, "conf_thresh": CONF, "nms_thresh": IOU,
+                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [32,1+1000*7] fp32 per step)" if world > 1 else "single GPU",
+                   "l2": f"inputs rotate over {R} distinct sets ({R * head_bytes / 1e6:.0f} MB of head tensors + "
+                         f"{R * BATCH * NET * NET * 3 / 1e6:.0f} MB of frames > 126 MB L2)",
+                   "cuda_graphs": not args.no_graph,
+                   "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
+        "clocks": sampler.summary([win_dev, win_e2e]),
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / K,
+                "note": "frames from pinned host memory (H2D) + compact detections back to pinned host (D2H) every step"},
+        "gpu_launches": 3 * K,  # letterbox_kernel + yolo_v8_scan_kernel + nms_kernel per step
+        "decode_nms_us_per_frame": ms_decnms * 1e3 / BATCH,
+        "decode_nms_ms_per_batch": ms_decnms,
+        "roofline": {"bound": "hbm", "kernel": "yolo_v8_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": algo, "kernel_us": scan_ms_avg * 1e3,
+                     "kernel_us_back_to_back": scan_ms_b2b * 1e3,
+                     "achieved_back_to_back": algo / (scan_ms_b2b * 1e-3) / 1e9,
+                     "how": "CUDA events around each scan launch on its stream, averaged over the K steps of the unfused loop"},
+    }
+    if not args.no_cpu_baseline:
+        cores = host_cores()
+        total = 128 * cores  # ~0.5 s of CPU work per core: bounded sample
+        cfps, _ = cpu_decode_nms_fps(heads_np0, total, cores)
+        c1fps, _ = cpu_decode_nms_fps(heads_np0, 64, 1)
+        out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": f"{total} frames (the b32 set cycled), decode+nms oracle, {cores} threads",
+                               "single_thread_fps": c1fps, "us_per_frame_single_thread": 1e6 / c1fps}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

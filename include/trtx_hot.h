@@ -1,0 +1,228 @@
+/*
+ * trtx_hot.h -- C ABI of the B200-native detection hot path (libtrtx_hot.so).
+ *
+ * This is the drop-in boundary: every entry point below is what a TensorRT plugin's
+ * enqueue()/getWorkspaceSize() (or the driver's cuda_* helper) in wang-xinyu/tensorrtx
+ * binds to.  Plain pointers and sizes only; all pointers named *_dev are DEVICE pointers
+ * owned by the caller (TensorRT owns inputs/outputs/workspace);
+ * nothing is allocated, freed, retained or synchronised inside an enqueue; every call is
+ * re-entrant and ordered on the given stream.  Return value: 0 = success (the reference's
+ * enqueue() convention, yolov8/plugin/yololayer.cu:171), non-zero = TRTX_ERR_*; the library
+ * never throws and never asserts.
+ *
+ * Reference citations are relative to /root/reference (wang-xinyu/tensorrtx @ 3ff22bb4).
+ * The header-only TensorRT adapters that forward the IPluginV2DynamicExt / IPluginV2IOExt /
+ * IPluginV2Ext virtuals to these functions live in include/trtx_plugins.h; the binding a
+ * maintainer adds on the reference side is shown in INTEGRATION.md.
+ */
+#ifndef TRTX_HOT_H
+#define TRTX_HOT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TRTX_API __declspec(dllexport)
+#else
+#define TRTX_API __attribute__((visibility("default")))
+#endif
+
+/* cudaStream_t, spelled without <cuda_runtime.h> so that C / cgo / ctypes callers can include this. */
+typedef void* trtx_stream_t;
+
+enum {
+    TRTX_OK = 0,
+    TRTX_ERR_INVALID = 1,     /* malformed params / null pointer */
+    TRTX_ERR_WORKSPACE = 2,   /* workspace too small (the reference throws here, rcnn/cuda_utils.h:22-24) */
+    TRTX_ERR_CUDA = 3,        /* a launch failed; see trtx_last_cuda_error() */
+    TRTX_ERR_UNSUPPORTED = 4, /* parameter combination outside what the kernels cover */
+};
+
+#define TRTX_MAX_LEVELS 8
+
+TRTX_API const char* trtx_version(void);
+/* cudaError_t of the last failing launch on this thread (0 if none). */
+TRTX_API int trtx_last_cuda_error(void);
+
+/* =====================================================================================
+ * 1. YoloLayer_TRT  -- fused per-anchor sigmoid / argmax / gate / box decode / compaction
+ *    replaces CalDetection + forwardGpu of
+ *      yolov8/plugin/yololayer.cu:178-316 (anchor-free: yolov8, yolo11, yolov12, yolov13, yolov9/10 subsets)
+ *      yolov5/plugin/yololayer.cu:161-227 (anchor-based: yolov5, yolov7, yolov5-lite, yolop)
+ * ===================================================================================== */
+enum { TRTX_YOLO_V8 = 0, TRTX_YOLO_V5 = 1 };
+enum { TRTX_F32 = 0, TRTX_F16 = 1 };
+
+typedef struct trtx_yolo_params {
+    int32_t variant;     /* TRTX_YOLO_V8 | TRTX_YOLO_V5 */
+    int32_t num_classes; /* combinedInfo[0] (yolov8/src/block.cpp:268) | netinfo[0] (yolov5/src/model.cpp:249) */
+    int32_t net_w;       /* kInputW */
+    int32_t net_h;       /* kInputH */
+    int32_t max_out;     /* kMaxNumOutputBbox: capacity of the plugin output, rows per image */
+    int32_t det_floats;  /* sizeof(Detection)/4 of the model dir: 90 (yolov8/include/types.h:4-12),
+                            38 (yolov5/src/types.h:11-16), 6 (yolov7/10/13) */
+    int32_t num_levels;  /* number of input tensors (strides) */
+    int32_t grid_h[TRTX_MAX_LEVELS]; /* v8: net_h/stride (yololayer.cu:294); v5: YoloKernel.height */
+    int32_t grid_w[TRTX_MAX_LEVELS];
+    int32_t strides[TRTX_MAX_LEVELS];   /* v8 only (combinedInfo[9..]) */
+    float anchors[TRTX_MAX_LEVELS][6];  /* v5 only: YoloKernel.anchors (yolov5/src/types.h:5-9) */
+    int32_t is_seg;      /* copy 32 mask coefficients */
+    int32_t is_pose;     /* v8: decode num_kpts keypoints */
+    int32_t is_obb;      /* v8: rotated box */
+    int32_t num_kpts;    /* combinedInfo[1] */
+    float kpt_thresh;    /* combinedInfo[2] (int-truncated by the reference builder, block.cpp:271) */
+    float gate;          /* 0.1f: literal of yolov8 yololayer.cu:203 / kIgnoreThresh yolov5 config.h:38 */
+    int32_t in_dtype;    /* TRTX_F32 (parity mode, what the reference accepts, yololayer.h:32-35) | TRTX_F16 */
+} trtx_yolo_params;
+
+/* Fill grid_h/grid_w from net size and strides (v8) -- convenience, mirrors yololayer.cu:292-296. */
+TRTX_API int trtx_yolo_params_init_v8(trtx_yolo_params* p, int num_classes, int net_w, int net_h, int max_out,
+                                      const int* strides, int num_levels);
+
+/* Scratch bytes for trtx_yolo_decode_enqueue / trtx_yolo_decode_nms_enqueue at `batch` images.
+ * (The reference plugin needs none, yololayer.h:22; this build stages candidates per tile so that
+ *  compaction is atomic-free and deterministic.) */
+TRTX_API size_t trtx_yolo_workspace_size(const trtx_yolo_params* p, int batch);
+
+/* Drop-in for YoloLayerPlugin::enqueue (yolov8/plugin/yololayer.cu:167-172, yolov5 :229-232).
+ *  inputs_dev[l] : level-l tensor [batch, C_l, grid_h*grid_w], channel-major, fp32 (or fp16)
+ *  output_dev    : [batch, 1 + max_out*det_floats] fp32: count, Detection rows.
+ * Rows appear in ascending anchor order (deterministic; the reference's order is atomicAdd arrival).
+ * count is clamped to max_out (the reference lets it run past, which overruns host readers). */
+TRTX_API int trtx_yolo_decode_enqueue(const trtx_yolo_params* p, int batch, const void* const* inputs_dev,
+                                      float* output_dev, void* workspace_dev, size_t workspace_bytes,
+                                      trtx_stream_t stream);
+
+/* =====================================================================================
+ * 2. NMS -- sort + greedy class-aware NMS, one CTA per image, all images in one launch.
+ *    replaces the host nms()/batch_nms() of yolov8/src/postprocess.cpp:94-129,
+ *    yolov5/src/postprocess.cpp:49-80, retinaface/common.hpp:110-130 and the device
+ *    cuda_decode()+cuda_nms() of yolov8/src/postprocess.cu:168-179 (batch 1 only there).
+ * ===================================================================================== */
+enum {
+    TRTX_BOX_LTRB = 0,   /* yolov8 Detection: x1,y1,x2,y2; IoU of postprocess.cpp:71-85 */
+    TRTX_BOX_CXCYWH = 1, /* yolov5 Detection: cx,cy,w,h;   IoU of yolov5 postprocess.cpp:30-43 */
+    TRTX_BOX_RETINA = 2, /* retinaface: x1,y1,x2,y2, +1e-6f in the denominator, single class (common.hpp:91-104) */
+};
+enum {
+    TRTX_NMS_GREEDY = 0,  /* CPU nms() semantics (the contract, SURVEY.md section 7 "Hard parts") */
+    TRTX_NMS_ONESHOT = 1, /* nms_kernel semantics, yolov8/src/postprocess.cu:89-111 */
+};
+
+typedef struct trtx_nms_params {
+    int32_t box_format;  /* TRTX_BOX_* */
+    int32_t mode;        /* TRTX_NMS_* */
+    float conf_thresh;   /* rows with !(conf > conf_thresh) are dropped (kConfThresh 0.5 / retinaface 0.1 rounded
+                            so that the float compare equals the reference's double compare) */
+    float nms_thresh;    /* kNmsThresh 0.45 / 0.4 */
+    int32_t max_det;     /* K: rows of the compact output per image (kMaxNumOutputBbox) */
+    int32_t class_aware; /* 1: only same-class rows interact (yolo); 0: single class (retinaface) */
+    int32_t tie_break_x0; /* 1: equal conf ordered by box[0] ascending (yolov8 cmp, postprocess.cpp:87-92); 0: none */
+    int32_t extra_floats; /* floats copied verbatim from each source row into the output row after `keep`
+                             (retinaface: 10 landmarks; yolo seg: 32 mask coefficients); 0 for plain det */
+    int32_t extra_offset; /* offset (floats) of the first extra in the source row (retinaface 5, yolo seg 6) */
+} trtx_nms_params;
+
+/* Compact detection output: [batch, 1 + max_det*R] fp32, R = 7 + extra_floats:
+ * count, (x0,x1,x2,x3,conf,cls,keep, extras...)*   (R = 7 is the layout of yolov8/include/types.h:18-19 +
+ * postprocess.cu:64-71; box in the input's format).  Rows are ordered class asc then conf desc -- the
+ * order of the reference's `res` vector (std::map iteration + std::sort).
+ * GREEDY: only kept rows are written (keep=1), count = number kept.  ONESHOT: all rows above
+ * conf_thresh, keep flag 0/1, count = rows.  Rows >= count are zero.
+ * At most `max_rows` (trtx_nms_enqueue) / `p->max_out` (fused) highest-conf rows enter NMS.
+ * keep_index_dev (optional, may be NULL): [batch, max_det] int32 flat anchor id of each written row. */
+
+/* NMS over a plugin-format buffer [batch, 1 + max_rows*det_floats] (drop-in for batch_nms()). */
+TRTX_API size_t trtx_nms_workspace_size(const trtx_nms_params* p, int batch, int max_rows);
+TRTX_API int trtx_nms_enqueue(const trtx_nms_params* p, int batch, const float* plugin_out_dev, int max_rows,
+                              int det_floats, float* compact_out_dev, int32_t* keep_index_dev, void* workspace_dev,
+                              size_t workspace_bytes, trtx_stream_t stream);
+
+/* Fused decode + NMS: YoloLayer inputs -> compact detections, no plugin-format round trip. */
+TRTX_API int trtx_yolo_decode_nms_enqueue(const trtx_yolo_params* p, const trtx_nms_params* q, int batch,
+                                          const void* const* inputs_dev, float* compact_out_dev,
+                                          int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
+                                          trtx_stream_t stream);
+
+/* Split form of the fused call (same workspace, same stream order): scan = the HBM-bound streaming
+ * kernel alone, then NMS over its tiles.  Used to time the scan kernel in isolation and to overlap the
+ * scan of batch i+1 with the NMS of batch i on two streams. */
+TRTX_API int trtx_yolo_scan_enqueue(const trtx_yolo_params* p, int batch, const void* const* inputs_dev,
+                                    void* workspace_dev, size_t workspace_bytes, trtx_stream_t stream);
+TRTX_API int trtx_yolo_nms_after_scan_enqueue(const trtx_yolo_params* p, const trtx_nms_params* q, int batch,
+                                              const void* const* inputs_dev, float* compact_out_dev,
+                                              int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
+                                              trtx_stream_t stream);
+
+/* =====================================================================================
+ * 3. Decode_TRT (RetinaFace) -- replaces retinaface/decode.cu:110-199
+ *    inputs_dev[l] : [batch, 32, (in_h/s)*(in_w/s)] fp32, s = 8,16,32, channels [bbox 2x4 | cls 2x2 | lmk 2x10]
+ *    output_dev    : [batch, 1 + total_priors*15] fp32, rows x1,y1,x2,y2,conf,lmk[10]
+ * ===================================================================================== */
+typedef struct trtx_retina_params {
+    int32_t in_h, in_w; /* decodeplugin::INPUT_H / INPUT_W (compile-time 480x640 in decode.h:16-17) */
+    float gate;         /* 0.02 (decode.cu:131); compared as `conf <= gate` */
+} trtx_retina_params;
+
+TRTX_API int trtx_retina_total_priors(const trtx_retina_params* p);
+TRTX_API size_t trtx_retina_workspace_size(const trtx_retina_params* p, int batch);
+TRTX_API int trtx_retina_decode_enqueue(const trtx_retina_params* p, int batch, const void* const* inputs_dev,
+                                        float* output_dev, void* workspace_dev, size_t workspace_bytes,
+                                        trtx_stream_t stream);
+
+/* =====================================================================================
+ * 4. Faster R-CNN plugins -- same "null workspace returns the size" idiom as the reference
+ *    free functions (rcnn/RpnNms.cu:63-80): call with workspace_dev == NULL to get bytes.
+ *    All images of the batch are processed in one launch (the reference loops on the host).
+ * ===================================================================================== */
+/* rpnDecode, rcnn/RpnDecode.cu:27-143.  inputs: scores [B,A,H,W], deltas [B,A*4,H,W];
+ * outputs: scores [B,top_n], boxes [B,top_n,4].  anchors_host: A*4 floats (host memory, copied
+ * into the launch parameters -- no H2D copy per enqueue). */
+TRTX_API int64_t trtx_rpn_decode(int batch, const float* scores_dev, const float* deltas_dev, float* out_scores_dev,
+                                 float* out_boxes_dev, int height, int width, int image_height, int image_width,
+                                 float stride, const float* anchors_host, int num_anchors, int top_n,
+                                 void* workspace_dev, size_t workspace_bytes, trtx_stream_t stream);
+/* rpnNms, rcnn/RpnNms.cu:59-121.  inputs: scores [B,pre], boxes [B,pre,4]; output boxes [B,post,4]. */
+TRTX_API int64_t trtx_rpn_nms(int batch, const float* scores_dev, const float* boxes_dev, float* out_boxes_dev,
+                              int pre_nms_topk, int post_nms_topk, float nms_thresh, void* workspace_dev,
+                              size_t workspace_bytes, trtx_stream_t stream);
+/* predictorDecode, rcnn/PredictorDecode.cu:24-110.  inputs: scores [B,N,C], deltas [B,N*C,4],
+ * proposals [B,N,4]; outputs scores/boxes/classes [B,N,...]. */
+TRTX_API int64_t trtx_predictor_decode(int batch, const float* scores_dev, const float* deltas_dev,
+                                       const float* proposals_dev, float* out_scores_dev, float* out_boxes_dev,
+                                       float* out_classes_dev, int num_boxes, int num_classes, int image_height,
+                                       int image_width, const float* bbox_reg_weights_host, void* workspace_dev,
+                                       size_t workspace_bytes, trtx_stream_t stream);
+/* batchedNms, rcnn/BatchedNms.cu:92-162.  nms_method 0 hard / 1 soft-linear / 2 soft-gaussian. */
+TRTX_API int64_t trtx_batched_nms(int nms_method, int batch, const float* scores_dev, const float* boxes_dev,
+                                  const float* classes_dev, float* out_scores_dev, float* out_boxes_dev,
+                                  float* out_classes_dev, int count, int detections_per_im, float nms_thresh,
+                                  void* workspace_dev, size_t workspace_bytes, trtx_stream_t stream);
+
+/* =====================================================================================
+ * 5. Pre-process -- batched letterbox warp + BGR->RGB + /255 + HWC->CHW (+fp16)
+ *    replaces warpaffine_kernel / cuda_preprocess / cuda_batch_preprocess,
+ *    yolov8/src/preprocess.cu:7-127 (one launch + one stream sync PER IMAGE there).
+ * ===================================================================================== */
+typedef struct trtx_image_desc {
+    const uint8_t* data_dev; /* u8 HWC BGR, row pitch = pitch bytes */
+    int32_t width, height;
+    int32_t pitch; /* bytes per row, >= 3*width */
+    int32_t reserved;
+} trtx_image_desc;
+
+/* images_host: array of `batch` descriptors in HOST memory (copied into launch parameters);
+ * dst_dev: [batch, 3, dst_h, dst_w] fp32 or fp16 (out_dtype TRTX_F32 | TRTX_F16). One launch. */
+TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, int batch, void* dst_dev, int dst_w,
+                                           int dst_h, int out_dtype, trtx_stream_t stream);
+/* The reference's d2s matrix (preprocess.cu:98-110): scale, centre, cv::invertAffineTransform. */
+TRTX_API void trtx_letterbox_matrix(int src_w, int src_h, int dst_w, int dst_h, float d2s[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRTX_HOT_H */

@@ -1,0 +1,577 @@
+// nms.cu -- sort + class-aware greedy NMS, one 1024-thread CTA per image, every image of the batch
+// in one launch.  Replaces
+//   host  nms()/batch_nms()      yolov8/src/postprocess.cpp:94-129, yolov5/src/postprocess.cpp:49-80,
+//                                retinaface/common.hpp:110-130           (std::map + std::sort + erase)
+//   device cuda_decode()+cuda_nms()  yolov8/src/postprocess.cu:42-111,168-179   (batch 1 only, one-shot)
+//
+// Phases (all on-chip after the first read of the candidates; latency/occupancy-bound, no roofline):
+//   A  collect rows with conf > conf_thresh into a list (conf key, id)
+//   B  if more than `pre_topk` survive: block radix-select (4 x 8-bit passes) of the top pre_topk,
+//      ties at the cut broken by the smaller id (second radix select over the ids)
+//   C  bitonic sort in shared memory by (class asc, conf desc, box[0] asc, id asc)  -- the order the
+//      reference builds with std::map<float,...> + std::sort(cmp)
+//   D  stage boxes of the sorted rows in shared memory (SoA)
+//   E  greedy NMS in chunks of 32 sorted rows: every chunk member is tested against the already-kept
+//      rows of its class (all 1024 threads, IoU tile in shared memory) and against its 31 chunk-mates
+//      (warp w = member w, lane j = mate j, one __ballot_sync per member gives its suppressor bitmap);
+//      warp 0 then resolves the chunk serially on the 32x32 bitmap.  2 barriers per 32 rows.
+//   F  write [count, (box, conf, cls, keep, extras)*].
+//
+// IoU arithmetic mirrors the reference's CPU functions operation by operation with round-to-nearest
+// intrinsics (no FMA contraction), so kept sets agree with the host code bit for bit.
+#include "yolo_layout.cuh"
+
+namespace trtx {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kMaxSort = 2048;  // rows entering NMS per image (>= kMaxNumOutputBbox = 1000)
+
+struct NmsArgs {
+    // source 0: plugin-format rows  [B, 1 + max_rows*det_floats]
+    const float* rows;
+    int max_rows;
+    int det_floats;
+    // source 1: YoloLayer tiles (fused path)
+    int from_tiles;
+    int tiles_per_image, slots_per_image, tile_slots;
+    int num_levels;
+    int lv_tile_begin[TRTX_MAX_LEVELS];
+    int lv_slot_begin[TRTX_MAX_LEVELS];
+    const int* tile_count;
+    const float4* cand;
+    // scratch list [B, list_stride] of (conf key, id)
+    uint2* list;
+    int list_stride;
+    // parameters
+    int box_format, mode, class_aware, tie_break_x0;
+    float conf_thresh, nms_thresh;
+    int pre_topk;  // rows entering NMS (<= kMaxSort)
+    int max_det;
+    int extra_floats, extra_offset;
+    float* out;           // [B, 1 + max_det*(7+extra)]
+    int32_t* keep_index;  // [B, max_det] or null
+};
+
+// ---- IoU variants -------------------------------------------------------------------------
+// yolov8/src/postprocess.cpp:71-85 (std::max(a,b) = a<b ? b : a ; std::min(a,b) = b<a ? b : a)
+__device__ __forceinline__ float iou_ltrb(const float4 l, const float4 r) {
+    float ib0 = l.x < r.x ? r.x : l.x;
+    float ib1 = r.z < l.z ? r.z : l.z;
+    float ib2 = l.y < r.y ? r.y : l.y;
+    float ib3 = r.w < l.w ? r.w : l.w;
+    if (ib2 > ib3 || ib0 > ib1) return 0.0f;
+    float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
+    float la = __fmul_rn(__fsub_rn(l.z, l.x), __fsub_rn(l.w, l.y));
+    float ra = __fmul_rn(__fsub_rn(r.z, r.x), __fsub_rn(r.w, r.y));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(la, ra), inter));
+}
+// yolov5/src/postprocess.cpp:30-43
+__device__ __forceinline__ float iou_cxcywh(const float4 l, const float4 r) {
+    float a0 = __fsub_rn(l.x, __fdiv_rn(l.z, 2.f)), b0 = __fsub_rn(r.x, __fdiv_rn(r.z, 2.f));
+    float a1 = __fadd_rn(l.x, __fdiv_rn(l.z, 2.f)), b1 = __fadd_rn(r.x, __fdiv_rn(r.z, 2.f));
+    float a2 = __fsub_rn(l.y, __fdiv_rn(l.w, 2.f)), b2 = __fsub_rn(r.y, __fdiv_rn(r.w, 2.f));
+    float a3 = __fadd_rn(l.y, __fdiv_rn(l.w, 2.f)), b3 = __fadd_rn(r.y, __fdiv_rn(r.w, 2.f));
+    float ib0 = a0 < b0 ? b0 : a0;
+    float ib1 = b1 < a1 ? b1 : a1;
+    float ib2 = a2 < b2 ? b2 : a2;
+    float ib3 = b3 < a3 ? b3 : a3;
+    if (ib2 > ib3 || ib0 > ib1) return 0.0f;
+    float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(l.z, l.w), __fmul_rn(r.z, r.w)), inter));
+}
+// retinaface/common.hpp:91-104
+__device__ __forceinline__ float iou_retina(const float4 l, const float4 r) {
+    float ib0 = l.x < r.x ? r.x : l.x;
+    float ib1 = r.z < l.z ? r.z : l.z;
+    float ib2 = l.y < r.y ? r.y : l.y;
+    float ib3 = r.w < l.w ? r.w : l.w;
+    if (ib2 > ib3 || ib0 > ib1) return 0.0f;
+    float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
+    float la = __fmul_rn(__fsub_rn(l.z, l.x), __fsub_rn(l.w, l.y));
+    float ra = __fmul_rn(__fsub_rn(r.z, r.x), __fsub_rn(r.w, r.y));
+    return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(la, ra), inter), 0.000001f));
+}
+// yolov8/src/postprocess.cu:74-87 (device box_iou of the one-shot path)
+__device__ __forceinline__ float iou_oneshot(const float4 a, const float4 b) {
+    float cl = fmaxf(a.x, b.x), ct = fmaxf(a.y, b.y), cr = fminf(a.z, b.z), cb = fminf(a.w, b.w);
+    float c_area = __fmul_rn(fmaxf(__fsub_rn(cr, cl), 0.0f), fmaxf(__fsub_rn(cb, ct), 0.0f));
+    if (c_area == 0.0f) return 0.0f;
+    float a_area = __fmul_rn(fmaxf(0.0f, __fsub_rn(a.z, a.x)), fmaxf(0.0f, __fsub_rn(a.w, a.y)));
+    float b_area = __fmul_rn(fmaxf(0.0f, __fsub_rn(b.z, b.x)), fmaxf(0.0f, __fsub_rn(b.w, b.y)));
+    return __fdiv_rn(c_area, __fsub_rn(__fadd_rn(a_area, b_area), c_area));
+}
+__device__ __forceinline__ float iou_any(int fmt, const float4 l, const float4 r) {
+    if (fmt == TRTX_BOX_LTRB) return iou_ltrb(l, r);
+    if (fmt == TRTX_BOX_CXCYWH) return iou_cxcywh(l, r);
+    return iou_retina(l, r);
+}
+
+// ---- candidate accessors --------------------------------------------------------------------
+struct Row {
+    float4 box;
+    float conf;
+    float cls;
+    int anchor;
+};
+__device__ __forceinline__ Row fetch_row(const NmsArgs& a, int b, uint32_t id) {
+    Row r;
+    if (a.from_tiles) {
+        const float4* c = a.cand + 2 * ((size_t)b * a.slots_per_image + id);
+        r.box = c[0];
+        float4 m = c[1];
+        r.conf = m.x;
+        r.cls = m.y;
+        r.anchor = __float_as_int(m.z);
+    } else {
+        const float* p = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 + (size_t)id * a.det_floats;
+        r.box = make_float4(p[0], p[1], p[2], p[3]);
+        r.conf = p[4];
+        r.cls = a.box_format == TRTX_BOX_RETINA ? 0.0f : p[5];
+        r.anchor = (int)id;
+    }
+    return r;
+}
+
+// Block-wide: find the bucket holding the `need`-th element counting from the top (descending)
+// or from the bottom (ascending) of a 256-bin histogram; returns bucket, updates need to the
+// rank inside that bucket.  Executed by thread 0, result broadcast through shared memory.
+__device__ __forceinline__ void pick_bucket(const int* hist, bool descending, int* need_io, int* bucket_out) {
+    int need = *need_io, c = 0, d;
+    if (descending) {
+        for (d = 255; d > 0; --d) {
+            if (c + hist[d] >= need) break;
+            c += hist[d];
+        }
+    } else {
+        for (d = 0; d < 255; ++d) {
+            if (c + hist[d] >= need) break;
+            c += hist[d];
+        }
+    }
+    *need_io = need - c;
+    *bucket_out = d;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // carve-up (S = sort capacity, power of two >= pre_topk)
+    const int S = a.pre_topk <= 1024 ? 1024 : kMaxSort;
+    unsigned long long* k_hi = reinterpret_cast<unsigned long long*>(smem_raw);  // S
+    unsigned long long* k_lo = k_hi + S;                                         // S
+    float4* s_box = reinterpret_cast<float4*>(k_lo + S);                         // S
+    float* s_conf = reinterpret_cast<float*>(s_box + S);                         // S
+    int* s_cls = reinterpret_cast<int*>(s_conf + S);                             // S
+    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_cls + S);                     // S
+    int* s_kcls = reinterpret_cast<int*>(s_id + S);                              // S
+    int* s_kpos = s_kcls + S;                                                    // S
+    float4* s_kbox = reinterpret_cast<float4*>(k_hi);  // aliases the sort keys (dead after phase D)
+
+    __shared__ int s_hist[256];
+    __shared__ int s_n, s_need, s_bucket, s_nkept;
+    __shared__ unsigned s_rem;
+    __shared__ unsigned s_sup[32];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint2* list = a.list + (size_t)b * a.list_stride;
+
+    // ---------------- A: collect rows above conf_thresh ----------------
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if (a.from_tiles) {
+        const int* cnt = a.tile_count + (size_t)b * a.tiles_per_image;
+        for (int t = warp; t < a.tiles_per_image; t += kNmsThreads / 32) {
+            const int n = cnt[t];
+            if (n == 0) continue;
+            int l = 0;
+            while (l + 1 < a.num_levels && t >= a.lv_tile_begin[l + 1]) ++l;
+            const uint32_t slot0 = a.lv_slot_begin[l] + (uint32_t)(t - a.lv_tile_begin[l]) * a.tile_slots;
+            for (int j = lane; j < n; j += 32) {
+                const uint32_t id = slot0 + j;
+                const float conf = a.cand[2 * ((size_t)b * a.slots_per_image + id) + 1].x;
+                // greedy: `conf <= thr -> skip` (postprocess.cpp:99; false for NaN, which v8 skips too);
+                // one-shot: `conf < thr -> skip` (postprocess.cu:57)
+                if (a.mode == TRTX_NMS_ONESHOT ? conf >= a.conf_thresh : conf > a.conf_thresh) {
+                    int pos = atomicAdd(&s_n, 1);
+                    list[pos] = make_uint2(float_key(conf), id);
+                }
+            }
+        }
+    } else {
+        const float* img = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats);
+        int n_in = (int)img[0];  // `i < output[0]`
+        n_in = max(0, min(n_in, a.max_rows));
+        for (int i = tid; i < n_in; i += kNmsThreads) {
+            const float conf = img[1 + (size_t)i * a.det_floats + 4];
+            if (a.mode == TRTX_NMS_ONESHOT ? conf >= a.conf_thresh : conf > a.conf_thresh) {
+                int pos = atomicAdd(&s_n, 1);
+                list[pos] = make_uint2(float_key(conf), (uint32_t)i);
+            }
+        }
+    }
+    __syncthreads();
+    const int n_valid = s_n;
+    int M = min(n_valid, a.pre_topk);
+
+    // ---------------- B: radix select when more than pre_topk rows survive ----------------
+    uint32_t key_cut = 0, id_cut = 0xffffffffu;  // take key > key_cut, or key == key_cut && id <= id_cut
+    if (n_valid > a.pre_topk) {
+        uint32_t prefix = 0, mask = 0;
+        if (tid == 0) s_need = a.pre_topk;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n_valid; i += kNmsThreads) {
+                uint32_t k = list[i].x;
+                if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int need = s_need, d;
+                pick_bucket(s_hist, true, &need, &d);
+                s_need = need;
+                s_bucket = d;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)s_bucket << shift;
+            mask |= 255u << shift;
+        }
+        key_cut = prefix;
+        const int need_eq = s_need;  // how many rows with key == key_cut are taken
+        // ties at the cut: take the need_eq smallest ids
+        uint32_t ip = 0, im = 0;
+        __syncthreads();
+        if (tid == 0) s_need = need_eq;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n_valid; i += kNmsThreads) {
+                uint2 e = list[i];
+                if (e.x == key_cut && (e.y & im) == ip) atomicAdd(&s_hist[(e.y >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int need = s_need, d;
+                pick_bucket(s_hist, false, &need, &d);
+                s_need = need;
+                s_bucket = d;
+            }
+            __syncthreads();
+            ip |= (uint32_t)s_bucket << shift;
+            im |= 255u << shift;
+        }
+        id_cut = ip;
+        __syncthreads();
+    }
+
+    // ---------------- C: build sort keys, bitonic sort ----------------
+    int S_eff = 32;
+    while (S_eff < M) S_eff <<= 1;
+    if (tid == 0) s_n = 0;
+    for (int i = tid; i < S_eff; i += kNmsThreads) {
+        k_hi[i] = ~0ull;
+        k_lo[i] = ~0ull;
+    }
+    __syncthreads();
+    for (int i = tid; i < n_valid; i += kNmsThreads) {
+        const uint2 e = list[i];
+        const bool take = (n_valid <= a.pre_topk) || e.x > key_cut || (e.x == key_cut && e.y <= id_cut);
+        if (take) {
+            const Row r = fetch_row(a, b, e.y);
+            const int pos = atomicAdd(&s_n, 1);
+            const uint32_t cls_u = a.class_aware ? (uint32_t)(int)r.cls : 0u;
+            const uint32_t x0k = a.tie_break_x0 ? float_key(r.box.x) : 0u;
+            k_hi[pos] = ((unsigned long long)cls_u << 32) | (uint32_t)(~e.x);  // class asc, conf desc
+            k_lo[pos] = ((unsigned long long)x0k << 32) | e.y;                 // box[0] asc, id asc
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= S_eff; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < S_eff; i += kNmsThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long ah = k_hi[i], al = k_lo[i], bh = k_hi[ixj], bl = k_lo[ixj];
+                    const bool gt = ah > bh || (ah == bh && al > bl);
+                    const bool asc = (i & k) == 0;
+                    if (gt == asc) {
+                        k_hi[i] = bh;
+                        k_lo[i] = bl;
+                        k_hi[ixj] = ah;
+                        k_lo[ixj] = al;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- D: stage sorted rows ----------------
+    for (int i = tid; i < M; i += kNmsThreads) {
+        const uint32_t id = (uint32_t)(k_lo[i] & 0xffffffffull);
+        const Row r = fetch_row(a, b, id);
+        s_box[i] = r.box;
+        s_conf[i] = r.conf;
+        s_cls[i] = a.class_aware ? (int)r.cls : 0;
+        s_id[i] = id;
+    }
+    if (tid == 0) {
+        s_nkept = 0;
+        s_rem = 0;
+    }
+    __syncthreads();  // sort keys are dead from here on: s_kbox aliases them
+
+    const int R = 7 + a.extra_floats;
+    float* o = a.out + (size_t)b * (1 + (size_t)a.max_det * R);
+    int32_t* oidx = a.keep_index ? a.keep_index + (size_t)b * a.max_det : nullptr;
+    int n_rows_out = 0;
+
+    if (a.mode == TRTX_NMS_GREEDY) {
+        // ---------------- E: chunked greedy NMS ----------------
+        int n_kept = 0, ks = 0;
+        for (int c0 = 0; c0 < M; c0 += 32) {
+            const int nchunk = min(32, M - c0);
+            const int cls_first = s_cls[c0];
+            while (ks < n_kept && s_kcls[ks] < cls_first) ++ks;  // kept rows of lower classes are irrelevant
+            // (1) chunk members x kept rows of classes >= cls_first
+            const int P = 32 * (n_kept - ks);
+            for (int p = tid; p < P; p += kNmsThreads) {
+                const int i = p & 31, k = ks + (p >> 5);
+                if (i < nchunk && s_kcls[k] == s_cls[c0 + i]) {
+                    if (iou_any(a.box_format, s_kbox[k], s_box[c0 + i]) > a.nms_thresh) atomicOr(&s_rem, 1u << i);
+                }
+            }
+            // (2) chunk members x chunk-mates: warp w <-> member w, lane j <-> earlier mate j
+            {
+                const int i = warp, j = lane;
+                bool hit = false;
+                if (i < nchunk && j < i && s_cls[c0 + j] == s_cls[c0 + i])
+                    hit = iou_any(a.box_format, s_box[c0 + j], s_box[c0 + i]) > a.nms_thresh;
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_sup[i] = m;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const unsigned my = s_sup[lane];
+                unsigned alive = ~s_rem & (nchunk == 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned kill = __ballot_sync(0xffffffffu, (my >> j) & 1u);
+                    if ((alive >> j) & 1u) alive &= ~kill;
+                }
+                if ((alive >> lane) & 1u) {
+                    const int pos = n_kept + __popc(alive & ((1u << lane) - 1u));
+                    s_kbox[pos] = s_box[c0 + lane];
+                    s_kcls[pos] = s_cls[c0 + lane];
+                    s_kpos[pos] = c0 + lane;
+                }
+                if (lane == 0) {
+                    s_nkept = n_kept + __popc(alive);
+                    s_rem = 0;
+                }
+            }
+            __syncthreads();
+            n_kept = s_nkept;
+        }
+        // ---------------- F: kept rows, reference `res` order ----------------
+        n_rows_out = min(n_kept, a.max_det);
+        for (int k = tid; k < n_rows_out; k += kNmsThreads) {
+            const int pos = s_kpos[k];
+            const float4 bx = s_kbox[k];
+            float* row = o + 1 + (size_t)k * R;
+            row[0] = bx.x;
+            row[1] = bx.y;
+            row[2] = bx.z;
+            row[3] = bx.w;
+            row[4] = s_conf[pos];
+            row[5] = (float)s_cls[pos];
+            row[6] = 1.0f;
+            if (oidx) oidx[k] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[pos]) + 1].z)
+                                             : (int)s_id[pos];
+            if (a.extra_floats && !a.from_tiles) {
+                const float* src = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 +
+                                   (size_t)s_id[pos] * a.det_floats + a.extra_offset;
+                for (int e = 0; e < a.extra_floats; ++e) row[7 + e] = src[e];
+            }
+        }
+    } else {
+        // one-shot: dropped iff some earlier same-class row (higher conf) overlaps (postprocess.cu:89-111)
+        n_rows_out = min(M, a.max_det);
+        for (int i = tid; i < n_rows_out; i += kNmsThreads) {
+            const int ci = s_cls[i];
+            const float4 bi = s_box[i];
+            bool keep = true;
+            for (int j = i - 1; j >= 0 && s_cls[j] == ci; --j) {
+                if (iou_oneshot(bi, s_box[j]) > a.nms_thresh) {
+                    keep = false;
+                    break;
+                }
+            }
+            float* row = o + 1 + (size_t)i * R;
+            row[0] = bi.x;
+            row[1] = bi.y;
+            row[2] = bi.z;
+            row[3] = bi.w;
+            row[4] = s_conf[i];
+            row[5] = (float)ci;
+            row[6] = keep ? 1.0f : 0.0f;
+            if (oidx) oidx[i] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[i]) + 1].z)
+                                             : (int)s_id[i];
+            if (a.extra_floats && !a.from_tiles) {
+                const float* src = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 +
+                                   (size_t)s_id[i] * a.det_floats + a.extra_offset;
+                for (int e = 0; e < a.extra_floats; ++e) row[7 + e] = src[e];
+            }
+        }
+    }
+    if (tid == 0) o[0] = (float)n_rows_out;
+    // rows >= count are zero (the reference memsets its decode buffer, yolov8_det.cpp:106)
+    for (int i = n_rows_out * R + tid; i < a.max_det * R; i += kNmsThreads) o[1 + i] = 0.0f;
+    if (oidx)
+        for (int i = n_rows_out + tid; i < a.max_det; i += kNmsThreads) oidx[i] = -1;
+}
+
+static size_t nms_smem_bytes(int pre_topk) {
+    const size_t S = pre_topk <= 1024 ? 1024 : kMaxSort;
+    return S * (8 + 8 + 16 + 4 + 4 + 4 + 4 + 4);
+}
+
+static int nms_validate(const trtx_nms_params* q) {
+    if (!q) return TRTX_ERR_INVALID;
+    if (q->box_format < 0 || q->box_format > 2) return TRTX_ERR_INVALID;
+    if (q->mode != TRTX_NMS_GREEDY && q->mode != TRTX_NMS_ONESHOT) return TRTX_ERR_INVALID;
+    if (q->max_det <= 0 || q->extra_floats < 0 || q->extra_offset < 0) return TRTX_ERR_INVALID;
+    return TRTX_OK;
+}
+
+static int nms_launch(NmsArgs& a, int batch, cudaStream_t st) {
+    if (a.pre_topk > kMaxSort) return TRTX_ERR_UNSUPPORTED;
+    const size_t smem = nms_smem_bytes(a.pre_topk);
+    // per-device function attribute; cheap and idempotent, so set on every call (no global state)
+    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(kMaxSort));
+    nms_kernel<<<batch, kNmsThreads, smem, st>>>(a);
+    return check_launch();
+}
+
+}  // namespace trtx
+
+using namespace trtx;
+
+extern "C" {
+
+TRTX_API size_t trtx_nms_workspace_size(const trtx_nms_params* p, int batch, int max_rows) {
+    if (nms_validate(p) || batch <= 0 || max_rows <= 0) return 0;
+    return align_up(sizeof(uint2) * (size_t)batch * max_rows);
+}
+
+TRTX_API int trtx_nms_enqueue(const trtx_nms_params* p, int batch, const float* plugin_out_dev, int max_rows,
+                              int det_floats, float* compact_out_dev, int32_t* keep_index_dev, void* workspace_dev,
+                              size_t workspace_bytes, trtx_stream_t stream) {
+    int rc = nms_validate(p);
+    if (rc) return rc;
+    if (batch <= 0 || max_rows <= 0 || det_floats < 5 || !plugin_out_dev || !compact_out_dev || !workspace_dev)
+        return TRTX_ERR_INVALID;
+    if (p->extra_floats && p->extra_offset + p->extra_floats > det_floats) return TRTX_ERR_INVALID;
+    if (p->box_format != TRTX_BOX_RETINA && det_floats < 6) return TRTX_ERR_INVALID;
+    if (workspace_bytes < trtx_nms_workspace_size(p, batch, max_rows)) return TRTX_ERR_WORKSPACE;
+    NmsArgs a{};
+    a.rows = plugin_out_dev;
+    a.max_rows = max_rows;
+    a.det_floats = det_floats;
+    a.from_tiles = 0;
+    a.list = static_cast<uint2*>(workspace_dev);
+    a.list_stride = max_rows;
+    a.box_format = p->box_format;
+    a.mode = p->mode;
+    a.class_aware = p->class_aware && p->box_format != TRTX_BOX_RETINA;
+    a.tie_break_x0 = p->tie_break_x0;
+    a.conf_thresh = p->conf_thresh;
+    a.nms_thresh = p->nms_thresh;
+    a.pre_topk = max_rows < kMaxSort ? max_rows : kMaxSort;
+    a.max_det = p->max_det;
+    a.extra_floats = p->extra_floats;
+    a.extra_offset = p->extra_offset;
+    a.out = compact_out_dev;
+    a.keep_index = keep_index_dev;
+    return nms_launch(a, batch, static_cast<cudaStream_t>(stream));
+}
+
+// shared by the fused call and its split form
+static int yolo_nms_tiles(const trtx_yolo_params* p, const trtx_nms_params* q, int batch, const YoloArgs& ya,
+                          const YoloLayout& L, float* compact_out_dev, int32_t* keep_index_dev, void* workspace_dev,
+                          cudaStream_t st) {
+    NmsArgs a{};
+    a.from_tiles = 1;
+    a.tiles_per_image = L.tiles_per_image;
+    a.slots_per_image = L.slots_per_image;
+    a.tile_slots = L.tile_cells * L.apc;
+    a.num_levels = p->num_levels;
+    for (int l = 0; l < p->num_levels; ++l) {
+        a.lv_tile_begin[l] = L.level_tile_begin[l];
+        a.lv_slot_begin[l] = L.level_slot_begin[l];
+    }
+    a.tile_count = ya.tile_count;
+    a.cand = ya.cand;
+    a.list = reinterpret_cast<uint2*>(static_cast<char*>(workspace_dev) + L.off_list);
+    a.list_stride = L.slots_per_image;
+    a.box_format = q->box_format;
+    a.mode = q->mode;
+    a.class_aware = q->class_aware;
+    a.tie_break_x0 = q->tie_break_x0;
+    a.conf_thresh = q->conf_thresh;
+    a.nms_thresh = q->nms_thresh;
+    a.pre_topk = p->max_out;  // the reference's plugin capacity bounds what reaches nms()
+    a.max_det = q->max_det;
+    a.out = compact_out_dev;
+    a.keep_index = keep_index_dev;
+    return nms_launch(a, batch, st);
+}
+
+TRTX_API int trtx_yolo_decode_nms_enqueue(const trtx_yolo_params* p, const trtx_nms_params* q, int batch,
+                                          const void* const* inputs_dev, float* compact_out_dev,
+                                          int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
+                                          trtx_stream_t stream) {
+    int rc = nms_validate(q);
+    if (rc) return rc;
+    if (!compact_out_dev) return TRTX_ERR_INVALID;
+    if (q->extra_floats) return TRTX_ERR_UNSUPPORTED;  // extras need the plugin-format rows (use the two-stage path)
+    YoloArgs ya;
+    YoloLayout L;
+    rc = yolo_fill_args(p, batch, inputs_dev, workspace_dev, workspace_bytes, &ya, &L);
+    if (rc) return rc;
+    if (p->max_out > kMaxSort) return TRTX_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = yolo_scan_launch(ya, L, p->in_dtype, batch, st);
+    if (rc) return rc;
+    return yolo_nms_tiles(p, q, batch, ya, L, compact_out_dev, keep_index_dev, workspace_dev, st);
+}
+
+TRTX_API int trtx_yolo_scan_enqueue(const trtx_yolo_params* p, int batch, const void* const* inputs_dev,
+                                    void* workspace_dev, size_t workspace_bytes, trtx_stream_t stream) {
+    YoloArgs ya;
+    YoloLayout L;
+    int rc = yolo_fill_args(p, batch, inputs_dev, workspace_dev, workspace_bytes, &ya, &L);
+    if (rc) return rc;
+    return yolo_scan_launch(ya, L, p->in_dtype, batch, static_cast<cudaStream_t>(stream));
+}
+
+TRTX_API int trtx_yolo_nms_after_scan_enqueue(const trtx_yolo_params* p, const trtx_nms_params* q, int batch,
+                                              const void* const* inputs_dev, float* compact_out_dev,
+                                              int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
+                                              trtx_stream_t stream) {
+    int rc = nms_validate(q);
+    if (rc) return rc;
+    if (!compact_out_dev) return TRTX_ERR_INVALID;
+    if (q->extra_floats) return TRTX_ERR_UNSUPPORTED;
+    YoloArgs ya;
+    YoloLayout L;
+    rc = yolo_fill_args(p, batch, inputs_dev, workspace_dev, workspace_bytes, &ya, &L);
+    if (rc) return rc;
+    if (p->max_out > kMaxSort) return TRTX_ERR_UNSUPPORTED;
+    return yolo_nms_tiles(p, q, batch, ya, L, compact_out_dev, keep_index_dev, workspace_dev,
+                          static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// preprocess.cu -- batched letterbox warp-affine + BGR->RGB + /255 + HWC->CHW (+fp16) for sm_100a.
+// Replaces warpaffine_kernel / cuda_preprocess / cuda_batch_preprocess, yolov8/src/preprocess.cu:7-127
+// (identical bodies in yolov5/7/9/10/11/12/13/26), which launch once per image and synchronise the
+// stream after every image (:119-127).  Here: ONE launch for the whole batch, per-image descriptors
+// and affine matrices in the kernel parameter block (no H2D copy of metadata), each thread produces 4
+// horizontally adjacent destination pixels so that the three planar stores are 128-bit (fp32) or
+// 64-bit (fp16) and fully coalesced.
+//
+// Roofline: HBM-bound; algorithmic bytes per image = src_w*src_h*3 (u8 read once) +
+// 3*dst_w*dst_h*sizeof(out) (6 144 000 B for 640x640 -> 640x640 fp32).
+//
+// Arithmetic follows the reference kernel statement by statement (including its `+0.5f` source
+// offset without a matching `-0.5f`, preprocess.cu:22-23) using round-to-nearest intrinsics so the
+// result is independent of FMA contraction.
+#include "common.cuh"
+
+namespace trtx {
+
+constexpr int kMaxImagesPerLaunch = 128;
+
+struct PreImage {
+    const uint8_t* src;
+    int sw, sh, pitch;
+    float m[6];  // d2s
+};
+struct PreArgs {
+    PreImage img[kMaxImagesPerLaunch];
+    int dw, dh;
+};
+
+__device__ __forceinline__ void sample_px(const PreImage& im, int dx, int dy, float& c0, float& c1, float& c2) {
+    // preprocess.cu:20-23
+    const float src_x =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(im.m[0], (float)dx), __fmul_rn(im.m[1], (float)dy)), im.m[2]), 0.5f);
+    const float src_y =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(im.m[3], (float)dx), __fmul_rn(im.m[4], (float)dy)), im.m[5]), 0.5f);
+    const float cv = 128.0f;  // const_value_st (:115)
+    if (src_x <= -1 || src_x >= im.sw || src_y <= -1 || src_y >= im.sh) {
+        c0 = c1 = c2 = cv;
+        return;
+    }
+    const int y_low = (int)floorf(src_y), x_low = (int)floorf(src_x);
+    const int y_high = y_low + 1, x_high = x_low + 1;
+    const float ly = __fsub_rn(src_y, (float)y_low), lx = __fsub_rn(src_x, (float)x_low);
+    const float hy = __fsub_rn(1.0f, ly), hx = __fsub_rn(1.0f, lx);
+    const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+    float v1[3] = {cv, cv, cv}, v2[3] = {cv, cv, cv}, v3[3] = {cv, cv, cv}, v4[3] = {cv, cv, cv};
+    const bool xl = x_low >= 0, xh = x_high < im.sw;
+    if (y_low >= 0) {
+        const uint8_t* row = im.src + (size_t)y_low * im.pitch;
+        if (xl) {
+            v1[0] = __ldg(row + x_low * 3);
+            v1[1] = __ldg(row + x_low * 3 + 1);
+            v1[2] = __ldg(row + x_low * 3 + 2);
+        }
+        if (xh) {
+            v2[0] = __ldg(row + x_high * 3);
+            v2[1] = __ldg(row + x_high * 3 + 1);
+            v2[2] = __ldg(row + x_high * 3 + 2);
+        }
+    }
+    if (y_high < im.sh) {
+        const uint8_t* row = im.src + (size_t)y_high * im.pitch;
+        if (xl) {
+            v3[0] = __ldg(row + x_low * 3);
+            v3[1] = __ldg(row + x_low * 3 + 1);
+            v3[2] = __ldg(row + x_low * 3 + 2);
+        }
+        if (xh) {
+            v4[0] = __ldg(row + x_high * 3);
+            v4[1] = __ldg(row + x_high * 3 + 1);
+            v4[2] = __ldg(row + x_high * 3 + 2);
+        }
+    }
+    // :59-61, left-to-right sums
+    c0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1[0]), __fmul_rn(w2, v2[0])), __fmul_rn(w3, v3[0])), __fmul_rn(w4, v4[0]));
+    c1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1[1]), __fmul_rn(w2, v2[1])), __fmul_rn(w3, v3[1])), __fmul_rn(w4, v4[1]));
+    c2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1[2]), __fmul_rn(w2, v2[2])), __fmul_rn(w3, v3[2])), __fmul_rn(w4, v4[2]));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
+                                                        int first_image) {
+    const int b = blockIdx.z;
+    const PreImage& im = a.img[b];
+    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (dy >= a.dh || dx0 >= a.dw) return;
+    const size_t area = (size_t)a.dw * a.dh;
+    OutT* base = dst + (size_t)(first_image + b) * 3 * area + (size_t)dy * a.dw + dx0;
+    float r[4], g[4], bl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float c0 = 0, c1 = 0, c2 = 0;
+        if (dx0 + i < a.dw) sample_px(im, dx0 + i, dy, c0, c1, c2);
+        // bgr -> rgb, /255 (:64-74)
+        r[i] = __fdiv_rn(c2, 255.0f);
+        g[i] = __fdiv_rn(c1, 255.0f);
+        bl[i] = __fdiv_rn(c0, 255.0f);
+    }
+    const bool vec_ok = (dx0 + 3 < a.dw) && (a.dw % 4 == 0);
+    if constexpr (sizeof(OutT) == 4) {
+        if (vec_ok) {
+            *reinterpret_cast<float4*>(base) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(base + area) = make_float4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<float4*>(base + 2 * area) = make_float4(bl[0], bl[1], bl[2], bl[3]);
+        } else {
+            for (int i = 0; i < 4 && dx0 + i < a.dw; ++i) {
+                base[i] = r[i];
+                base[area + i] = g[i];
+                base[2 * area + i] = bl[i];
+            }
+        }
+    } else {
+        if (vec_ok && (area % 4 == 0)) {
+            __half2 r01 = __floats2half2_rn(r[0], r[1]), r23 = __floats2half2_rn(r[2], r[3]);
+            __half2 g01 = __floats2half2_rn(g[0], g[1]), g23 = __floats2half2_rn(g[2], g[3]);
+            __half2 b01 = __floats2half2_rn(bl[0], bl[1]), b23 = __floats2half2_rn(bl[2], bl[3]);
+            uint2 pr = make_uint2(*reinterpret_cast<uint32_t*>(&r01), *reinterpret_cast<uint32_t*>(&r23));
+            uint2 pg = make_uint2(*reinterpret_cast<uint32_t*>(&g01), *reinterpret_cast<uint32_t*>(&g23));
+            uint2 pb = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
+            *reinterpret_cast<uint2*>(base) = pr;
+            *reinterpret_cast<uint2*>(base + area) = pg;
+            *reinterpret_cast<uint2*>(base + 2 * area) = pb;
+        } else {
+            for (int i = 0; i < 4 && dx0 + i < a.dw; ++i) {
+                base[i] = __float2half_rn(r[i]);
+                base[area + i] = __float2half_rn(g[i]);
+                base[2 * area + i] = __float2half_rn(bl[i]);
+            }
+        }
+    }
+}
+
+}  // namespace trtx
+
+using namespace trtx;
+
+extern "C" {
+
+// preprocess.cu:98-110 + cv::invertAffineTransform (CV_32F branch: float products, double inverse)
+TRTX_API void trtx_letterbox_matrix(int sw, int sh, int dw, int dh, float d2s[6]) {
+    float a = dh / (float)sh, b = dw / (float)sw;
+    float scale = a < b ? a : b;  // std::min
+    float s2d[6];
+    s2d[0] = scale;
+    s2d[1] = 0;
+    s2d[2] = (float)(-scale * sw * 0.5 + dw * 0.5);
+    s2d[3] = 0;
+    s2d[4] = scale;
+    s2d[5] = (float)(-scale * sh * 0.5 + dh * 0.5);
+    double D = s2d[0] * s2d[4] - s2d[1] * s2d[3];
+    D = D != 0 ? 1. / D : 0;
+    double A11 = s2d[4] * D, A22 = s2d[0] * D, A12 = -s2d[1] * D, A21 = -s2d[3] * D;
+    double b1 = -A11 * s2d[2] - A12 * s2d[5];
+    double b2 = -A21 * s2d[2] - A22 * s2d[5];
+    d2s[0] = (float)A11;
+    d2s[1] = (float)A12;
+    d2s[2] = (float)b1;
+    d2s[3] = (float)A21;
+    d2s[4] = (float)A22;
+    d2s[5] = (float)b2;
+}
+
+TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, int batch, void* dst_dev, int dst_w,
+                                           int dst_h, int out_dtype, trtx_stream_t stream) {
+    if (!images_host || batch <= 0 || !dst_dev || dst_w <= 0 || dst_h <= 0) return TRTX_ERR_INVALID;
+    if (out_dtype != TRTX_F32 && out_dtype != TRTX_F16) return TRTX_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int first = 0; first < batch; first += kMaxImagesPerLaunch) {
+        const int n = batch - first < kMaxImagesPerLaunch ? batch - first : kMaxImagesPerLaunch;
+        PreArgs a;
+        a.dw = dst_w;
+        a.dh = dst_h;
+        for (int i = 0; i < n; ++i) {
+            const trtx_image_desc& d = images_host[first + i];
+            if (!d.data_dev || d.width <= 0 || d.height <= 0 || d.pitch < 3 * d.width) return TRTX_ERR_INVALID;
+            a.img[i].src = d.data_dev;
+            a.img[i].sw = d.width;
+            a.img[i].sh = d.height;
+            a.img[i].pitch = d.pitch;
+            trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, a.img[i].m);
+        }
+        dim3 block(64, 4, 1);
+        dim3 grid((dst_w + 4 * 64 - 1) / (4 * 64), (dst_h + 3) / 4, n);
+        if (out_dtype == TRTX_F32)
+            letterbox_kernel<float><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
+        else
+            letterbox_kernel<__half><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
+        int rc = check_launch();
+        if (rc) return rc;
+    }
+    return TRTX_OK;
+}
+
+}  // extern "C"

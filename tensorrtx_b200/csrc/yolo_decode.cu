@@ -1,0 +1,701 @@
+// yolo_decode.cu -- YoloLayer_TRT hot path for sm_100a.
+//
+// Replaces CalDetection/forwardGpu of yolov8/plugin/yololayer.cu:178-316 (anchor-free) and
+// yolov5/plugin/yololayer.cu:161-227 (anchor-based) with
+//   (1) ONE streaming "scan" launch over all strides and images: 128-bit coalesced loads along the
+//       anchor axis, class range sliced across the warps of a CTA, sigmoid evaluated only on
+//       running-max logits above the gate logit (bit-identical result, see scan_classes), warp
+//       ballot/scan compaction into a per-tile slot range (no atomics, deterministic order);
+//   (2) a tiny "pack" launch that turns the per-tile candidates into the reference's plugin
+//       buffer [count, Detection rows] (only used by the drop-in plugin ABI; the fused NMS
+//       kernel in nms.cu consumes the tiles directly).
+//
+// Roofline: HBM-bound.  Algorithmic bytes per image = sum_l C*g_l*sizeof(in)  (SURVEY 8d).
+#include <math.h>
+
+#include "yolo_layout.cuh"
+
+namespace trtx {
+
+thread_local int g_last_cuda_error = 0;
+
+// tuning knobs (set through trtx_tune_set; defaults chosen from the B200 sweep in profiles/)
+static int g_slices = 4;
+static int g_unroll = 10;
+
+// --------------------------------------------------------------------------------------------
+// scan_classes: running (max sigmoid, first argmax) over `nrows` channel rows for VEC adjacent
+// anchors, bit-identical to the reference loop
+//     for i: p = Logist(x_i); if (p > max) { max = p; cls = i; }          (yololayer.cu:195-201)
+// for every anchor whose final max is >= gate.  Proof sketch: sigmoid is
+// monotone non-decreasing in fp32, so the first class attaining the maximum probability has a
+// logit strictly greater than every earlier logit and (if the max passes the gate) than x_lo;
+// hence it is always taken by the `x > bx` test and wins the strict `p > bp` comparison.
+// Background logits never reach the slow path, so the hot loop is 1 compare per element.
+// --------------------------------------------------------------------------------------------
+template <int VEC>
+struct Best {
+    float bx[VEC];
+    float bp[VEC];
+    int bc[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ void update_one(Best<VEC>& s, int j, float x, int cls) {
+    if (x > s.bx[j]) {
+        s.bx[j] = x;
+        float p = logist(x);
+        if (p > s.bp[j]) {
+            s.bp[j] = p;
+            s.bc[j] = cls;
+        }
+    }
+}
+
+template <typename T, int VEC, int U>
+__device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t g, int nrows, int cls0, Best<VEC>& s) {
+    const T* p = row0;
+#pragma unroll 1
+    for (int r = 0; r < nrows; r += U) {
+        if constexpr (VEC == 4) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u < nrows)
+                    v[u] = Elem<T>::ld4(p + (size_t)u * g);
+                else
+                    v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bool any = (v[u].x > s.bx[0]) | (v[u].y > s.bx[1]) | (v[u].z > s.bx[2]) | (v[u].w > s.bx[3]);
+                if (any) {
+                    int c = cls0 + r + u;
+                    update_one<VEC>(s, 0, v[u].x, c);
+                    update_one<VEC>(s, 1, v[u].y, c);
+                    update_one<VEC>(s, 2, v[u].z, c);
+                    update_one<VEC>(s, 3, v[u].w, c);
+                }
+            }
+        } else {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = (r + u < nrows) ? Elem<T>::ld1(p + (size_t)u * g) : -INFINITY;
+#pragma unroll
+            for (int u = 0; u < U; ++u) update_one<VEC>(s, 0, v[u], cls0 + r + u);
+        }
+        p += (size_t)U * g;
+    }
+}
+
+__device__ __forceinline__ void store_record(float4* cand, size_t slot, float b0, float b1, float b2, float b3,
+                                             float conf, int cls, int anchor_id) {
+    cand[2 * slot] = make_float4(b0, b1, b2, b3);
+    cand[2 * slot + 1] = make_float4(conf, (float)cls, __int_as_float(anchor_id), 0.0f);
+}
+
+// --------------------------------------------------------------------------------------------
+// Anchor-free scan (yolov8 family).  grid = B * tiles_per_image CTAs of SLICES warps.
+// --------------------------------------------------------------------------------------------
+template <typename T, int VEC, int SLICES, int U>
+__global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_constant__ YoloArgs a) {
+    constexpr int TILE = 32 * VEC;
+    __shared__ float s_p[SLICES > 1 ? SLICES - 1 : 1][TILE];
+    __shared__ int s_c[SLICES > 1 ? SLICES - 1 : 1][TILE];
+
+    const int b = blockIdx.x / a.tiles_per_image;
+    const int t = blockIdx.x - b * a.tiles_per_image;
+    int l = 0;
+    while (l + 1 < a.num_levels && t >= a.lv[l + 1].tile_begin) ++l;
+    const LevelArg& L = a.lv[l];
+    const int tile = t - L.tile_begin;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int a0 = tile * TILE + lane * VEC;  // first cell handled by this lane
+    const size_t g = (size_t)L.g;
+    const bool active = a0 < L.g;  // vector path: g % 4 == 0, so a0 < g implies the whole quad is in range
+    const T* base = reinterpret_cast<const T*>(L.in) + (size_t)b * a.C * g;
+
+    Best<VEC> s;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        s.bx[j] = a.x_lo;
+        s.bp[j] = 0.0f;
+        s.bc[j] = 0;
+    }
+    const int per = (a.nc + SLICES - 1) / SLICES;
+    const int c0 = warp * per;
+    const int c1 = min(a.nc, c0 + per);
+    if (active && c1 > c0) scan_classes<T, VEC, U>(base + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
+
+    if constexpr (SLICES > 1) {
+        bool mine = false;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) mine |= !(s.bp[j] < a.gate);
+        if (warp > 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                s_p[warp - 1][lane * VEC + j] = s.bp[j];
+                s_c[warp - 1][lane * VEC + j] = s.bc[j];
+            }
+        }
+        int any = __syncthreads_or(mine ? 1 : 0);
+        if (!any) {
+            if (threadIdx.x == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = 0;
+            return;
+        }
+        if (warp > 0) return;
+        // combine in ascending class-slice order: strict > keeps the FIRST class with the max prob
+#pragma unroll
+        for (int w = 1; w < SLICES; ++w) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float p2 = s_p[w - 1][lane * VEC + j];
+                if (p2 > s.bp[j]) {
+                    s.bp[j] = p2;
+                    s.bc[j] = s_c[w - 1][lane * VEC + j];
+                }
+            }
+        }
+    }
+
+    // gate (yololayer.cu:203: `if (max_cls_prob < 0.1) return;`) + warp-scan compaction
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+        if (active && (a0 + j < L.g) && !(s.bp[j] < a.gate)) flags |= 1u << j;
+    int total;
+    int off = warp_excl_scan(__popc(flags), lane, &total);
+    if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
+    if (flags) {
+        float d[4][VEC];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if constexpr (VEC == 4) {
+                float4 v = Elem<T>::ld4(base + (size_t)k * g + a0);
+                d[k][0] = v.x;
+                d[k][1] = v.y;
+                d[k][2] = v.z;
+                d[k][3] = v.w;
+            } else {
+                d[k][0] = Elem<T>::ld1(base + (size_t)k * g + a0);
+            }
+        }
+        const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE;
+        const float fs = (float)L.stride;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            if (flags & (1u << j)) {
+                const int e = a0 + j;
+                const int row = e / L.gw, col = e - row * L.gw;
+                // yololayer.cu:217-220
+                float x1 = ((float)col + 0.5f - d[0][j]) * fs;
+                float y1 = ((float)row + 0.5f - d[1][j]) * fs;
+                float x2 = ((float)col + 0.5f + d[2][j]) * fs;
+                float y2 = ((float)row + 0.5f + d[3][j]) * fs;
+                store_record(a.cand, slot0 + off, x1, y1, x2, y2, s.bp[j], s.bc[j], L.slot_begin + e);
+                ++off;
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Anchor-based scan (yolov5 family).  CTA = 4 warps over a tile of 32*VEC cells x 3 anchors.
+// Objectness rows are read first; the class rows of anchor k are only streamed when some cell of
+// the tile passes the objectness gate for k (the reference skips its class loop per thread,
+// yololayer.cu:176-177; here the skip is per tile so that the loads stay coalesced).
+// --------------------------------------------------------------------------------------------
+template <typename T, int VEC, int U>
+__global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant__ YoloArgs a) {
+    constexpr int TILE = 32 * VEC;
+    constexpr int SLICES = 4;
+    __shared__ float s_obj[3][TILE];            // objectness prob (0 if not passing)
+    __shared__ float s_p[SLICES - 1][TILE];     // partial class max of slices 1..3
+    __shared__ int s_c[SLICES - 1][TILE];
+    __shared__ float s_fp[3][TILE];             // final class prob per (k, cell)
+    __shared__ int s_fc[3][TILE];
+    __shared__ int s_anyk[3];
+
+    const int b = blockIdx.x / a.tiles_per_image;
+    const int t = blockIdx.x - b * a.tiles_per_image;
+    int l = 0;
+    while (l + 1 < a.num_levels && t >= a.lv[l + 1].tile_begin) ++l;
+    const LevelArg& L = a.lv[l];
+    const int tile = t - L.tile_begin;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int a0 = tile * TILE + lane * VEC;
+    const size_t g = (size_t)L.g;
+    const bool active = a0 < L.g;
+    const int ilen = a.info_len;
+    const T* base = reinterpret_cast<const T*>(L.in) + (size_t)b * a.C * g;
+
+    if (threadIdx.x < 3) s_anyk[threadIdx.x] = 0;
+    __syncthreads();
+    // ---- objectness: warp k reads row k*ilen+4 ----
+    if (warp < 3) {
+        float x[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) x[j] = -INFINITY;
+        if (active) {
+            const T* p = base + ((size_t)warp * ilen + 4) * g + a0;
+            if constexpr (VEC == 4) {
+                float4 v = Elem<T>::ld4(p);
+                x[0] = v.x;
+                x[1] = v.y;
+                x[2] = v.z;
+                x[3] = v.w;
+            } else {
+                x[0] = Elem<T>::ld1(p);
+            }
+        }
+        bool anyp = false;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float pr = 0.0f;
+            bool pass = false;
+            if (active && (a0 + j < L.g) && x[j] > a.x_lo) {
+                pr = logist(x[j]);
+                pass = !(pr < a.gate);  // yololayer.cu:177 `if (box_prob < kIgnoreThresh) continue;`
+            }
+            s_obj[warp][lane * VEC + j] = pass ? pr : -1.0f;
+            anyp |= pass;
+        }
+        if (__any_sync(0xffffffffu, anyp) && lane == 0) s_anyk[warp] = 1;
+    }
+    __syncthreads();
+    const int anyk0 = s_anyk[0], anyk1 = s_anyk[1], anyk2 = s_anyk[2];
+    if (!(anyk0 | anyk1 | anyk2)) {
+        if (threadIdx.x == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = 0;
+        return;
+    }
+    // ---- class scan for each anchor k that has a passing cell in this tile ----
+    const int per = (a.nc + SLICES - 1) / SLICES;
+    const int c0 = warp * per;
+    const int c1 = min(a.nc, c0 + per);
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        const int anyk = k == 0 ? anyk0 : (k == 1 ? anyk1 : anyk2);
+        if (!anyk) continue;
+        Best<VEC> s;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            // non-passing anchors never take the slow path; passing ones see every running max
+            s.bx[j] = (s_obj[k][lane * VEC + j] >= 0.0f) ? -INFINITY : INFINITY;
+            s.bp[j] = 0.0f;
+            s.bc[j] = 0;
+        }
+        if (active && c1 > c0)
+            scan_classes<T, VEC, U>(base + ((size_t)k * ilen + 5 + c0) * g + a0, g, c1 - c0, c0, s);
+        if (warp > 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                s_p[warp - 1][lane * VEC + j] = s.bp[j];
+                s_c[warp - 1][lane * VEC + j] = s.bc[j];
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int w = 1; w < SLICES; ++w) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    float p2 = s_p[w - 1][lane * VEC + j];
+                    if (p2 > s.bp[j]) {
+                        s.bp[j] = p2;
+                        s.bc[j] = s_c[w - 1][lane * VEC + j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                s_fp[k][lane * VEC + j] = s.bp[j];
+                s_fc[k][lane * VEC + j] = s.bc[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (warp > 0) return;
+    // ---- compaction in ascending (cell, k) order + box decode (yololayer.cu:188-208) ----
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (s_obj[k][lane * VEC + j] >= 0.0f) flags |= 1u << (j * 3 + k);
+    int total;
+    int off = warp_excl_scan(__popc(flags), lane, &total);
+    if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
+    if (flags) {
+        const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE * 3;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (flags & (1u << (j * 3 + k))) {
+                    const int e = a0 + j;
+                    const int row = e / L.gw, col = e - row * L.gw;
+                    const T* ck = base + (size_t)k * ilen * g + e;
+                    float t0 = logist(Elem<T>::ld1_cached(ck));
+                    float t1 = logist(Elem<T>::ld1_cached(ck + g));
+                    float t2 = logist(Elem<T>::ld1_cached(ck + 2 * g));
+                    float t3 = logist(Elem<T>::ld1_cached(ck + 3 * g));
+                    // yololayer.cu:196-203 (left-to-right: (..)*netw/yoloWidth)
+                    float cx = ((float)col - 0.5f + 2.0f * t0) * (float)a.net_w / (float)L.gw;
+                    float cy = ((float)row - 0.5f + 2.0f * t1) * (float)a.net_h / (float)L.gh;
+                    float w = 2.0f * t2;
+                    w = w * w * L.anc[2 * k];
+                    float h = 2.0f * t3;
+                    h = h * h * L.anc[2 * k + 1];
+                    float conf = s_obj[k][lane * VEC + j] * s_fp[k][lane * VEC + j];
+                    store_record(a.cand, slot0 + off, cx, cy, w, h, conf, s_fc[k][lane * VEC + j],
+                                 L.slot_begin + e * 3 + k);
+                    ++off;
+                }
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// pack: per-tile candidates -> reference plugin buffer [count, Detection rows] (one CTA per image).
+// Extras (seg coefficients, pose keypoints, obb) are gathered from the inputs per candidate,
+// exactly the reference's per-candidate work (yololayer.cu:222-279, yolov5 :206-208).
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void write_extras_v8(const YoloArgs& a, int b, int anchor_id, float* det) {
+    int l = 0;
+    while (l + 1 < a.num_levels && anchor_id >= a.lv[l + 1].slot_begin) ++l;
+    const LevelArg& L = a.lv[l];
+    const int e = anchor_id - L.slot_begin;
+    const size_t g = (size_t)L.g;
+    const T* cur = reinterpret_cast<const T*>(L.in) + (size_t)b * a.C * g + e;
+    const int row = e / L.gw, col = e - row * L.gw;
+    const int nc = a.nc, nk = a.num_kpts;
+    if (a.is_seg) {
+        for (int k = 0; k < 32; ++k)
+            det[6 + k] = Elem<T>::ld1_cached(cur + (size_t)(4 + nc + (a.is_pose ? nk * 3 : 0) + (a.is_obb ? 1 : 0) + k) * g);
+    }
+    if (a.is_pose) {
+        float* kp = det + 6 + 32;
+        for (int k = 0; k < nk; ++k) {
+            const size_t base = (size_t)(4 + nc + (a.is_seg ? 32 : 0) + (a.is_obb ? 1 : 0) + k * 3);
+            float kc = logist(Elem<T>::ld1_cached(cur + (base + 2) * g));
+            // `* 2.0` is a double literal in the reference (yololayer.cu:238-239)
+            float kx = (float)(((double)Elem<T>::ld1_cached(cur + base * g) * 2.0 + col) * L.stride);
+            float ky = (float)(((double)Elem<T>::ld1_cached(cur + (base + 1) * g) * 2.0 + row) * L.stride);
+            bool inside = kx >= det[0] && kx <= det[2] && ky >= det[1] && ky <= det[3];
+            if (kc < a.kpt_thresh || !inside) {
+                kp[k * 3] = -1;
+                kp[k * 3 + 1] = -1;
+                kp[k * 3 + 2] = -1;
+            } else {
+                kp[k * 3] = kx;
+                kp[k * 3 + 1] = ky;
+                kp[k * 3 + 2] = kc;
+            }
+        }
+    }
+    if (a.is_obb) {
+        const double pi = 3.14159265358979323846;
+        float d0 = Elem<T>::ld1_cached(cur), d1 = Elem<T>::ld1_cached(cur + g);
+        float d2 = Elem<T>::ld1_cached(cur + 2 * g), d3 = Elem<T>::ld1_cached(cur + 3 * g);
+        float ain = Elem<T>::ld1_cached(cur + (size_t)(4 + nc + (a.is_seg ? 32 : 0) + (a.is_pose ? nk * 3 : 0)) * g);
+        double angle = (double)(logist(ain) - 0.25f) * pi;
+        double cos1 = cos(angle), sin1 = sin(angle);
+        float xf = (d2 - d0) / 2;
+        float yf = (d3 - d1) / 2;
+        double x = xf * cos1 - yf * sin1;
+        double y = xf * sin1 + yf * cos1;
+        det[0] = (float)(((double)((float)col + 0.5f) + x) * L.stride);
+        det[1] = (float)(((double)((float)row + 0.5f) + y) * L.stride);
+        det[2] = (d0 + d2) * L.stride;
+        det[3] = (d1 + d3) * L.stride;
+        det[a.det_floats - 1] = (float)angle;
+    }
+}
+
+template <typename T>
+__device__ void write_extras_v5(const YoloArgs& a, int b, int anchor_id, float* det) {
+    if (!a.is_seg) return;
+    int l = 0;
+    while (l + 1 < a.num_levels && anchor_id >= a.lv[l + 1].slot_begin) ++l;
+    const LevelArg& L = a.lv[l];
+    const int local = anchor_id - L.slot_begin;
+    const int e = local / 3, k = local - e * 3;
+    const size_t g = (size_t)L.g;
+    const T* ck = reinterpret_cast<const T*>(L.in) + (size_t)b * a.C * g + (size_t)k * a.info_len * g + e;
+    for (int i = 0; i < 32; ++i) det[6 + i] = Elem<T>::ld1_cached(ck + (size_t)(i + 5 + a.nc) * g);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) yolo_pack_rows_kernel(const __grid_constant__ YoloArgs a, float* __restrict__ out) {
+    extern __shared__ int s_prefix[];  // tiles_per_image + 1
+    const int b = blockIdx.x;
+    const int T_ = a.tiles_per_image;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int* cnt = a.tile_count + (size_t)b * T_;
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < T_; base += 32) {
+            int v = (base + lane < T_) ? cnt[base + lane] : 0;
+            int tot;
+            int ex = warp_excl_scan(v, lane, &tot);
+            if (base + lane < T_) s_prefix[base + lane] = carry + ex;
+            carry += tot;
+        }
+        if (lane == 0) s_prefix[T_] = carry;
+    }
+    __syncthreads();
+    const int total = s_prefix[T_];
+    const int out_elem = 1 + a.max_out * a.det_floats;
+    float* o = out + (size_t)b * out_elem;
+    if (threadIdx.x == 0) o[0] = (float)min(total, a.max_out);  // clamped (see trtx_hot.h)
+    const int tile_slots = a.tile_cells * a.apc;
+    for (int t = warp; t < T_; t += nwarps) {
+        const int n = s_prefix[t + 1] - s_prefix[t];
+        if (n == 0) continue;
+        int l = 0;
+        while (l + 1 < a.num_levels && t >= a.lv[l + 1].tile_begin) ++l;
+        const size_t slot0 =
+                (size_t)b * a.slots_per_image + a.lv[l].slot_begin + (size_t)(t - a.lv[l].tile_begin) * tile_slots;
+        for (int j = lane; j < n; j += 32) {
+            const int rank = s_prefix[t] + j;
+            if (rank >= a.max_out) continue;  // yololayer.cu:207
+            float4 r0 = a.cand[2 * (slot0 + j)];
+            float4 r1 = a.cand[2 * (slot0 + j) + 1];
+            float* det = o + 1 + (size_t)rank * a.det_floats;
+            det[0] = r0.x;
+            det[1] = r0.y;
+            det[2] = r0.z;
+            det[3] = r0.w;
+            det[4] = r1.x;
+            det[5] = r1.y;
+            const int anchor_id = __float_as_int(r1.z);
+            if (a.variant == TRTX_YOLO_V8) {
+                if (a.is_seg | a.is_pose | a.is_obb) write_extras_v8<T>(a, b, anchor_id, det);
+            } else {
+                write_extras_v5<T>(a, b, anchor_id, det);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+int yolo_pick_vec(const trtx_yolo_params* p, const void* const* inputs_dev) {
+    const size_t need = (p->in_dtype == TRTX_F16) ? 8 : 16;
+    for (int l = 0; l < p->num_levels; ++l) {
+        int g = p->grid_h[l] * p->grid_w[l];
+        if (g % 4 != 0) return 1;
+        if (inputs_dev && (reinterpret_cast<uintptr_t>(inputs_dev[l]) % need) != 0) return 1;
+    }
+    return 4;
+}
+
+static int validate(const trtx_yolo_params* p, int batch) {
+    if (!p || batch <= 0) return TRTX_ERR_INVALID;
+    if (p->variant != TRTX_YOLO_V8 && p->variant != TRTX_YOLO_V5) return TRTX_ERR_INVALID;
+    if (p->num_levels <= 0 || p->num_levels > TRTX_MAX_LEVELS) return TRTX_ERR_INVALID;
+    if (p->num_classes <= 0 || p->max_out <= 0 || p->det_floats < 6) return TRTX_ERR_INVALID;
+    if (p->in_dtype != TRTX_F32 && p->in_dtype != TRTX_F16) return TRTX_ERR_INVALID;
+    for (int l = 0; l < p->num_levels; ++l)
+        if (p->grid_h[l] <= 0 || p->grid_w[l] <= 0) return TRTX_ERR_INVALID;
+    if (p->variant == TRTX_YOLO_V8) {
+        int need = 6 + (p->is_seg || p->is_pose || p->is_obb ? 32 : 0);
+        if (p->is_pose) need = 6 + 32 + p->num_kpts * 3;
+        if (p->is_obb) need = (need > 7 ? need : 7);
+        if (p->det_floats < need) return TRTX_ERR_INVALID;
+        if (p->is_pose && p->num_kpts <= 0) return TRTX_ERR_INVALID;
+    } else {
+        if (p->is_seg && p->det_floats < 38) return TRTX_ERR_INVALID;
+        if (p->is_pose || p->is_obb) return TRTX_ERR_UNSUPPORTED;
+    }
+    return TRTX_OK;
+}
+
+int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inputs_dev, void* workspace_dev,
+                   size_t workspace_bytes, YoloArgs* a, YoloLayout* Lo) {
+    int rc = validate(p, batch);
+    if (rc) return rc;
+    if (!inputs_dev || !workspace_dev) return TRTX_ERR_INVALID;
+    for (int l = 0; l < p->num_levels; ++l)
+        if (!inputs_dev[l]) return TRTX_ERR_INVALID;
+    const int vec = yolo_pick_vec(p, inputs_dev);
+    YoloLayout L = yolo_layout(p, batch, vec);
+    if (workspace_bytes < L.total_bytes) return TRTX_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0) return TRTX_ERR_INVALID;
+    memset(a, 0, sizeof(*a));
+    for (int l = 0; l < p->num_levels; ++l) {
+        LevelArg& v = a->lv[l];
+        v.in = inputs_dev[l];
+        v.gh = p->grid_h[l];
+        v.gw = p->grid_w[l];
+        v.g = v.gh * v.gw;
+        v.stride = p->strides[l];
+        v.tile_begin = L.level_tile_begin[l];
+        v.slot_begin = L.level_slot_begin[l];
+        for (int i = 0; i < 6; ++i) v.anc[i] = p->anchors[l][i];
+    }
+    a->num_levels = p->num_levels;
+    a->variant = p->variant;
+    a->tiles_per_image = L.tiles_per_image;
+    a->slots_per_image = L.slots_per_image;
+    a->tile_cells = L.tile_cells;
+    a->apc = L.apc;
+    a->nc = p->num_classes;
+    if (p->variant == TRTX_YOLO_V8) {
+        // yololayer.cu:186
+        a->info_len = 4 + p->num_classes + (p->is_seg ? 32 : 0) + (p->is_pose ? p->num_kpts * 3 : 0) + (p->is_obb ? 1 : 0);
+        a->C = a->info_len;
+    } else {
+        a->info_len = 5 + p->num_classes + (p->is_seg ? 32 : 0);  // yolov5 yololayer.cu:170-171
+        a->C = 3 * a->info_len;
+    }
+    a->net_w = p->net_w;
+    a->net_h = p->net_h;
+    a->max_out = p->max_out;
+    a->det_floats = p->det_floats;
+    a->is_seg = p->is_seg;
+    a->is_pose = p->is_pose;
+    a->is_obb = p->is_obb;
+    a->num_kpts = p->num_kpts;
+    a->kpt_thresh = p->kpt_thresh;
+    a->gate = p->gate;
+    // logit below which sigmoid(x) < gate for certain (0.05 logit units of slack >> any rounding)
+    if (p->gate <= 0.0f)
+        a->x_lo = -INFINITY;
+    else if (p->gate >= 1.0f)
+        a->x_lo = 10.0f;
+    else
+        a->x_lo = logf(p->gate / (1.0f - p->gate)) - 0.05f;
+    a->tile_count = reinterpret_cast<int*>(static_cast<char*>(workspace_dev) + L.off_tile_count);
+    a->cand = reinterpret_cast<float4*>(static_cast<char*>(workspace_dev) + L.off_cand);
+    *Lo = L;
+    return TRTX_OK;
+}
+
+template <typename T, int VEC>
+static void launch_v8(const YoloArgs& a, int grid, cudaStream_t st) {
+#define TRTX_V8_CASE(S, UU)                                                        \
+    if (g_slices == S && g_unroll == UU) {                                         \
+        yolo_v8_scan_kernel<T, VEC, S, UU><<<grid, 32 * S, 0, st>>>(a);            \
+        return;                                                                    \
+    }
+    TRTX_V8_CASE(1, 8)
+    TRTX_V8_CASE(1, 16)
+    TRTX_V8_CASE(2, 10)
+    TRTX_V8_CASE(2, 20)
+    TRTX_V8_CASE(4, 5)
+    TRTX_V8_CASE(4, 10)
+    TRTX_V8_CASE(4, 20)
+    TRTX_V8_CASE(8, 5)
+    TRTX_V8_CASE(8, 10)
+#undef TRTX_V8_CASE
+    yolo_v8_scan_kernel<T, VEC, 4, 10><<<grid, 128, 0, st>>>(a);
+}
+
+int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
+    const int grid = batch * L.tiles_per_image;
+    if (a.variant == TRTX_YOLO_V8) {
+        if (in_dtype == TRTX_F32) {
+            if (L.vec == 4)
+                launch_v8<float, 4>(a, grid, st);
+            else
+                launch_v8<float, 1>(a, grid, st);
+        } else {
+            if (L.vec == 4)
+                launch_v8<__half, 4>(a, grid, st);
+            else
+                launch_v8<__half, 1>(a, grid, st);
+        }
+    } else {
+        if (in_dtype == TRTX_F32) {
+            if (L.vec == 4)
+                yolo_v5_scan_kernel<float, 4, 10><<<grid, 128, 0, st>>>(a);
+            else
+                yolo_v5_scan_kernel<float, 1, 10><<<grid, 128, 0, st>>>(a);
+        } else {
+            if (L.vec == 4)
+                yolo_v5_scan_kernel<__half, 4, 10><<<grid, 128, 0, st>>>(a);
+            else
+                yolo_v5_scan_kernel<__half, 1, 10><<<grid, 128, 0, st>>>(a);
+        }
+    }
+    return check_launch();
+}
+
+}  // namespace trtx
+
+using namespace trtx;
+
+extern "C" {
+
+TRTX_API const char* trtx_version(void) { return "trtx_hot 0.1 (sm_100a)"; }
+TRTX_API int trtx_last_cuda_error(void) { return g_last_cuda_error; }
+
+// tuning knob for the bench sweep (not part of the drop-in ABI): key 0 = class slices, 1 = unroll
+TRTX_API int trtx_tune_set(int key, int value) {
+    if (key == 0) g_slices = value;
+    else if (key == 1) g_unroll = value;
+    else return TRTX_ERR_INVALID;
+    return TRTX_OK;
+}
+
+TRTX_API int trtx_yolo_params_init_v8(trtx_yolo_params* p, int num_classes, int net_w, int net_h, int max_out,
+                                      const int* strides, int num_levels) {
+    if (!p || !strides || num_levels <= 0 || num_levels > TRTX_MAX_LEVELS) return TRTX_ERR_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->variant = TRTX_YOLO_V8;
+    p->num_classes = num_classes;
+    p->net_w = net_w;
+    p->net_h = net_h;
+    p->max_out = max_out;
+    p->det_floats = 90;  // yolov8/include/types.h:4-12 with kNumberOfPoints = 17
+    p->num_levels = num_levels;
+    for (int i = 0; i < num_levels; ++i) {
+        if (strides[i] <= 0) return TRTX_ERR_INVALID;
+        p->strides[i] = strides[i];
+        p->grid_h[i] = net_h / strides[i];  // yololayer.cu:294-295
+        p->grid_w[i] = net_w / strides[i];
+    }
+    p->num_kpts = 17;
+    p->gate = 0.1f;
+    p->in_dtype = TRTX_F32;
+    return TRTX_OK;
+}
+
+TRTX_API size_t trtx_yolo_workspace_size(const trtx_yolo_params* p, int batch) {
+    if (validate(p, batch)) return 0;
+    // the scalar layout has the most tiles; the candidate array is identical
+    return yolo_layout(p, batch, 1).total_bytes;
+}
+
+TRTX_API int trtx_yolo_decode_enqueue(const trtx_yolo_params* p, int batch, const void* const* inputs_dev,
+                                      float* output_dev, void* workspace_dev, size_t workspace_bytes,
+                                      trtx_stream_t stream) {
+    if (!output_dev) return TRTX_ERR_INVALID;
+    YoloArgs a;
+    YoloLayout L;
+    int rc = yolo_fill_args(p, batch, inputs_dev, workspace_dev, workspace_bytes, &a, &L);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = yolo_scan_launch(a, L, p->in_dtype, batch, st);
+    if (rc) return rc;
+    const size_t smem = sizeof(int) * (size_t)(L.tiles_per_image + 1);
+    if (smem > 200 * 1024) return TRTX_ERR_UNSUPPORTED;
+    if (p->in_dtype == TRTX_F32) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(yolo_pack_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        yolo_pack_rows_kernel<float><<<batch, 256, smem, st>>>(a, output_dev);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(yolo_pack_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        yolo_pack_rows_kernel<__half><<<batch, 256, smem, st>>>(a, output_dev);
+    }
+    return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// yolo_layout.cuh -- workspace layout + kernel argument blocks shared by the YoloLayer scan,
+// the row packer and the fused NMS kernel.
+//
+// HBM layout:
+//   inputs      : per level l, [B, C, g_l] channel-major (the reference's plugin input)
+//   tile_count  : [B, tiles_per_image] int32   -- candidates found in each 32*VEC-slot tile
+//   cand        : [B, slots_per_image] records of 32 B (two float4):
+//                 {b0,b1,b2,b3} {conf, cls, anchor_id (int bits), 0}
+//                 tile t of image b owns slots [tile_slot_begin(t), +tile_slots); its candidates are
+//                 written densely from the tile's first slot, in ascending anchor order.
+//   list        : [B, slots_per_image] uint2 (conf key, slot) -- scratch of the fused NMS kernel
+// Because every tile writes its own count and its own slot range, compaction needs no atomics and
+// no zero-initialisation, and the result is deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace trtx {
+
+struct LevelArg {
+    const void* in;   // level tensor
+    int g;            // cells = grid_h*grid_w
+    int gw;           // grid width
+    int gh;
+    int stride;       // v8
+    int tile_begin;   // first tile index of this level within an image
+    int slot_begin;   // first slot (flat anchor id) of this level within an image
+    float anc[6];     // v5 anchors
+};
+
+struct YoloArgs {
+    LevelArg lv[TRTX_MAX_LEVELS];
+    int num_levels;
+    int variant;
+    int tiles_per_image;
+    int slots_per_image;
+    int tile_cells;  // cells per tile = 32*VEC
+    int apc;         // anchors per cell: 1 (v8) / 3 (v5)
+    int C;           // channels per image per level (v8: info_len; v5: 3*info_len_i)
+    int info_len;    // v8: 4+nc+extras ; v5: 5+nc(+32)
+    int nc;
+    int net_w, net_h;
+    int max_out, det_floats;
+    int is_seg, is_pose, is_obb, num_kpts;
+    float kpt_thresh;
+    float gate;
+    float x_lo;  // logit below which sigmoid(x) < gate for certain
+    int* tile_count;
+    float4* cand;
+};
+
+struct YoloLayout {
+    int vec;
+    int tile_cells;
+    int apc;
+    int tiles_per_image;
+    int slots_per_image;
+    int level_tile_begin[TRTX_MAX_LEVELS];
+    int level_slot_begin[TRTX_MAX_LEVELS];
+    size_t off_tile_count;
+    size_t off_cand;
+    size_t off_list;  // fused NMS: per-image list of (conf key, slot id) of rows above conf_thresh
+    size_t total_bytes;
+};
+
+// vec = 4 (128-bit rows) or 1 (scalar fallback for grids not divisible by 4 / unaligned pointers).
+inline YoloLayout yolo_layout(const trtx_yolo_params* p, int batch, int vec) {
+    YoloLayout L{};
+    L.vec = vec;
+    L.tile_cells = 32 * vec;
+    L.apc = (p->variant == TRTX_YOLO_V5) ? 3 : 1;
+    int tiles = 0, slots = 0;
+    for (int l = 0; l < p->num_levels; ++l) {
+        int g = p->grid_h[l] * p->grid_w[l];
+        L.level_tile_begin[l] = tiles;
+        L.level_slot_begin[l] = slots;
+        tiles += (g + L.tile_cells - 1) / L.tile_cells;
+        slots += g * L.apc;
+    }
+    L.tiles_per_image = tiles;
+    L.slots_per_image = slots;
+    L.off_tile_count = 0;
+    L.off_cand = align_up(sizeof(int) * (size_t)batch * tiles);
+    L.off_list = L.off_cand + align_up(sizeof(float4) * 2 * (size_t)batch * slots);
+    L.total_bytes = L.off_list + align_up(sizeof(uint2) * (size_t)batch * slots);
+    return L;
+}
+
+int yolo_pick_vec(const trtx_yolo_params* p, const void* const* inputs_dev);
+int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inputs_dev, void* workspace_dev,
+                   size_t workspace_bytes, YoloArgs* a, YoloLayout* L);
+int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t stream);
+
+}  // namespace trtx

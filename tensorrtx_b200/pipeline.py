@@ -1,0 +1,78 @@
+"""Detection hot path as one object: pinned frames -> H2D -> batched letterbox pre-process ->
+[backbone: TensorRT in the reference, injected here] -> fused YoloLayer decode + NMS -> D2H of the
+compact detections.  This is the call a user of the reference's `yolov8_det -d` loop makes per batch
+(yolov8/yolov8_det.cpp:223-244), minus disk IO and drawing.
+
+Everything is asynchronous on one CUDA stream; the only host synchronisation is the caller's.
+Multi-GPU: one pipeline per process/GPU (batch-sharded, images are independent -- SURVEY 8e);
+`gather()` is the single NCCL collective (fixed-size all-gather of the compact detections).
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+from . import _lib as L
+from .plugins import FusedYoloDecodeNms, PreprocessPlan, YoloLayerPlugin
+
+
+class DetectionPipeline:
+    def __init__(self, batch: int, src_h: int = 640, src_w: int = 640, net_h: int = 640, net_w: int = 640,
+                 num_classes: int = 80, strides: Sequence[int] = (8, 16, 32), max_out: int = 1000,
+                 conf_thresh: float = 0.5, nms_thresh: float = 0.45, device: str | torch.device = "cuda",
+                 input_dtype: torch.dtype = torch.float32, head_dtype: int = L.F32,
+                 backbone: Callable[[torch.Tensor], Sequence[torch.Tensor]] | None = None):
+        self.batch, self.src_h, self.src_w, self.net_h, self.net_w = batch, src_h, src_w, net_h, net_w
+        self.device = torch.device(device)
+        self.backbone = backbone
+        self.plugin = YoloLayerPlugin(num_classes, 17, 0.0, net_w, net_h, max_out, False, False, False, strides,
+                                      in_dtype=head_dtype)
+        self.fused = FusedYoloDecodeNms(self.plugin, batch, conf_thresh, nms_thresh, max_det=max_out,
+                                        device=self.device, return_index=False)
+        self.frames_dev = torch.empty((batch, src_h, src_w, 3), dtype=torch.uint8, device=self.device)
+        self.net_input = torch.empty((batch, 3, net_h, net_w), dtype=input_dtype, device=self.device)
+        self.out_host = torch.empty((batch, 1 + max_out * 7), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.frames_dev.numel()
+        self.d2h_bytes = self.out_host.numel() * 4
+        # descriptors of the (persistent) device frame buffers are built once, not per step
+        self.pre = PreprocessPlan(list(self.frames_dev.unbind(0)), self.net_input, net_w, net_h)
+
+    def run(self, frames_host: torch.Tensor, heads: Sequence[torch.Tensor] | None = None, stream=None) -> torch.Tensor:
+        """frames_host: pinned uint8 [B, H, W, 3] BGR.  heads: the backbone's per-stride outputs when no
+        backbone callable was given.  Returns the pinned host buffer [B, 1+K*7] (valid after a stream sync)."""
+        self.frames_dev.copy_(frames_host, non_blocking=True)
+        self.pre.enqueue(stream)
+        if self.backbone is not None:
+            heads = self.backbone(self.net_input)
+        out, _ = self.fused.enqueue(self.batch, heads, stream)
+        self.out_host.copy_(out, non_blocking=True)
+        return self.out_host
+
+    def run_device(self, heads: Sequence[torch.Tensor], stream=None) -> torch.Tensor:
+        """Device-resident step: pre-process the frames already in HBM + decode + NMS (no host copies)."""
+        self.pre.enqueue(stream)
+        out, _ = self.fused.enqueue(self.batch, heads, stream)
+        return out
+
+    # ---- CUDA graphs: the step is launch-bound (4 kernels of 10-30 us), so replaying a captured graph
+    # removes the per-launch host cost (guide: "capture launch-bound inner loops in CUDA graphs") ----
+    def capture(self, fn: Callable[[], object]) -> "torch.cuda.CUDAGraph":
+        """Capture `fn` (which must only enqueue work on the current stream) into a CUDA graph."""
+        fn()  # warm-up outside capture (lazy module loads, cudaFuncSetAttribute)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+
+def gather(local: torch.Tensor, world_size: int) -> torch.Tensor:
+    """The one collective of the path: fixed-size all-gather of [B_local, 1+K*7]."""
+    import torch.distributed as dist
+
+    if world_size == 1:
+        return local
+    out = torch.empty((world_size * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out

@@ -1,0 +1,323 @@
+"""Parity of the YoloLayer scan / pack / NMS kernels against the CPU oracle, through the C ABI
+(tensorrtx_b200.plugins forwards to libtrtx_hot.so).  Tolerances: boxes/scores abs 1e-4
+(BASELINE.json north_star), counts / classes / kept-index sets exact."""
+import numpy as np
+import pytest
+import torch
+
+from tensorrtx_b200 import _lib as L
+from tensorrtx_b200 import plugins as P
+from tensorrtx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-4
+
+
+def _to_dev(heads, dev, dtype=torch.float32):
+    return [torch.from_numpy(h).to(dev).to(dtype).contiguous() for h in heads]
+
+
+def _decode_gpu(plug, heads_dev, B, dev):
+    out = torch.full((B, plug.output_elems()), -123.0, dtype=torch.float32, device=dev)
+    ws = torch.empty(plug.getWorkspaceSize(B), dtype=torch.uint8, device=dev)
+    assert plug.enqueue(B, heads_dev, [out], ws) == 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _check_rows(got, ref, B, F, ncols, max_out):
+    assert np.array_equal(np.minimum(ref[:, 0], max_out), got[:, 0])
+    for b in range(B):
+        n = int(got[b, 0])
+        g = got[b, 1:1 + n * F].reshape(n, F)[:, :ncols]
+        r = ref[b, 1:1 + n * F].reshape(n, F)[:, :ncols]
+        np.testing.assert_allclose(g, r, atol=ATOL, rtol=0)
+        assert np.array_equal(g[:, 5], r[:, 5])  # class ids exact
+
+
+@pytest.mark.parametrize("seed,B", [(0, 1), (1, 4), (2, 5)])
+def test_v8_decode_parity(oracle, dev, seed, B):
+    heads = synth.yolov8_heads(B, seed=seed)
+    ref, _ = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    got = _decode_gpu(plug, _to_dev(heads, dev), B, dev)
+    assert ref[:, 0].min() > 100  # the synthetic set really has candidates
+    _check_rows(got, ref, B, 90, 6, 1000)
+
+
+def test_v8_decode_empty_and_overflow(oracle, dev):
+    # empty: background only
+    heads = synth.yolov8_heads(2, seed=5, n_obj=0)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
+    ref, _ = oracle.yolov8_decode(heads)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    # overflow: ~3000 candidates / image, capacity 1000 -> first 1000 in anchor order, count clamped
+    heads = synth.yolov8_heads(2, seed=6, n_obj=220)
+    ref, _ = oracle.yolov8_decode(heads)
+    assert ref[:, 0].min() > 1000
+    got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
+    _check_rows(got, ref, 2, 90, 6, 1000)
+    # determinism: identical bytes on a second run
+    got2 = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
+    assert np.array_equal(got[:, :1 + 1000 * 90].reshape(2, -1)[:, 0], got2[:, 0])
+    for b in range(2):
+        a = got[b, 1:].reshape(1000, 90)[:, :6]
+        c = got2[b, 1:].reshape(1000, 90)[:, :6]
+        assert np.array_equal(a, c)
+
+
+def test_v8_scalar_path_odd_grid(oracle, dev):
+    # 648x648 -> grids 81^2, 40^2 (648/16=40.5 -> 40), 20^2: level 0 has an odd cell count -> scalar kernels
+    net = 648
+    strides = (8, 16, 32)
+    heads = synth.yolov8_heads(3, seed=7, net_w=net, net_h=net, strides=strides)
+    ref, _ = oracle.yolov8_decode(heads, strides=strides, net_w=net, net_h=net)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, net, net, 1000, False, False, False, strides)
+    got = _decode_gpu(plug, _to_dev(heads, dev), 3, dev)
+    _check_rows(got, ref, 3, 90, 6, 1000)
+
+
+def test_v8_nonsquare_and_classes(oracle, dev):
+    heads = synth.yolov8_heads(2, seed=8, nc=15, net_w=1024, net_h=576, strides=(8, 16, 32))
+    ref, _ = oracle.yolov8_decode(heads, net_w=1024, net_h=576, nc=15)
+    plug = P.YoloLayerPlugin(15, 17, 0.0, 1024, 576, 1000, False, False, False, (8, 16, 32))
+    got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
+    _check_rows(got, ref, 2, 90, 6, 1000)
+
+
+@pytest.mark.parametrize("mode", ["seg", "pose", "obb"])
+def test_v8_extras(oracle, dev, mode):
+    seg, pose, obb = mode == "seg", mode == "pose", mode == "obb"
+    nc = 1 if pose else (15 if obb else 80)
+    extra = 32 if seg else (51 if pose else 1)
+    heads = synth.yolov8_heads(2, seed=9, nc=nc, extra=extra, n_obj=20)
+    kt = 0.3
+    ref, _ = oracle.yolov8_decode(heads, nc=nc, is_seg=seg, is_pose=pose, is_obb=obb, kpt_thresh=kt)
+    plug = P.YoloLayerPlugin(nc, 17, kt, 640, 640, 1000, seg, pose, obb, (8, 16, 32))
+    got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    for b in range(2):
+        n = int(got[b, 0])
+        g = got[b, 1:1 + n * 90].reshape(n, 90)
+        r = ref[b, 1:1 + n * 90].reshape(n, 90)
+        cols = list(range(6))
+        if seg:
+            cols += list(range(6, 38))
+        if pose:
+            cols += list(range(38, 89))
+        if obb:
+            cols += [89]
+        np.testing.assert_allclose(g[:, cols], r[:, cols], atol=ATOL, rtol=0)
+
+
+def test_v8_fp16_inputs(oracle, dev):
+    heads = [h.astype(np.float16).astype(np.float32) for h in synth.yolov8_heads(2, seed=10)]  # fp16-representable
+    ref, _ = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32), in_dtype=L.F16)
+    got = _decode_gpu(plug, _to_dev(heads, dev, torch.float16), 2, dev)
+    _check_rows(got, ref, 2, 90, 6, 1000)
+
+
+@pytest.mark.parametrize("slices,unroll", [(1, 8), (1, 16), (2, 10), (2, 20), (4, 5), (4, 20), (8, 5), (8, 10)])
+def test_v8_all_scan_variants(oracle, dev, slices, unroll):
+    lib = L.load()
+    heads = synth.yolov8_heads(2, seed=11)
+    ref, _ = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    try:
+        lib.trtx_tune_set(0, slices)
+        lib.trtx_tune_set(1, unroll)
+        got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
+    finally:
+        lib.trtx_tune_set(0, 4)
+        lib.trtx_tune_set(1, 10)
+    _check_rows(got, ref, 2, 90, 6, 1000)
+
+
+def test_first_argmax_on_sigmoid_collisions(oracle, dev):
+    # saturating logits: sigmoid(18) == sigmoid(25) == 1.0f -> the reference keeps the FIRST class
+    heads = synth.yolov8_heads(1, seed=12, n_obj=0)
+    h = heads[0]
+    h[0, 4 + 7, 100] = 25.0
+    h[0, 4 + 3, 100] = 18.0   # earlier class, smaller logit, same sigmoid
+    h[0, 4 + 50, 200] = 6.0000
+    h[0, 4 + 20, 200] = 6.0000  # exact tie -> first class wins
+    ref, _ = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    got = _decode_gpu(plug, _to_dev(heads, dev), 1, dev)
+    assert got[0, 0] == ref[0, 0] == 2
+    g = got[0, 1:181].reshape(2, 90)
+    assert g[0, 5] == 3 and g[1, 5] == 20
+    _check_rows(got, ref, 1, 90, 6, 1000)
+
+
+# ------------------------------------------------------------------ NMS ------------------------
+@pytest.mark.parametrize("seed", [0, 1])
+def test_batch_nms_matches_reference_nms(oracle, dev, seed):
+    B = 3
+    heads = synth.yolov8_heads(B, seed=20 + seed)
+    ref, _ = oracle.yolov8_decode(heads)
+    comp, idx = P.batch_nms(torch.from_numpy(ref).to(dev), B, ref.shape[1], 0.5, 0.45, return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        res, src = oracle.nms(0, ref[b], 1000, 90, 0.5, 0.45)
+        n = int(comp[b, 0])
+        assert n == len(res) and n > 20
+        assert np.array_equal(idx[b, :n], src)            # identical kept rows, identical (class, conf) order
+        rows = comp[b, 1:1 + n * 7].reshape(n, 7)
+        assert np.array_equal(rows[:, :6], res[:, :6])    # rows are copies: bit-exact
+        assert np.all(rows[:, 6] == 1)
+        assert np.all(comp[b, 1 + n * 7:] == 0)
+
+
+def test_fused_decode_nms(oracle, dev):
+    B = 4
+    heads = synth.yolov8_heads(B, seed=30)
+    ref, ref_idx = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    fused = P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev)
+    comp, idx = fused.enqueue(B, _to_dev(heads, dev))
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        res, src = oracle.nms(0, ref[b], 1000, 90, 0.5, 0.45)
+        n = int(comp[b, 0])
+        assert n == len(res)
+        assert np.array_equal(idx[b, :n], ref_idx[b][src])  # identical kept ANCHOR ids
+        np.testing.assert_allclose(comp[b, 1:1 + n * 7].reshape(n, 7)[:, :6], res[:, :6], atol=ATOL, rtol=0)
+
+
+def test_nms_dense_single_class_and_ties(oracle, dev):
+    # all candidates in one class, heavy overlap, duplicated confidences (ties broken by box[0], then row)
+    rng = np.random.default_rng(5)
+    n = 1000
+    buf = np.zeros((1, 1 + n * 90), np.float32)
+    rows = buf[0, 1:].reshape(n, 90)
+    cx, cy = rng.uniform(100, 540, n), rng.uniform(100, 540, n)
+    w, h = rng.uniform(40, 200, n), rng.uniform(40, 200, n)
+    rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3] = cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2
+    rows[:, 4] = np.round(rng.uniform(0.3, 1.0, n), 2)   # many exact ties
+    rows[:, 5] = 3
+    buf[0, 0] = n
+    comp, idx = P.batch_nms(torch.from_numpy(buf).to(dev), 1, buf.shape[1], 0.5, 0.45, return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    res, src = oracle.nms(0, buf[0], n, 90, 0.5, 0.45)
+    k = int(comp[0, 0])
+    assert k == len(res)
+    assert np.array_equal(idx[0, :k], src)
+
+
+def test_nms_empty_and_below_threshold(oracle, dev):
+    buf = np.zeros((2, 1 + 1000 * 90), np.float32)
+    buf[1, 0] = 3
+    buf[1, 1:1 + 3 * 90].reshape(3, 90)[:, 4] = 0.4  # all below conf 0.5
+    comp = P.batch_nms(torch.from_numpy(buf).to(dev), 2, buf.shape[1], 0.5, 0.45).cpu().numpy()
+    assert np.all(comp == 0)
+
+
+def test_nms_oneshot_mode(oracle, dev):
+    heads = synth.yolov8_heads(1, seed=40)
+    ref, _ = oracle.yolov8_decode(heads)
+    comp, idx = P.batch_nms(torch.from_numpy(ref).to(dev), 1, ref.shape[1], 0.5, 0.45, mode=L.NMS_ONESHOT,
+                            return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    exp = oracle.cuda_decode_nms(ref[0], 1000, 90, 0.5, 0.45, 1000)
+    n = int(comp[0, 0])
+    rows = comp[0, 1:1 + n * 7].reshape(n, 7)
+    exp_rows = exp[1:].reshape(1000, 7)
+    exp_valid = {i for i in range(int(exp[0])) if exp_rows[i, 4] > 0}
+    assert set(idx[0, :n].tolist()) == exp_valid
+    kept_gpu = {int(idx[0, i]) for i in range(n) if rows[i, 6] == 1}
+    kept_ref = {i for i in exp_valid if exp_rows[i, 6] == 1}
+    assert kept_gpu == kept_ref
+
+
+def test_nms_topk_select_when_overflowing(oracle, dev):
+    # fused path with > max_out candidates above conf_thresh: the top max_out by conf enter NMS
+    B = 1
+    heads = synth.yolov8_heads(B, seed=41, n_obj=300)
+    big, big_idx = oracle.yolov8_decode(heads, max_out=8400)
+    n_all = int(big[0, 0])
+    rows = big[0, 1:1 + n_all * 90].reshape(n_all, 90)
+    valid = np.where(rows[:, 4] > 0.5)[0]
+    assert len(valid) > 1000
+    order = sorted(valid, key=lambda i: (-rows[i, 4], big_idx[0, i]))[:1000]   # ties -> smaller anchor id
+    order = sorted(order)                                                       # back to anchor order
+    sub = np.zeros((1 + 1000 * 90,), np.float32)
+    sub[0] = 1000
+    sub[1:].reshape(1000, 90)[:] = rows[order]
+    res, src = oracle.nms(0, sub, 1000, 90, 0.5, 0.45)
+    exp_anchor = big_idx[0][np.asarray(order)[src]]
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    fused = P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev)
+    comp, idx = fused.enqueue(B, _to_dev(heads, dev))
+    n = int(comp[0, 0].item())
+    assert n == len(res)
+    assert np.array_equal(idx[0, :n].cpu().numpy(), exp_anchor)
+
+
+# ------------------------------------------------------------------ v5 -------------------------
+def _v5_plugin(seg=False):
+    ks = [P.YoloKernel(640 // s, 640 // s, a) for s, a in zip((8, 16, 32), synth.V5_ANCHORS)]
+    return P.YoloLayerPluginV5(80, 640, 640, 1000, seg, ks)
+
+
+@pytest.mark.parametrize("seed,B,seg", [(0, 1, False), (1, 3, False), (2, 2, True)])
+def test_v5_decode_parity(oracle, dev, seed, B, seg):
+    heads = synth.yolov5_heads(B, seed=50 + seed, seg=seg)
+    ref, _ = oracle.yolov5_decode(heads, synth.V5_ANCHORS, is_seg=seg)
+    plug = _v5_plugin(seg)
+    got = _decode_gpu(plug, _to_dev(heads, dev), B, dev)
+    assert ref[:, 0].min() > 100
+    _check_rows(got, ref, B, 38, 38 if seg else 6, 1000)
+
+
+def test_v5_fused_nms(oracle, dev):
+    B = 2
+    heads = synth.yolov5_heads(B, seed=60)
+    ref, ref_idx = oracle.yolov5_decode(heads, synth.V5_ANCHORS)
+    fused = P.FusedYoloDecodeNms(_v5_plugin(), B, 0.5, 0.45, device=dev)
+    comp, idx = fused.enqueue(B, _to_dev(heads, dev))
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        res, src = oracle.nms(1, ref[b], 1000, 38, 0.5, 0.45)
+        n = int(comp[b, 0])
+        assert n == len(res)
+        assert np.array_equal(idx[b, :n], ref_idx[b][src])
+        np.testing.assert_allclose(comp[b, 1:1 + n * 7].reshape(n, 7)[:, :6], res[:, :6], atol=ATOL, rtol=0)
+
+
+# ------------------------------------------------------------------ full size ------------------
+def test_full_size_b32_properties(oracle, dev):
+    """BASELINE configs[1] size: b32.  Size-independent properties + oracle spot checks on 3 images."""
+    B = 32
+    heads = synth.yolov8_heads(B, seed=70)
+    hd = _to_dev(heads, dev)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    fused = P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev)
+    comp, idx = fused.enqueue(B, hd)
+    comp, idx = comp.clone(), idx.clone()
+    # determinism / idempotence of the whole path
+    comp2, idx2 = fused.enqueue(B, hd)
+    assert torch.equal(comp, comp2) and torch.equal(idx, idx2)
+    c = comp.cpu().numpy()
+    counts = c[:, 0].astype(int)
+    assert counts.min() > 20 and counts.max() <= 1000
+    # NMS of the NMS output is the identity (kept rows never suppress each other)
+    again = P.batch_nms(comp.contiguous(), B, comp.shape[1], 0.5, 0.45, det_floats=7, max_det=1000).cpu().numpy()
+    assert np.array_equal(again[:, 0], c[:, 0])
+    # rows sorted by (class asc, conf desc); anchors unique
+    ii = idx.cpu().numpy()
+    for b in range(B):
+        n = counts[b]
+        rows = c[b, 1:1 + n * 7].reshape(n, 7)
+        key = list(zip(rows[:, 5], -rows[:, 4]))
+        assert key == sorted(key)
+        assert len(set(ii[b, :n].tolist())) == n
+    # oracle spot checks
+    for b in (0, 13, 31):
+        one = [h[b:b + 1] for h in heads]
+        ref, ref_idx = oracle.yolov8_decode(one)
+        res, src = oracle.nms(0, ref[0], 1000, 90, 0.5, 0.45)
+        assert counts[b] == len(res)
+        assert np.array_equal(ii[b, :counts[b]], ref_idx[0][src])
