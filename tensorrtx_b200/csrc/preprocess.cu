@@ -138,7 +138,7 @@ using namespace trtx;
 
 extern "C" {
 
-// preprocess.cu:98-110 + cv::invertAffineTransform (CV_32F branch: float products, double inverse)
+// preprocess.cu:98-110 + cv::invertAffineTransform (CV_32F branch)
 TRTX_API void trtx_letterbox_matrix(int sw, int sh, int dw, int dh, float d2s[6]) {
     float a = dh / (float)sh, b = dw / (float)sw;
     float scale = a < b ? a : b;  // std::min
@@ -149,9 +149,17 @@ TRTX_API void trtx_letterbox_matrix(int sw, int sh, int dw, int dh, float d2s[6]
     s2d[3] = 0;
     s2d[4] = scale;
     s2d[5] = (float)(-scale * sh * 0.5 + dh * 0.5);
-    double D = s2d[0] * s2d[4] - s2d[1] * s2d[3];
+    /* cv::invertAffineTransform, CV_32F branch, as OpenCV >= 4.x evaluates it with softfloat/softdouble
+     * (pinned against cv2 4.13 on 3000 sizes, tests/test_oracle_cpu.py): the determinant and the
+     * A = M*D products are FLOAT operations (softfloat::operator* converts D to float), 1/D and the
+     * translation terms are double. */
+    float p0 = s2d[0] * s2d[4], p1 = s2d[1] * s2d[3];
+    float det = p0 - p1;
+    double D = (double)det;
     D = D != 0 ? 1. / D : 0;
-    double A11 = s2d[4] * D, A22 = s2d[0] * D, A12 = -s2d[1] * D, A21 = -s2d[3] * D;
+    float Df = (float)D;
+    float fA11 = s2d[4] * Df, fA22 = s2d[0] * Df, fA12 = (-s2d[1]) * Df, fA21 = (-s2d[3]) * Df;
+    double A11 = fA11, A22 = fA22, A12 = fA12, A21 = fA21;
     double b1 = -A11 * s2d[2] - A12 * s2d[5];
     double b2 = -A21 * s2d[2] - A22 * s2d[5];
     d2s[0] = (float)A11;

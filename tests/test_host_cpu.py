@@ -1,0 +1,174 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+plugin (de)serialization keeps the reference's byte layout, parameter validation, the letterbox
+matrix of the library equals the oracle's (and therefore cv2's), and the N>1 gather path under gloo."""
+import ctypes as C
+import os
+import re
+import struct
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from tensorrtx_b200 import _lib as L
+
+    lib = L.load()
+    hdr = (ROOT / "include" / "trtx_hot.h").read_text()
+    declared = set(re.findall(r"TRTX_API\s+[\w\s\*]+?\b(trtx_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.trtx_version()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert declared <= exported
+    # nothing but the C ABI (and the tuning knob) is exported: no C++ symbols leak
+    assert all(s.startswith("trtx_") for s in exported), [s for s in exported if not s.startswith("trtx_")]
+
+
+def test_no_torch_types_in_abi():
+    hdr = (ROOT / "include" / "trtx_hot.h").read_text()
+    assert "torch" not in hdr.lower() and "at::" not in hdr and "#include <cuda" not in hdr
+
+
+def test_yolo_plugin_serialization_layout_v8():
+    from tensorrtx_b200 import plugins as P
+
+    p = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, True, False, (8, 16, 32))
+    blob = p.serialize()
+    # yololayer.cu:75-95: classCount, nKpt, kptThr(float), threadCount, W, H, maxOut, nStrides, strides..., 3 bools
+    assert len(blob) == p.getSerializationSize() == 4 * 8 + 12 + 3
+    assert struct.unpack_from("<ii", blob, 0) == (80, 17)
+    assert struct.unpack_from("<i", blob, 12)[0] == 256
+    assert struct.unpack_from("<iii", blob, 32) == (8, 16, 32)
+    assert blob[-3:] == b"\x00\x01\x00"
+    q = P.YoloLayerPlugin.deserialize(blob)
+    assert q.serialize() == blob and q.is_pose_ and q.mStrides == [8, 16, 32]
+    with pytest.raises(Exception):
+        P.YoloLayerPlugin.deserialize(blob + b"\0")
+    c = p.clone()
+    assert c.serialize() == blob and c is not p
+    assert p.getOutputDimensions() == (1000 * 90 + 1, 1, 1)
+    assert p.getPluginType() == "YoloLayer_TRT" and p.getPluginVersion() == "1"
+    assert p.getWorkspaceSize(32) > 0
+
+
+def test_yolo_creator_fields():
+    from tensorrtx_b200 import plugins as P
+
+    cr = P.YoloPluginCreator()
+    cr.setPluginNamespace("ns")
+    # combinedInfo of yolov8/src/block.cpp:264-296
+    ci = [80, 17, 0, 640, 640, 1000, 0, 0, 0, 8, 16, 32]
+    p = cr.createPlugin("yololayer", {"combinedInfo": ci})
+    assert p.mClassCount == 80 and p.mStrides == [8, 16, 32] and p.getPluginNamespace() == "ns"
+    assert cr.deserializePlugin("yololayer", p.serialize()).serialize() == p.serialize()
+    with pytest.raises(Exception):
+        cr.createPlugin("yololayer", {"netinfo": ci})
+
+
+def test_yolo_v5_serialization_layout():
+    from tensorrtx_b200 import plugins as P
+    from tensorrtx_b200 import synth
+
+    ks = [P.YoloKernel(640 // s, 640 // s, a) for s, a in zip((8, 16, 32), synth.V5_ANCHORS)]
+    p = P.YoloLayerPluginV5(80, 640, 640, 1000, False, ks)
+    blob = p.serialize()
+    assert len(blob) == p.getSerializationSize() == 25 + 3 * 32   # yolov5 yololayer.cu:48-83
+    q = P.YoloLayerPluginV5.deserialize(blob)
+    assert q.serialize() == blob
+    assert [k.anchors for k in q.mYoloKernel] == [list(map(float, a)) for a in synth.V5_ANCHORS]
+
+
+def test_param_validation_returns_error_codes_without_gpu():
+    from tensorrtx_b200 import _lib as L
+
+    lib = L.load()
+    p = L.YoloParams()
+    assert lib.trtx_yolo_workspace_size(C.byref(p), 1) == 0          # zeroed params are invalid
+    strides = (C.c_int * 3)(8, 16, 32)
+    assert lib.trtx_yolo_params_init_v8(C.byref(p), 80, 640, 640, 1000, strides, 3) == L.OK
+    assert list(p.grid_w[:3]) == [80, 40, 20] and p.det_floats == 90
+    assert lib.trtx_yolo_params_init_v8(C.byref(p), 80, 640, 640, 1000, strides, 9) == L.ERR_INVALID
+    assert lib.trtx_yolo_workspace_size(C.byref(p), 32) >= 32 * 8400 * 32
+    # null device pointers are rejected before any CUDA call
+    assert lib.trtx_yolo_decode_enqueue(C.byref(p), 1, None, None, None, 0, None) == L.ERR_INVALID
+    q = L.NmsParams()
+    q.max_det = 0
+    assert lib.trtx_nms_workspace_size(C.byref(q), 1, 1000) == 0
+    r = L.RetinaParams()
+    r.in_h, r.in_w = 640, 640
+    assert lib.trtx_retina_total_priors(C.byref(r)) == 16800
+
+
+def test_library_letterbox_matrix_equals_oracle(oracle):
+    from tensorrtx_b200 import plugins as P
+
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        sw, sh = (int(v) for v in rng.integers(40, 4000, 2))
+        assert np.array_equal(np.asarray(P.letterbox_matrix(sw, sh, 640, 640), np.float32),
+                              oracle.letterbox_matrix(sw, sh, 640, 640))
+
+
+def test_threshold_rounding_for_double_literals():
+    from tensorrtx_b200.plugins import float_le_threshold
+
+    for lit in (0.1, 0.02, 0.5, 0.45):
+        t = np.float32(float_le_threshold(lit))
+        assert float(t) <= lit < float(np.nextafter(t, np.float32(np.inf)))
+
+
+def test_missing_library_raises(monkeypatch, tmp_path):
+    from tensorrtx_b200 import _lib as L
+
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(L.TrtxError):
+        L.load()
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["TRTX_ROOT"])
+from tensorrtx_b200.pipeline import gather
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+B, K = 4, 10
+local = torch.full((B, 1 + K * 7), float(rank)) + torch.arange(B)[:, None]
+out = gather(local, world)
+assert out.shape == (world * B, 1 + K * 7)
+for r in range(world):
+    assert torch.equal(out[r * B:(r + 1) * B], torch.full((B, 1 + K * 7), float(r)) + torch.arange(B)[:, None])
+# batch sharding: rank r owns images [B*r, B*(r+1)) of the global batch
+dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+"""
+
+
+def test_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, TRTX_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_bench_reference_arm_prints_contract_json():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    import json
+
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

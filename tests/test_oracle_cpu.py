@@ -1,0 +1,165 @@
+"""CPU-only checks of the oracle (test infrastructure) against independent implementations:
+torchvision.ops.nms / batched_nms (greedy, plain IoU, `>` threshold), cv2.invertAffineTransform and
+cv2.warpAffine-free closed forms.  These pin the oracle where the reference has no fixtures
+(SURVEY.md 8c)."""
+import numpy as np
+import pytest
+import torch
+
+from tensorrtx_b200 import synth
+
+
+def test_decode_count_and_box_formula(oracle):
+    heads = synth.yolov8_heads(2, seed=0)
+    out, idx = oracle.yolov8_decode(heads)
+    # independent numpy restatement of yololayer.cu:193-220
+    lv_off = 0
+    exp = [[] for _ in range(2)]
+    for h, s in zip(heads, (8, 16, 32)):
+        gw = 640 // s
+        x = h[:, 4:84].astype(np.float32)
+        p = (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(np.float32)
+        best = p.max(1)
+        cls = p.argmax(1)  # first max
+        for b in range(2):
+            for e in np.where(best[b] >= np.float32(0.1))[0]:
+                row, col = divmod(int(e), gw)
+                d = h[b, :4, e]
+                exp[b].append((lv_off + e, (col + 0.5 - d[0]) * s, (row + 0.5 - d[1]) * s, (col + 0.5 + d[2]) * s,
+                               (row + 0.5 + d[3]) * s, best[b, e], cls[b, e]))
+        lv_off += h.shape[2]
+    for b in range(2):
+        n = int(out[b, 0])
+        assert n == len(exp[b])
+        rows = out[b, 1:1 + n * 90].reshape(n, 90)
+        e = np.asarray(exp[b], dtype=np.float64)
+        assert np.array_equal(idx[b, :n], e[:, 0].astype(np.int32))
+        np.testing.assert_allclose(rows[:, :4], e[:, 1:5], atol=1e-4)
+        np.testing.assert_allclose(rows[:, 4], e[:, 5], atol=1e-6)
+        assert np.array_equal(rows[:, 5], e[:, 6])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_nms_v8_matches_torchvision_batched_nms(oracle, seed):
+    import torchvision
+
+    heads = synth.yolov8_heads(1, seed=seed)
+    out, _ = oracle.yolov8_decode(heads)
+    n = int(out[0, 0])
+    rows = out[0, 1:1 + n * 90].reshape(n, 90)
+    res, src = oracle.nms(0, out[0], 1000, 90, 0.5, 0.45)
+    valid = np.where(rows[:, 4] > 0.5)[0]
+    keep = torchvision.ops.batched_nms(torch.from_numpy(rows[valid, :4].copy()), torch.from_numpy(rows[valid, 4].copy()),
+                                       torch.from_numpy(rows[valid, 5].astype(np.int64)), 0.45)
+    assert sorted(valid[keep.numpy()].tolist()) == sorted(src.tolist())
+    # order of `res`: class ascending, conf descending (std::map + std::sort)
+    key = list(zip(res[:, 5], -res[:, 4]))
+    assert key == sorted(key)
+
+
+def test_nms_v5_cxcywh_matches_torchvision(oracle):
+    import torchvision
+
+    heads = synth.yolov5_heads(1, seed=3)
+    out, _ = oracle.yolov5_decode(heads, synth.V5_ANCHORS)
+    n = int(out[0, 0])
+    rows = out[0, 1:1 + n * 38].reshape(n, 38)
+    res, src = oracle.nms(1, out[0], 1000, 38, 0.5, 0.45)
+    valid = np.where(rows[:, 4] > 0.5)[0]
+    b = rows[valid, :4]
+    xyxy = np.stack([b[:, 0] - b[:, 2] / 2, b[:, 1] - b[:, 3] / 2, b[:, 0] + b[:, 2] / 2, b[:, 1] + b[:, 3] / 2], 1)
+    keep = torchvision.ops.batched_nms(torch.from_numpy(xyxy), torch.from_numpy(rows[valid, 4].copy()),
+                                       torch.from_numpy(rows[valid, 5].astype(np.int64)), 0.45)
+    assert sorted(valid[keep.numpy()].tolist()) == sorted(src.tolist())
+
+
+def test_nms_properties_permutation_invariance(oracle):
+    heads = synth.yolov8_heads(1, seed=4)
+    out, _ = oracle.yolov8_decode(heads)
+    n = int(out[0, 0])
+    rows = out[0, 1:1 + n * 90].reshape(n, 90).copy()
+    res, _ = oracle.nms(0, out[0], 1000, 90, 0.5, 0.45)
+    perm = np.random.default_rng(0).permutation(n)
+    out2 = out[0].copy()
+    out2[1:1 + n * 90] = rows[perm].reshape(-1)
+    res2, _ = oracle.nms(0, out2, 1000, 90, 0.5, 0.45)
+    assert np.array_equal(res, res2)  # tie-free input -> identical kept rows in identical order
+
+
+def _s2d(sw, sh, dw=640, dh=640):
+    f = np.float32
+    scale = f(min(f(dh) / f(sh), f(dw) / f(sw)))  # preprocess.cu:98
+    m2 = f(float(f(-scale * f(sw))) * 0.5 + dw * 0.5)
+    m5 = f(float(f(-scale * f(sh))) * 0.5 + dh * 0.5)
+    return np.array([[scale, 0, m2], [0, scale, m5]], np.float32)
+
+
+def test_letterbox_matrix_matches_opencv(oracle):
+    """cv::invertAffineTransform is third-party arithmetic (OpenCV); pin the restatement to cv2 4.13."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    sizes = [(640, 640), (1920, 1080), (1080, 1920), (333, 517), (3000, 2000)]
+    sizes += [tuple(int(v) for v in rng.integers(50, 4000, 2)) for _ in range(500)]
+    for (sw, sh) in sizes:
+        d2s = cv2.invertAffineTransform(_s2d(sw, sh))
+        m = oracle.letterbox_matrix(sw, sh, 640, 640)
+        assert np.array_equal(m, d2s.reshape(-1).astype(np.float32)), (sw, sh, m, d2s)
+
+
+def test_warpaffine_identity_scale_is_2x2_mean(oracle):
+    # at scale 1 the reference's +0.5 offset makes every pixel the mean of a 2x2 neighbourhood
+    img = synth.frames(1, seed=1, h=64, w=64)[0]
+    dst = oracle.warpaffine(img, 64, 64)
+    f = img.astype(np.float32)
+    exp = (f[:-1, :-1] + f[:-1, 1:] + f[1:, :-1] + f[1:, 1:]) * 0.25 / 255.0
+    np.testing.assert_allclose(dst[2, :-1, :-1], exp[:, :, 0], atol=1e-6)  # dst plane 2 = B (bgr->rgb swap)
+    np.testing.assert_allclose(dst[0, :-1, :-1], exp[:, :, 2], atol=1e-6)
+    assert dst.shape == (3, 64, 64)
+
+
+def test_warpaffine_letterbox_padding_value(oracle):
+    img = synth.frames(1, seed=2, h=90, w=160)[0]
+    dst = oracle.warpaffine(img, 64, 64)
+    # 160x90 -> scale 0.4 -> 64x36 band, rows < 13 and > 51 are pure border 128/255
+    assert np.allclose(dst[:, :12, :], 128 / 255.0)
+    assert np.allclose(dst[:, 52:, :], 128 / 255.0)
+    assert not np.allclose(dst[:, 20:40, :], 128 / 255.0)
+
+
+def test_rcnn_oracles_against_torchvision(oracle):
+    import torchvision
+
+    # rpnNms: greedy, class-agnostic, thr 0.7, then first `post` survivors in score order
+    rng = np.random.default_rng(0)
+    n = 600
+    xy = rng.uniform(0, 500, (n, 2)).astype(np.float32)
+    wh = rng.uniform(20, 200, (n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], 1)[None]
+    scores = rng.standard_normal((1, n)).astype(np.float32)
+    out = oracle.rpn_nms(scores, boxes, 100, 0.7)
+    keep = torchvision.ops.nms(torch.from_numpy(boxes[0]), torch.from_numpy(scores[0]), 0.7).numpy()
+    assert len(keep) >= 100
+    assert np.array_equal(out[0], boxes[0][keep[:100]])
+    # batchedNms hard mode vs torchvision.batched_nms
+    cls = rng.integers(0, 5, (1, n)).astype(np.float32)
+    sc = rng.uniform(0.05, 1, (1, n)).astype(np.float32)
+    os_, ob, oc = oracle.batched_nms(0, sc, boxes, cls, 100, 0.5)
+    keep = torchvision.ops.batched_nms(torch.from_numpy(boxes[0]), torch.from_numpy(sc[0]),
+                                       torch.from_numpy(cls[0].astype(np.int64)), 0.5).numpy()
+    k = min(100, len(keep))
+    assert np.array_equal(os_[0, :k], sc[0][keep[:k]])
+    assert np.array_equal(ob[0, :k], boxes[0][keep[:k]])
+    assert np.array_equal(oc[0, :k], cls[0][keep[:k]])
+
+
+def test_rpn_decode_topn_and_clip(oracle):
+    scores, deltas = synth.rpn_inputs(2, seed=1, A=15, H=10, W=12)
+    anchors = synth.rcnn_anchors()
+    os_, ob = oracle.rpn_decode(scores, deltas, 160, 192, 16.0, anchors, 300)
+    for b in range(2):
+        flat = scores[b].reshape(-1)
+        order = np.argsort(-flat, kind="stable")[:300]
+        valid = os_[b] > -1e38
+        assert np.array_equal(os_[b][valid], flat[order][valid])
+        assert ob[b][:, 0].min() >= 0 and ob[b][:, 2].max() <= 192 and ob[b][:, 3].max() <= 160
+        assert np.all(np.diff(flat[order]) <= 0)

@@ -11,6 +11,9 @@ from tensorrtx_b200 import synth
 
 pytestmark = pytest.mark.gpu
 ATOL = 1e-4
+# v5 / retinaface boxes pass through expf(): the oracle uses glibc expf, the kernels CUDA expf (<= 2 ulp), and the
+# result is scaled by up to ~1500 px, so those columns get a relative slack of 16 fp32 ulps on top of ATOL.
+RTOL_EXP = 2e-6
 
 
 def _to_dev(heads, dev, dtype=torch.float32):
@@ -25,13 +28,13 @@ def _decode_gpu(plug, heads_dev, B, dev):
     return out.cpu().numpy()
 
 
-def _check_rows(got, ref, B, F, ncols, max_out):
+def _check_rows(got, ref, B, F, ncols, max_out, rtol=0.0):
     assert np.array_equal(np.minimum(ref[:, 0], max_out), got[:, 0])
     for b in range(B):
         n = int(got[b, 0])
         g = got[b, 1:1 + n * F].reshape(n, F)[:, :ncols]
         r = ref[b, 1:1 + n * F].reshape(n, F)[:, :ncols]
-        np.testing.assert_allclose(g, r, atol=ATOL, rtol=0)
+        np.testing.assert_allclose(g, r, atol=ATOL, rtol=rtol)
         assert np.array_equal(g[:, 5], r[:, 5])  # class ids exact
 
 
@@ -269,7 +272,7 @@ def test_v5_decode_parity(oracle, dev, seed, B, seg):
     plug = _v5_plugin(seg)
     got = _decode_gpu(plug, _to_dev(heads, dev), B, dev)
     assert ref[:, 0].min() > 100
-    _check_rows(got, ref, B, 38, 38 if seg else 6, 1000)
+    _check_rows(got, ref, B, 38, 38 if seg else 6, 1000, rtol=RTOL_EXP)
 
 
 def test_v5_fused_nms(oracle, dev):
@@ -284,7 +287,7 @@ def test_v5_fused_nms(oracle, dev):
         n = int(comp[b, 0])
         assert n == len(res)
         assert np.array_equal(idx[b, :n], ref_idx[b][src])
-        np.testing.assert_allclose(comp[b, 1:1 + n * 7].reshape(n, 7)[:, :6], res[:, :6], atol=ATOL, rtol=0)
+        np.testing.assert_allclose(comp[b, 1:1 + n * 7].reshape(n, 7)[:, :6], res[:, :6], atol=ATOL, rtol=RTOL_EXP)
 
 
 # ------------------------------------------------------------------ full size ------------------
