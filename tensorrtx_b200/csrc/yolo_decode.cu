@@ -22,6 +22,8 @@ thread_local int g_last_cuda_error = 0;
 // tuning knobs (set through trtx_tune_set; defaults chosen from the B200 sweep in profiles/)
 static int g_slices = 4;
 static int g_unroll = 10;
+static int g_use_pipe = 1;  // TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
+void yolo_pipe_set_consumers(int n);
 
 // --------------------------------------------------------------------------------------------
 // scan_classes: running (max sigmoid, first argmax) over `nrows` channel rows for VEC adjacent
@@ -33,25 +35,6 @@ static int g_unroll = 10;
 // hence it is always taken by the `x > bx` test and wins the strict `p > bp` comparison.
 // Background logits never reach the slow path, so the hot loop is 1 compare per element.
 // --------------------------------------------------------------------------------------------
-template <int VEC>
-struct Best {
-    float bx[VEC];
-    float bp[VEC];
-    int bc[VEC];
-};
-
-template <int VEC>
-__device__ __forceinline__ void update_one(Best<VEC>& s, int j, float x, int cls) {
-    if (x > s.bx[j]) {
-        s.bx[j] = x;
-        float p = logist(x);
-        if (p > s.bp[j]) {
-            s.bp[j] = p;
-            s.bc[j] = cls;
-        }
-    }
-}
-
 template <typename T, int VEC, int U>
 __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t g, int nrows, int cls0, Best<VEC>& s) {
     const T* p = row0;
@@ -86,12 +69,6 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
         }
         p += (size_t)U * g;
     }
-}
-
-__device__ __forceinline__ void store_record(float4* cand, size_t slot, float b0, float b1, float b2, float b3,
-                                             float conf, int cls, int anchor_id) {
-    cand[2 * slot] = make_float4(b0, b1, b2, b3);
-    cand[2 * slot + 1] = make_float4(conf, (float)cls, __int_as_float(anchor_id), 0.0f);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -599,6 +576,10 @@ static void launch_v8(const YoloArgs& a, int grid, cudaStream_t st) {
 
 int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
     const int grid = batch * L.tiles_per_image;
+    if (g_use_pipe && a.variant == TRTX_YOLO_V8) {
+        const int rc = yolo_scan_pipe_launch(a, L, in_dtype, batch, st);
+        if (rc != TRTX_ERR_UNSUPPORTED) return rc;
+    }
     if (a.variant == TRTX_YOLO_V8) {
         if (in_dtype == TRTX_F32) {
             if (L.vec == 4)
@@ -636,10 +617,13 @@ extern "C" {
 TRTX_API const char* trtx_version(void) { return "trtx_hot 0.1 (sm_100a)"; }
 TRTX_API int trtx_last_cuda_error(void) { return g_last_cuda_error; }
 
-// tuning knob for the bench sweep (not part of the drop-in ABI): key 0 = class slices, 1 = unroll
+// tuning knobs for the bench sweep (not part of the drop-in ABI):
+// 0 = class slices, 1 = unroll (register scan); 2 = use the TMA pipeline scan; 3 = its consumer warps
 TRTX_API int trtx_tune_set(int key, int value) {
     if (key == 0) g_slices = value;
     else if (key == 1) g_unroll = value;
+    else if (key == 2) g_use_pipe = value;
+    else if (key == 3) yolo_pipe_set_consumers(value);
     else return TRTX_ERR_INVALID;
     return TRTX_OK;
 }

@@ -85,9 +85,37 @@ inline YoloLayout yolo_layout(const trtx_yolo_params* p, int batch, int vec) {
     return L;
 }
 
+// ---- device helpers shared by the scan kernels ----
+template <int VEC>
+struct Best {
+    float bx[VEC];
+    float bp[VEC];
+    int bc[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ void update_one(Best<VEC>& s, int j, float x, int cls) {
+    if (x > s.bx[j]) {
+        s.bx[j] = x;
+        float p = logist(x);
+        if (p > s.bp[j]) {
+            s.bp[j] = p;
+            s.bc[j] = cls;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_record(float4* cand, size_t slot, float b0, float b1, float b2, float b3,
+                                             float conf, int cls, int anchor_id) {
+    cand[2 * slot] = make_float4(b0, b1, b2, b3);
+    cand[2 * slot + 1] = make_float4(conf, (float)cls, __int_as_float(anchor_id), 0.0f);
+}
+
 int yolo_pick_vec(const trtx_yolo_params* p, const void* const* inputs_dev);
 int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inputs_dev, void* workspace_dev,
                    size_t workspace_bytes, YoloArgs* a, YoloLayout* L);
 int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t stream);
+// TMA-pipelined scan (yolo_scan_pipe.cu); returns TRTX_ERR_UNSUPPORTED when the shape does not fit it
+int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t stream);
 
 }  // namespace trtx

@@ -1,0 +1,295 @@
+// yolo_scan_pipe.cu -- the YoloLayer scan as a persistent, TMA-fed pipeline (sm_100a).
+//
+// One CTA per SM, resident for the whole launch.  A producer warp streams tiles of the level tensors
+// (all C channel rows x 128 anchors, 43 KB for YOLOv8 fp32) into a ring of shared-memory stages with
+// bulk asynchronous copies (cp.async.bulk.shared::cluster.global, one per channel row, completion
+// counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and ~170 KB per
+// SM are in flight from the first cycle).  NCONS consumer warps each scan a slice of the class rows
+// out of shared memory (conflict-free 128-bit LDS), hand their partial (max sigmoid, first argmax) to
+// the tile's epilogue warp through shared memory + a named barrier, and release the stage through
+// an "empty" mbarrier.  The epilogue (gate, warp-scan compaction, box decode from the 4 box rows that
+// are already in shared memory, 32-byte candidate records) rotates over the consumer warps so no
+// single warp becomes the per-tile bottleneck.
+//
+// The arithmetic is the same bit-exact running-max scheme as yolo_decode.cu::scan_classes.
+// HBM traffic = algorithmic bytes (every row is read exactly once); candidates add <= 4%.
+#include "yolo_layout.cuh"
+
+namespace trtx {
+
+constexpr int kTileAnchors = 128;
+constexpr int kMaxStages = 8;
+
+// ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(addr), "r"(parity)
+                : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy, bytes counted on `bar` (size and both addresses multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ float4 lds4(const T* p);
+template <>
+__device__ __forceinline__ float4 lds4<float>(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 lds4<__half>(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+struct TileRef {
+    int b, t, l, tile, col0, ncols;
+};
+__device__ __forceinline__ TileRef tile_ref(const YoloArgs& a, int T) {
+    TileRef r;
+    r.b = T / a.tiles_per_image;
+    r.t = T - r.b * a.tiles_per_image;
+    int l = 0;
+    while (l + 1 < a.num_levels && r.t >= a.lv[l + 1].tile_begin) ++l;
+    r.l = l;
+    r.tile = r.t - a.lv[l].tile_begin;
+    r.col0 = r.tile * kTileAnchors;
+    r.ncols = min(kTileAnchors, a.lv[l].g - r.col0);
+    return r;
+}
+
+// scratch per stage: partial results of every consumer warp
+template <int NCONS>
+struct StageScratch {
+    float p[NCONS][kTileAnchors];
+    int c[NCONS][kTileAnchors];
+    int any[NCONS];
+    int pad[4];
+};
+
+template <typename T, int NCONS>
+__global__ void __launch_bounds__(32 * (NCONS + 1), 1)
+        yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, int total_tiles, int stages, int stage_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* stage_base = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    StageScratch<NCONS>* scratch = reinterpret_cast<StageScratch<NCONS>*>(empty_bar + kMaxStages);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);       // producer's arrive.expect_tx
+            mbar_init(&empty_bar[s], NCONS);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NCONS) {
+        // ------------------------------ producer warp ------------------------------
+        int it = 0;
+        for (int Tg = blockIdx.x; Tg < total_tiles; Tg += gridDim.x, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            const TileRef r = tile_ref(a, Tg);
+            const LevelArg& L = a.lv[r.l];
+            const uint32_t row_bytes = (uint32_t)r.ncols * sizeof(T);
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], row_bytes * (uint32_t)a.C);
+            __syncwarp();
+            const T* src = reinterpret_cast<const T*>(L.in) + ((size_t)r.b * a.C) * L.g + r.col0;
+            unsigned char* dst = stage_base + (size_t)s * stage_bytes;
+            for (int row = lane; row < a.C; row += 32)
+                bulk_g2s(dst + (size_t)row * kTileAnchors * sizeof(T), src + (size_t)row * L.g, row_bytes, &full_bar[s]);
+        }
+        return;
+    }
+
+    // ------------------------------ consumer warps ------------------------------
+    const int per = (a.nc + NCONS - 1) / NCONS;
+    const int c0 = min(a.nc, warp * per);
+    const int c1 = min(a.nc, c0 + per);
+    int it = 0;
+    for (int Tg = blockIdx.x; Tg < total_tiles; Tg += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        const TileRef r = tile_ref(a, Tg);
+        const LevelArg& L = a.lv[r.l];
+        const bool active = lane * 4 < r.ncols;
+        const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * stage_bytes);
+        StageScratch<NCONS>& sc = scratch[s];
+        const int epi = it % NCONS;  // this tile's epilogue warp
+
+        mbar_wait(&full_bar[s], ph);
+        Best<4> st;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            st.bx[j] = a.x_lo;
+            st.bp[j] = 0.0f;
+            st.bc[j] = 0;
+        }
+        if (active) {
+            const T* p = tile + (size_t)(4 + c0) * kTileAnchors + lane * 4;
+#pragma unroll 4
+            for (int c = c0; c < c1; ++c, p += kTileAnchors) {
+                const float4 v = lds4<T>(p);
+                const bool any = (v.x > st.bx[0]) | (v.y > st.bx[1]) | (v.z > st.bx[2]) | (v.w > st.bx[3]);
+                if (any) {
+                    update_one<4>(st, 0, v.x, c);
+                    update_one<4>(st, 1, v.y, c);
+                    update_one<4>(st, 2, v.z, c);
+                    update_one<4>(st, 3, v.w, c);
+                }
+            }
+        }
+        bool mine = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine |= !(st.bp[j] < a.gate);
+        const bool warp_any = __any_sync(0xffffffffu, mine);
+        if (warp_any) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sc.p[warp][lane * 4 + j] = st.bp[j];
+                sc.c[warp][lane * 4 + j] = st.bc[j];
+            }
+        }
+        if (lane == 0) sc.any[warp] = warp_any ? 1 : 0;
+
+        if (warp != epi) {
+            named_bar_arrive(1 + s, NCONS * 32);  // publish partials; do not wait for the epilogue
+        } else {
+            named_bar_sync(1 + s, NCONS * 32);
+            int any_mask = 0;
+#pragma unroll
+            for (int w = 0; w < NCONS; ++w) any_mask |= sc.any[w] << w;
+            unsigned flags = 0;
+            if (any_mask) {
+                // combine in ascending class-slice order; strict > keeps the FIRST class with the max prob
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st.bp[j] = 0.0f;
+                    st.bc[j] = 0;
+                }
+#pragma unroll
+                for (int w = 0; w < NCONS; ++w) {
+                    if ((any_mask >> w) & 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float p2 = sc.p[w][lane * 4 + j];
+                            if (p2 > st.bp[j]) {
+                                st.bp[j] = p2;
+                                st.bc[j] = sc.c[w][lane * 4 + j];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (active && !(st.bp[j] < a.gate)) flags |= 1u << j;  // yololayer.cu:203
+            }
+            int total;
+            int off = warp_excl_scan(__popc(flags), lane, &total);
+            if (lane == 0) a.tile_count[(size_t)r.b * a.tiles_per_image + r.t] = total;
+            if (flags) {
+                const float4 d0 = lds4<T>(tile + 0 * kTileAnchors + lane * 4);
+                const float4 d1 = lds4<T>(tile + 1 * kTileAnchors + lane * 4);
+                const float4 d2 = lds4<T>(tile + 2 * kTileAnchors + lane * 4);
+                const float4 d3 = lds4<T>(tile + 3 * kTileAnchors + lane * 4);
+                const float dd[4][4] = {{d0.x, d0.y, d0.z, d0.w}, {d1.x, d1.y, d1.z, d1.w},
+                                        {d2.x, d2.y, d2.z, d2.w}, {d3.x, d3.y, d3.z, d3.w}};
+                const size_t slot0 = (size_t)r.b * a.slots_per_image + L.slot_begin + (size_t)r.col0;
+                const float fs = (float)L.stride;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (flags & (1u << j)) {
+                        const int e = r.col0 + lane * 4 + j;
+                        const int row = e / L.gw, col = e - row * L.gw;
+                        // yololayer.cu:217-220
+                        const float x1 = ((float)col + 0.5f - dd[0][j]) * fs;
+                        const float y1 = ((float)row + 0.5f - dd[1][j]) * fs;
+                        const float x2 = ((float)col + 0.5f + dd[2][j]) * fs;
+                        const float y2 = ((float)row + 0.5f + dd[3][j]) * fs;
+                        store_record(a.cand, slot0 + off, x1, y1, x2, y2, st.bp[j], st.bc[j], L.slot_begin + e);
+                        ++off;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage (and its scratch)
+    }
+}
+
+template <typename T, int NCONS>
+static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaStream_t st) {
+    int dev = 0, sms = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int stage_bytes = a.C * kTileAnchors * (int)sizeof(T);
+    const int fixed = 2 * kMaxStages * (int)sizeof(uint64_t);
+    int stages = kMaxStages;
+    while (stages >= 2 && (size_t)stages * (stage_bytes + sizeof(StageScratch<NCONS>)) + fixed + 128 > (size_t)max_smem) --stages;
+    if (stages < 2) return TRTX_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)stages * (stage_bytes + sizeof(StageScratch<NCONS>)) + fixed;
+    const int total_tiles = batch * L.tiles_per_image;
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    auto kern = yolo_v8_scan_pipe_kernel<T, NCONS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 32 * (NCONS + 1), smem, st>>>(a, total_tiles, stages, stage_bytes);
+    return check_launch();
+}
+
+static int g_pipe_consumers = 8;
+void yolo_pipe_set_consumers(int n) { g_pipe_consumers = n; }
+
+int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
+    if (a.variant != TRTX_YOLO_V8 || L.vec != 4 || L.tile_cells != kTileAnchors) return TRTX_ERR_UNSUPPORTED;
+    // bulk copies need 16-byte rows: fp32 rows are (g % 4 == 0 => ok); fp16 rows need g % 8 == 0
+    for (int l = 0; l < a.num_levels; ++l) {
+        if (in_dtype == TRTX_F16 && (a.lv[l].g % 8 != 0 || reinterpret_cast<uintptr_t>(a.lv[l].in) % 16 != 0))
+            return TRTX_ERR_UNSUPPORTED;
+    }
+    if (in_dtype == TRTX_F32) {
+        if (g_pipe_consumers == 4) return launch_pipe<float, 4>(a, L, batch, st);
+        return launch_pipe<float, 8>(a, L, batch, st);
+    }
+    if (g_pipe_consumers == 4) return launch_pipe<__half, 4>(a, L, batch, st);
+    return launch_pipe<__half, 8>(a, L, batch, st);
+}
+
+}  // namespace trtx

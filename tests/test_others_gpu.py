@@ -1,0 +1,200 @@
+"""GPU parity: RetinaFace Decode_TRT, Faster R-CNN plugins, batched letterbox pre-process -- all through
+the C ABI (tensorrtx_b200.plugins -> libtrtx_hot.so) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tensorrtx_b200 import _lib as L
+from tensorrtx_b200 import plugins as P
+from tensorrtx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-4
+RTOL_EXP = 2e-6  # columns that pass through expf (CUDA expf vs glibc expf), see test_yolo_gpu.py
+
+
+def _ws(nbytes, dev):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+# ------------------------------------------------------------------ RetinaFace ----------------
+@pytest.mark.parametrize("B,h,w,seed", [(1, 640, 640, 0), (4, 640, 640, 1), (2, 480, 640, 2), (2, 488, 648, 3)])
+def test_retina_decode_parity(oracle, dev, B, h, w, seed):
+    heads = synth.retina_heads(B, seed=seed, in_h=h, in_w=w)
+    ref, _ = oracle.retina_decode(heads, in_h=h, in_w=w, gate=0.02)
+    plug = P.DecodePlugin(h, w)
+    out = torch.zeros((B, plug.output_elems()), dtype=torch.float32, device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(x).to(dev) for x in heads], [out], _ws(plug.getWorkspaceSize(B), dev)) == 0
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, 0], ref[:, 0]) and ref[:, 0].min() > 50
+    for b in range(B):
+        n = int(ref[b, 0])
+        np.testing.assert_allclose(got[b, 1:1 + n * 15], ref[b, 1:1 + n * 15], atol=ATOL, rtol=RTOL_EXP)
+
+
+def test_retina_nms_with_landmarks(oracle, dev):
+    B = 3
+    heads = synth.retina_heads(B, seed=5)
+    ref, _ = oracle.retina_decode(heads)
+    tp = oracle.retina_total_priors(640, 640)
+    comp, idx = P.batch_nms(torch.from_numpy(ref).to(dev), B, ref.shape[1], P.float_le_threshold(0.1), 0.4,
+                            box_format=L.BOX_RETINA, det_floats=15, max_det=2048, extra_floats=10, extra_offset=5,
+                            return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        res, src = oracle.nms(2, ref[b], tp, 15, 0.1, 0.4)
+        n = int(comp[b, 0])
+        assert n == len(res) and n > 10
+        # single class: reference order = conf descending
+        assert np.array_equal(idx[b, :n], src)
+        rows = comp[b, 1:1 + n * 17].reshape(n, 17)
+        assert np.array_equal(rows[:, :5], res[:, :5])
+        assert np.array_equal(rows[:, 7:17], res[:, 5:15])  # landmarks travel with the box
+
+
+# ------------------------------------------------------------------ Faster R-CNN --------------
+def test_rpn_decode_parity(oracle, dev):
+    B, A, H, W, top_n = 3, 15, 50, 67, 6000
+    scores, deltas = synth.rpn_inputs(B, seed=1, A=A, H=H, W=W)
+    anchors = synth.rcnn_anchors()
+    ref_s, ref_b = oracle.rpn_decode(scores, deltas, 800, 1067, 16.0, anchors, top_n)
+    plug = P.RpnDecodePlugin(top_n, anchors, 16.0, 800, 1067, H, W)
+    os_ = torch.zeros((B, top_n), device=dev)
+    ob = torch.zeros((B, top_n, 4), device=dev)
+    rc = plug.enqueue(B, [torch.from_numpy(scores).to(dev), torch.from_numpy(deltas).to(dev)], [os_, ob],
+                      _ws(plug.getWorkspaceSize(B), dev))
+    assert rc == 0
+    assert np.array_equal(os_.cpu().numpy(), ref_s)       # same ordered top-6000, same -FLT_MAX markers
+    np.testing.assert_allclose(ob.cpu().numpy(), ref_b, atol=ATOL, rtol=RTOL_EXP)
+
+
+def test_rpn_decode_fewer_than_topn(oracle, dev):
+    B, A, H, W, top_n = 2, 15, 8, 9, 2000   # 1080 scores < top_n: unsorted pass-through + -FLT_MAX fill
+    scores, deltas = synth.rpn_inputs(B, seed=2, A=A, H=H, W=W)
+    anchors = synth.rcnn_anchors()
+    ref_s, ref_b = oracle.rpn_decode(scores, deltas, 128, 144, 16.0, anchors, top_n)
+    plug = P.RpnDecodePlugin(top_n, anchors, 16.0, 128, 144, H, W)
+    os_ = torch.zeros((B, top_n), device=dev)
+    ob = torch.zeros((B, top_n, 4), device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(scores).to(dev), torch.from_numpy(deltas).to(dev)], [os_, ob], _ws(256, dev)) == 0
+    n = A * H * W
+    assert np.array_equal(os_.cpu().numpy(), ref_s)
+    np.testing.assert_allclose(ob.cpu().numpy()[:, :n], ref_b[:, :n], atol=ATOL, rtol=RTOL_EXP)
+
+
+@pytest.mark.parametrize("seed,thr", [(0, 0.7), (1, 0.3)])
+def test_rpn_nms_parity(oracle, dev, seed, thr):
+    B, A, H, W, pre, post = 2, 15, 50, 67, 6000, 1000
+    scores, deltas = synth.rpn_inputs(B, seed=10 + seed, A=A, H=H, W=W)
+    s6, b6 = oracle.rpn_decode(scores, deltas, 800, 1067, 16.0, synth.rcnn_anchors(), pre)
+    ref = oracle.rpn_nms(s6, b6, post, thr)
+    plug = P.RpnNmsPlugin(thr, post, pre)
+    ob = torch.zeros((B, post, 4), device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(s6).to(dev), torch.from_numpy(b6).to(dev)], [ob], _ws(256, dev)) == 0
+    assert np.array_equal(ob.cpu().numpy(), ref)          # gathered boxes are copies: bit-exact, same order
+
+
+def test_rpn_nms_fewer_survivors_than_post(oracle, dev):
+    # heavy overlap: < post survivors -> suppressed boxes follow in sorted order (RpnNms.cu:111-117)
+    rng = np.random.default_rng(3)
+    B, pre, post = 2, 700, 300
+    xy = rng.uniform(0, 60, (B, pre, 2)).astype(np.float32)
+    wh = rng.uniform(80, 120, (B, pre, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], -1)
+    scores = rng.standard_normal((B, pre)).astype(np.float32)
+    scores[:, ::7] = -np.finfo(np.float32).max            # empty boxes marked by RpnDecode
+    ref = oracle.rpn_nms(scores, boxes, post, 0.5)
+    plug = P.RpnNmsPlugin(0.5, post, pre)
+    ob = torch.zeros((B, post, 4), device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(scores).to(dev), torch.from_numpy(boxes).to(dev)], [ob], _ws(256, dev)) == 0
+    assert np.array_equal(ob.cpu().numpy(), ref)
+
+
+def test_predictor_decode_parity(oracle, dev):
+    B, N, Cc = 2, 1000, 80
+    scores, deltas, props = synth.predictor_inputs(B, seed=4, N=N, Ccls=Cc)
+    w = (10.0, 10.0, 5.0, 5.0)
+    rs, rb, rc_ = oracle.predictor_decode(scores, deltas, props, 800, 1067, w)
+    plug = P.PredictorDecodePlugin(N, 800, 1067, w, Cc)
+    os_, ob, oc = torch.zeros((B, N), device=dev), torch.zeros((B, N, 4), device=dev), torch.zeros((B, N), device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(x).to(dev) for x in (scores, deltas, props)], [os_, ob, oc], _ws(256, dev)) == 0
+    assert np.array_equal(os_.cpu().numpy(), rs)
+    assert np.array_equal(oc.cpu().numpy(), rc_)
+    np.testing.assert_allclose(ob.cpu().numpy(), rb, atol=ATOL, rtol=RTOL_EXP)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_batched_nms_parity(oracle, dev, method):
+    B, N, Cc = 3, 1000, 80
+    scores, deltas, props = synth.predictor_inputs(B, seed=6 + method, N=N, Ccls=Cc)
+    s, b, c = oracle.predictor_decode(scores, deltas, props, 800, 1067, (10.0, 10.0, 5.0, 5.0))
+    rs, rb, rc_ = oracle.batched_nms(method, s, b, c, 100, 0.5)
+    plug = P.BatchedNmsPlugin(method, 0.5, 100, N)
+    os_, ob, oc = torch.zeros((B, 100), device=dev), torch.zeros((B, 100, 4), device=dev), torch.zeros((B, 100), device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(x).to(dev) for x in (s, b, c)], [os_, ob, oc], _ws(256, dev)) == 0
+    got_s = os_.cpu().numpy()
+    if method == 2:  # gaussian decay goes through expf
+        np.testing.assert_allclose(got_s, rs, atol=1e-6, rtol=RTOL_EXP)
+    else:
+        assert np.array_equal(got_s, rs)
+    assert np.array_equal(ob.cpu().numpy(), rb)
+    assert np.array_equal(oc.cpu().numpy(), rc_)
+
+
+def test_rcnn_workspace_idiom(dev):
+    plug = P.BatchedNmsPlugin(1, 0.5, 100, 1000)
+    assert plug.getWorkspaceSize(8) > 0        # null workspace -> required bytes (BatchedNmsPlugin.h:106-114)
+    assert P.RpnNmsPlugin(0.7, 1000, 6000).getWorkspaceSize(8) > 0
+
+
+# ------------------------------------------------------------------ pre-process ---------------
+@pytest.mark.parametrize("h,w", [(640, 640), (1080, 1920), (517, 333), (64, 48)])
+@pytest.mark.parametrize("odt", [torch.float32, torch.float16])
+def test_letterbox_parity(oracle, dev, h, w, odt):
+    B = 3
+    fr = synth.frames(B, seed=h + w, h=h, w=w)
+    dst = torch.zeros((B, 3, 640, 640), dtype=odt, device=dev)
+    P.cuda_batch_preprocess([torch.from_numpy(f).to(dev) for f in fr], dst, 640, 640)
+    got = dst.float().cpu().numpy()
+    for b in range(B):
+        ref = oracle.warpaffine(fr[b], 640, 640)
+        if odt == torch.float32:
+            np.testing.assert_allclose(got[b], ref, atol=1e-6, rtol=0)
+        else:
+            np.testing.assert_allclose(got[b], ref.astype(np.float16).astype(np.float32), atol=1e-3, rtol=0)
+
+
+def test_letterbox_mixed_sizes_one_launch(oracle, dev):
+    sizes = [(480, 640), (720, 1280), (1000, 300), (33, 47)]
+    frs = [synth.frames(1, seed=i, h=h, w=w)[0] for i, (h, w) in enumerate(sizes)]
+    dst = torch.zeros((len(sizes), 3, 416, 608), dtype=torch.float32, device=dev)
+    P.cuda_batch_preprocess([torch.from_numpy(f).to(dev) for f in frs], dst, 608, 416)
+    got = dst.cpu().numpy()
+    for b, f in enumerate(frs):
+        np.testing.assert_allclose(got[b], oracle.warpaffine(f, 608, 416), atol=1e-6, rtol=0)
+
+
+def test_pipeline_e2e_matches_oracle(oracle, dev):
+    from tensorrtx_b200.pipeline import DetectionPipeline
+
+    B = 4
+    heads = synth.yolov8_heads(B, seed=90)
+    fr = torch.from_numpy(synth.frames(B, seed=91)).pin_memory()
+    pipe = DetectionPipeline(B, device=dev)
+    hd = [torch.from_numpy(h).to(dev) for h in heads]
+    out = pipe.run(fr, hd)
+    torch.cuda.synchronize()
+    out = out.numpy()
+    ref, _ = oracle.yolov8_decode(heads)
+    for b in range(B):
+        res, _ = oracle.nms(0, ref[b], 1000, 90, 0.5, 0.45)
+        n = int(out[b, 0])
+        assert n == len(res)
+        np.testing.assert_allclose(out[b, 1:1 + n * 7].reshape(n, 7)[:, :6], res[:, :6], atol=ATOL, rtol=0)
+    np.testing.assert_allclose(pipe.net_input[1].cpu().numpy(), oracle.warpaffine(fr[1].numpy(), 640, 640), atol=1e-6)
+    # graph replay gives the same bytes
+    g = pipe.capture(lambda: pipe.run(fr, hd))
+    first = out.copy()
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(pipe.out_host.numpy(), first)

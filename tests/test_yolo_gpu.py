@@ -123,19 +123,42 @@ def test_v8_fp16_inputs(oracle, dev):
 
 
 @pytest.mark.parametrize("slices,unroll", [(1, 8), (1, 16), (2, 10), (2, 20), (4, 5), (4, 20), (8, 5), (8, 10)])
-def test_v8_all_scan_variants(oracle, dev, slices, unroll):
+def test_v8_all_register_scan_variants(oracle, dev, slices, unroll):
     lib = L.load()
     heads = synth.yolov8_heads(2, seed=11)
     ref, _ = oracle.yolov8_decode(heads)
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
     try:
+        lib.trtx_tune_set(2, 0)  # register-path scan instead of the TMA pipeline
         lib.trtx_tune_set(0, slices)
         lib.trtx_tune_set(1, unroll)
         got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
     finally:
         lib.trtx_tune_set(0, 4)
         lib.trtx_tune_set(1, 10)
+        lib.trtx_tune_set(2, 1)
     _check_rows(got, ref, 2, 90, 6, 1000)
+
+
+@pytest.mark.parametrize("consumers", [4, 8])
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+@pytest.mark.parametrize("B", [1, 7, 40])
+def test_v8_tma_pipeline_scan(oracle, dev, consumers, dtype, B):
+    """The persistent TMA-fed scan (yolo_scan_pipe.cu): every CTA loops over many tiles, stages wrap around."""
+    lib = L.load()
+    heads = synth.yolov8_heads(B, seed=13 + B, n_obj=40)
+    if dtype == "f16":
+        heads = [h.astype(np.float16).astype(np.float32) for h in heads]
+    ref, _ = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32),
+                             in_dtype=L.F16 if dtype == "f16" else L.F32)
+    try:
+        lib.trtx_tune_set(2, 1)
+        lib.trtx_tune_set(3, consumers)
+        got = _decode_gpu(plug, _to_dev(heads, dev, torch.float16 if dtype == "f16" else torch.float32), B, dev)
+    finally:
+        lib.trtx_tune_set(3, 8)
+    _check_rows(got, ref, B, 90, 6, 1000)
 
 
 def test_first_argmax_on_sigmoid_collisions(oracle, dev):

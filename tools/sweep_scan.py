@@ -22,9 +22,14 @@ res = []
 for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32), in_dtype=dt)
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-    for slices, unroll in [(1, 8), (1, 16), (2, 10), (2, 20), (4, 5), (4, 10), (4, 20), (8, 5), (8, 10)]:
-        lib.trtx_tune_set(0, slices)
-        lib.trtx_tune_set(1, unroll)
+    for slices, unroll in [(-1, 4), (-1, 8), (4, 5), (4, 10), (1, 16), (8, 5)]:
+        if slices < 0:   # TMA pipeline kernel, `unroll` = consumer warps
+            lib.trtx_tune_set(2, 1)
+            lib.trtx_tune_set(3, unroll)
+        else:
+            lib.trtx_tune_set(2, 0)
+            lib.trtx_tune_set(0, slices)
+            lib.trtx_tune_set(1, unroll)
         for i in range(10):
             fused.enqueue_scan(B, ss[i % R])
         torch.cuda.synchronize()
@@ -41,6 +46,8 @@ for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
         print(json.dumps(r), flush=True)
 lib.trtx_tune_set(0, 4)
 lib.trtx_tune_set(1, 10)
+lib.trtx_tune_set(2, 1)
+lib.trtx_tune_set(3, 8)
 # NMS alone and preprocess alone
 plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
 fused = P.FusedYoloDecodeNms(plug, B, device=dev)
