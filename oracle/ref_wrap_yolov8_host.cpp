@@ -1,0 +1,29 @@
+// ref_wrap_yolov8_host.cpp -- TEST INFRASTRUCTURE.  CPU-only wrapper around the reference's host nms()
+// (yolov8/src/postprocess.cpp:94-129) so that the oracle can be pinned WITHOUT a GPU, and so that
+// bench.py can time the reference's own CPU code (cpu_baseline.kind = "reference" for the NMS part).
+#include <cstring>
+#include <vector>
+
+#include "postprocess.h"
+#include "types.h"
+
+extern "C" {
+__attribute__((visibility("default"))) int ref_v8_det_floats() { return (int)(sizeof(Detection) / sizeof(float)); }
+__attribute__((visibility("default"))) int ref_v8_nms(float* output_host, float conf_thresh, float nms_thresh, float* res_out) {
+    std::vector<Detection> res;
+    nms(res, output_host, conf_thresh, nms_thresh);
+    for (size_t i = 0; i < res.size(); ++i) memcpy(res_out + i * (sizeof(Detection) / 4), &res[i], sizeof(Detection));
+    return (int)res.size();
+}
+__attribute__((visibility("default"))) int ref_v8_batch_nms(float* output_host, int batch, int output_size, float conf_thresh,
+                                                            float nms_thresh, float* res_out, int* counts, int max_rows) {
+    std::vector<std::vector<Detection>> rb;
+    batch_nms(rb, output_host, batch, output_size, conf_thresh, nms_thresh);
+    for (int b = 0; b < batch; ++b) {
+        counts[b] = (int)rb[b].size();
+        for (size_t i = 0; i < rb[b].size() && (int)i < max_rows; ++i)
+            memcpy(res_out + ((size_t)b * max_rows + i) * (sizeof(Detection) / 4), &rb[b][i], sizeof(Detection));
+    }
+    return 0;
+}
+}

@@ -8,14 +8,20 @@
 //   A  collect rows with conf > conf_thresh into a list (conf key, id)
 //   B  if more than `pre_topk` survive: block radix-select (4 x 8-bit passes) of the top pre_topk,
 //      ties at the cut broken by the smaller id (second radix select over the ids)
-//   C  bitonic sort in shared memory by (class asc, conf desc, box[0] asc, id asc)  -- the order the
-//      reference builds with std::map<float,...> + std::sort(cmp)
+//   C  bitonic sort by (class asc, conf desc, box[0] asc, id asc) -- the order the reference builds with
+//      std::map<float,...> + std::sort(cmp).  Up to 1024 rows: one row per thread in registers, the
+//      j < 32 exchange steps are warp shuffles, only the 15 j >= 32 steps go through shared memory
+//      (1 barrier each, ping-pong buffers); up to 2048 rows: plain shared-memory network.
 //   D  stage boxes of the sorted rows in shared memory (SoA)
-//   E  greedy NMS in chunks of 32 sorted rows: every chunk member is tested against the already-kept
-//      rows of its class (all 1024 threads, IoU tile in shared memory) and against its 31 chunk-mates
-//      (warp w = member w, lane j = mate j, one __ballot_sync per member gives its suppressor bitmap);
-//      warp 0 then resolves the chunk serially on the 32x32 bitmap.  2 barriers per 32 rows.
-//   F  write [count, (box, conf, cls, keep, extras)*].
+//   E  greedy NMS per CLASS SEGMENT of the sorted list (rows of different classes never interact):
+//      short segments (<= 96 rows, the normal multi-class case) are claimed by single warps and
+//      resolved with shuffles + ballots only -- no block barrier at all;  long segments (single-class
+//      models such as retinaface, or degenerate inputs) are processed by the whole CTA in chunks of 32
+//      rows: every chunk member is tested against the already-kept rows (all 1024 threads, IoU tile in
+//      shared memory) and against its 31 chunk-mates (warp w = member w, lane j = mate j, one
+//      __ballot_sync per member gives its suppressor bitmap); warp 0 resolves the chunk serially on
+//      the 32x32 bitmap.  2 barriers per 32 rows.
+//   F  block scan of the keep flags -> [count, (box, conf, cls, keep, extras)*] in sorted order.
 //
 // IoU arithmetic mirrors the reference's CPU functions operation by operation with round-to-nearest
 // intrinsics (no FMA contraction), so kept sets agree with the host code bit for bit.
@@ -25,6 +31,7 @@ namespace trtx {
 
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxSort = 2048;  // rows entering NMS per image (>= kMaxNumOutputBbox = 1000)
+constexpr int kShortSeg = 96;  // class segments up to this many rows are resolved by a single warp
 
 struct NmsArgs {
     // source 0: plugin-format rows  [B, 1 + max_rows*det_floats]
@@ -162,14 +169,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     float* s_conf = reinterpret_cast<float*>(s_box + S);                         // S
     int* s_cls = reinterpret_cast<int*>(s_conf + S);                             // S
     uint32_t* s_id = reinterpret_cast<uint32_t*>(s_cls + S);                     // S
-    int* s_kcls = reinterpret_cast<int*>(s_id + S);                              // S
-    int* s_kpos = s_kcls + S;                                                    // S
+    int* s_seg = reinterpret_cast<int*>(s_id + S);                               // S  short class segments (start<<16 | len)
+    int* s_long = s_seg + S;                                                     // S/2 long class segments
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_long + S / 2);    // S  keep flags
     float4* s_kbox = reinterpret_cast<float4*>(k_hi);  // aliases the sort keys (dead after phase D)
 
     __shared__ int s_hist[256];
-    __shared__ int s_n, s_need, s_bucket, s_nkept;
+    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nlong, s_cursor;
     __shared__ unsigned s_rem;
     __shared__ unsigned s_sup[32];
+    __shared__ int s_wsum[32];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -288,136 +297,241 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         }
     }
     __syncthreads();
-    for (int k = 2; k <= S_eff; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < S_eff; i += kNmsThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long ah = k_hi[i], al = k_lo[i], bh = k_hi[ixj], bl = k_lo[ixj];
-                    const bool gt = ah > bh || (ah == bh && al > bl);
-                    const bool asc = (i & k) == 0;
-                    if (gt == asc) {
-                        k_hi[i] = bh;
-                        k_lo[i] = bl;
-                        k_hi[ixj] = ah;
-                        k_lo[ixj] = al;
-                    }
+    if (S_eff <= kNmsThreads) {
+        // one key per thread in registers; shuffles for partner distance < 32, smem ping-pong otherwise
+        unsigned long long* ex_hi = reinterpret_cast<unsigned long long*>(s_box);  // scratch: s_box.. are not live yet
+        unsigned long long* ex_lo = ex_hi + 2 * kNmsThreads;
+        unsigned long long mh = tid < S_eff ? k_hi[tid] : ~0ull, ml = tid < S_eff ? k_lo[tid] : ~0ull;
+        int pp = 0;
+        for (int k = 2; k <= S_eff; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                unsigned long long oh, ol;
+                if (jj >= 32) {
+                    ex_hi[pp * kNmsThreads + tid] = mh;
+                    ex_lo[pp * kNmsThreads + tid] = ml;
+                    __syncthreads();
+                    oh = ex_hi[pp * kNmsThreads + (tid ^ jj)];
+                    ol = ex_lo[pp * kNmsThreads + (tid ^ jj)];
+                    pp ^= 1;
+                } else {
+                    oh = __shfl_xor_sync(0xffffffffu, mh, jj);
+                    ol = __shfl_xor_sync(0xffffffffu, ml, jj);
+                }
+                const bool other_less = oh < mh || (oh == mh && ol < ml);
+                const bool want_min = (((tid & k) == 0) == ((tid & jj) == 0));
+                if (want_min == other_less) {
+                    mh = oh;
+                    ml = ol;
                 }
             }
-            __syncthreads();
+        }
+        __syncthreads();
+        if (tid < S_eff) {
+            k_hi[tid] = mh;
+            k_lo[tid] = ml;
+        }
+        __syncthreads();
+    } else {
+        for (int k = 2; k <= S_eff; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int i = tid; i < S_eff; i += kNmsThreads) {
+                    const int ixj = i ^ jj;
+                    if (ixj > i) {
+                        const unsigned long long ah = k_hi[i], al = k_lo[i], bh = k_hi[ixj], bl = k_lo[ixj];
+                        const bool gt = ah > bh || (ah == bh && al > bl);
+                        const bool asc = (i & k) == 0;
+                        if (gt == asc) {
+                            k_hi[i] = bh;
+                            k_lo[i] = bl;
+                            k_hi[ixj] = ah;
+                            k_lo[ixj] = al;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
 
     // ---------------- D: stage sorted rows ----------------
-    for (int i = tid; i < M; i += kNmsThreads) {
-        const uint32_t id = (uint32_t)(k_lo[i] & 0xffffffffull);
-        const Row r = fetch_row(a, b, id);
-        s_box[i] = r.box;
-        s_conf[i] = r.conf;
-        s_cls[i] = a.class_aware ? (int)r.cls : 0;
-        s_id[i] = id;
+    {
+        uint32_t ids[2];
+        int cnt = 0;
+        for (int i = tid; i < M; i += kNmsThreads) ids[cnt++] = (uint32_t)(k_lo[i] & 0xffffffffull);
+        __syncthreads();  // all keys read: the key area / exchange scratch may be overwritten from here on
+        cnt = 0;
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const uint32_t id = ids[cnt++];
+            const Row r = fetch_row(a, b, id);
+            s_box[i] = r.box;
+            s_conf[i] = r.conf;
+            s_cls[i] = a.class_aware ? (int)r.cls : 0;
+            s_id[i] = id;
+            s_keep[i] = 0;
+        }
     }
     if (tid == 0) {
         s_nkept = 0;
         s_rem = 0;
+        s_nshort = 0;
+        s_nlong = 0;
+        s_cursor = 0;
     }
-    __syncthreads();  // sort keys are dead from here on: s_kbox aliases them
+    __syncthreads();
 
     const int R = 7 + a.extra_floats;
     float* o = a.out + (size_t)b * (1 + (size_t)a.max_det * R);
     int32_t* oidx = a.keep_index ? a.keep_index + (size_t)b * a.max_det : nullptr;
-    int n_rows_out = 0;
 
     if (a.mode == TRTX_NMS_GREEDY) {
-        // ---------------- E: chunked greedy NMS ----------------
-        int n_kept = 0, ks = 0;
-        for (int c0 = 0; c0 < M; c0 += 32) {
-            const int nchunk = min(32, M - c0);
-            const int cls_first = s_cls[c0];
-            while (ks < n_kept && s_kcls[ks] < cls_first) ++ks;  // kept rows of lower classes are irrelevant
-            // (1) chunk members x kept rows of classes >= cls_first
-            const int P = 32 * (n_kept - ks);
-            for (int p = tid; p < P; p += kNmsThreads) {
-                const int i = p & 31, k = ks + (p >> 5);
-                if (i < nchunk && s_kcls[k] == s_cls[c0 + i]) {
-                    if (iou_any(a.box_format, s_kbox[k], s_box[c0 + i]) > a.nms_thresh) atomicOr(&s_rem, 1u << i);
+        // ---------------- E: class segments ----------------
+        for (int i = tid; i < M; i += kNmsThreads) {
+            if (i == 0 || s_cls[i] != s_cls[i - 1]) {
+                int e = i + 1;
+                while (e < M && s_cls[e] == s_cls[i]) ++e;
+                const int m = e - i;
+                if (m > kShortSeg)
+                    s_long[atomicAdd(&s_nlong, 1)] = (i << 16) | m;  // M <= 2048: start and length fit 16 bits
+                else
+                    s_seg[atomicAdd(&s_nshort, 1)] = (i << 16) | m;
+            }
+        }
+        __syncthreads();
+        // ---- long segments: whole CTA, chunks of 32 ----
+        const int n_long = s_nlong;
+        for (int ls = 0; ls < n_long; ++ls) {
+            const int p0 = s_long[ls] >> 16, m = s_long[ls] & 0xffff;
+            int n_kept = 0;
+            for (int c0 = 0; c0 < m; c0 += 32) {
+                const int nchunk = min(32, m - c0);
+                const int P = 32 * n_kept;
+                for (int p = tid; p < P; p += kNmsThreads) {
+                    const int i = p & 31, k = p >> 5;
+                    if (i < nchunk && iou_any(a.box_format, s_kbox[p0 + k], s_box[p0 + c0 + i]) > a.nms_thresh)
+                        atomicOr(&s_rem, 1u << i);
                 }
-            }
-            // (2) chunk members x chunk-mates: warp w <-> member w, lane j <-> earlier mate j
-            {
-                const int i = warp, j = lane;
-                bool hit = false;
-                if (i < nchunk && j < i && s_cls[c0 + j] == s_cls[c0 + i])
-                    hit = iou_any(a.box_format, s_box[c0 + j], s_box[c0 + i]) > a.nms_thresh;
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) s_sup[i] = m;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const unsigned my = s_sup[lane];
-                unsigned alive = ~s_rem & (nchunk == 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
+                {
+                    const int i = warp, jx = lane;
+                    bool hit = false;
+                    if (i < nchunk && jx < i)
+                        hit = iou_any(a.box_format, s_box[p0 + c0 + jx], s_box[p0 + c0 + i]) > a.nms_thresh;
+                    const unsigned mm = __ballot_sync(0xffffffffu, hit);
+                    if (lane == 0) s_sup[i] = mm;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    const unsigned my = s_sup[lane];
+                    unsigned alive = ~s_rem & (nchunk == 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const unsigned kill = __ballot_sync(0xffffffffu, (my >> j) & 1u);
-                    if ((alive >> j) & 1u) alive &= ~kill;
+                    for (int jx = 0; jx < 32; ++jx) {
+                        const unsigned kill = __ballot_sync(0xffffffffu, (my >> jx) & 1u);
+                        if ((alive >> jx) & 1u) alive &= ~kill;
+                    }
+                    if ((alive >> lane) & 1u) {
+                        const int pos = n_kept + __popc(alive & ((1u << lane) - 1u));
+                        s_kbox[p0 + pos] = s_box[p0 + c0 + lane];
+                        s_keep[p0 + c0 + lane] = 1;
+                    }
+                    if (lane == 0) {
+                        s_nkept = n_kept + __popc(alive);
+                        s_rem = 0;
+                    }
+                }
+                __syncthreads();
+                n_kept = s_nkept;
+            }
+        }
+        // ---- short segments: one warp each, shuffles + ballots only ----
+        const int n_short = s_nshort;
+        for (;;) {
+            int sidx = 0;
+            if (lane == 0) sidx = atomicAdd(&s_cursor, 1);
+            sidx = __shfl_sync(0xffffffffu, sidx, 0);
+            if (sidx >= n_short) break;
+            const int p0 = s_seg[sidx] >> 16, m = s_seg[sidx] & 0xffff;
+            if (m == 1) {
+                if (lane == 0) s_keep[p0] = 1;
+                continue;
+            }
+            int nk = 0;
+            for (int c0 = 0; c0 < m; c0 += 32) {
+                const int nchunk = min(32, m - c0);
+                const bool in = lane < nchunk;
+                const float4 mybox = in ? s_box[p0 + c0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                bool removed = false;
+                for (int k = 0; k < nk; ++k) {
+                    const float4 kb = s_kbox[p0 + k];  // broadcast read
+                    if (in && !removed && iou_any(a.box_format, kb, mybox) > a.nms_thresh) removed = true;
+                }
+                unsigned mymask = 0;
+                for (int jx = 0; jx + 1 < nchunk; ++jx) {
+                    float4 bj;
+                    bj.x = __shfl_sync(0xffffffffu, mybox.x, jx);
+                    bj.y = __shfl_sync(0xffffffffu, mybox.y, jx);
+                    bj.z = __shfl_sync(0xffffffffu, mybox.z, jx);
+                    bj.w = __shfl_sync(0xffffffffu, mybox.w, jx);
+                    if (in && !removed && lane > jx && iou_any(a.box_format, bj, mybox) > a.nms_thresh) mymask |= 1u << jx;
+                }
+                unsigned alive = __ballot_sync(0xffffffffu, in && !removed);
+                for (int jx = 0; jx < nchunk; ++jx) {
+                    const unsigned kill = __ballot_sync(0xffffffffu, (mymask >> jx) & 1u);
+                    if ((alive >> jx) & 1u) alive &= ~kill;
                 }
                 if ((alive >> lane) & 1u) {
-                    const int pos = n_kept + __popc(alive & ((1u << lane) - 1u));
-                    s_kbox[pos] = s_box[c0 + lane];
-                    s_kcls[pos] = s_cls[c0 + lane];
-                    s_kpos[pos] = c0 + lane;
+                    const int pos = nk + __popc(alive & ((1u << lane) - 1u));
+                    s_kbox[p0 + pos] = mybox;
+                    s_keep[p0 + c0 + lane] = 1;
                 }
-                if (lane == 0) {
-                    s_nkept = n_kept + __popc(alive);
-                    s_rem = 0;
+                nk += __popc(alive);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    } else {
+        // one-shot: dropped iff some earlier same-class row (higher conf) overlaps (postprocess.cu:89-111)
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const int ci = s_cls[i];
+            const float4 bi = s_box[i];
+            bool keep = true;
+            for (int jx = i - 1; jx >= 0 && s_cls[jx] == ci; --jx) {
+                if (iou_oneshot(bi, s_box[jx]) > a.nms_thresh) {
+                    keep = false;
+                    break;
                 }
             }
-            __syncthreads();
-            n_kept = s_nkept;
+            s_keep[i] = keep ? 1 : 0;
         }
-        // ---------------- F: kept rows, reference `res` order ----------------
-        n_rows_out = min(n_kept, a.max_det);
-        for (int k = tid; k < n_rows_out; k += kNmsThreads) {
-            const int pos = s_kpos[k];
-            const float4 bx = s_kbox[k];
+        __syncthreads();
+    }
+
+    // ---------------- F: block scan of the output flags, rows in sorted (class, conf) order ----------------
+    // greedy: only kept rows are emitted; one-shot: every row is emitted with its keep flag
+    int carry = 0;
+    for (int base = 0; base < M; base += kNmsThreads) {
+        const int i = base + tid;
+        const bool emit = i < M && (a.mode == TRTX_NMS_ONESHOT || s_keep[i]);
+        const unsigned bal = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_wsum[lane], tot;
+            const int ex = warp_excl_scan(v, lane, &tot);
+            s_wsum[lane] = ex;
+            if (lane == 0) s_nkept = tot;
+        }
+        __syncthreads();
+        const int k = carry + s_wsum[warp] + __popc(bal & ((1u << lane) - 1u));
+        if (emit && k < a.max_det) {
+            const float4 bx = s_box[i];
             float* row = o + 1 + (size_t)k * R;
             row[0] = bx.x;
             row[1] = bx.y;
             row[2] = bx.z;
             row[3] = bx.w;
-            row[4] = s_conf[pos];
-            row[5] = (float)s_cls[pos];
-            row[6] = 1.0f;
-            if (oidx) oidx[k] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[pos]) + 1].z)
-                                             : (int)s_id[pos];
-            if (a.extra_floats && !a.from_tiles) {
-                const float* src = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 +
-                                   (size_t)s_id[pos] * a.det_floats + a.extra_offset;
-                for (int e = 0; e < a.extra_floats; ++e) row[7 + e] = src[e];
-            }
-        }
-    } else {
-        // one-shot: dropped iff some earlier same-class row (higher conf) overlaps (postprocess.cu:89-111)
-        n_rows_out = min(M, a.max_det);
-        for (int i = tid; i < n_rows_out; i += kNmsThreads) {
-            const int ci = s_cls[i];
-            const float4 bi = s_box[i];
-            bool keep = true;
-            for (int j = i - 1; j >= 0 && s_cls[j] == ci; --j) {
-                if (iou_oneshot(bi, s_box[j]) > a.nms_thresh) {
-                    keep = false;
-                    break;
-                }
-            }
-            float* row = o + 1 + (size_t)i * R;
-            row[0] = bi.x;
-            row[1] = bi.y;
-            row[2] = bi.z;
-            row[3] = bi.w;
             row[4] = s_conf[i];
-            row[5] = (float)ci;
-            row[6] = keep ? 1.0f : 0.0f;
-            if (oidx) oidx[i] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[i]) + 1].z)
+            row[5] = (float)s_cls[i];
+            row[6] = s_keep[i] ? 1.0f : 0.0f;
+            if (oidx) oidx[k] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[i]) + 1].z)
                                              : (int)s_id[i];
             if (a.extra_floats && !a.from_tiles) {
                 const float* src = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 +
@@ -425,7 +539,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 for (int e = 0; e < a.extra_floats; ++e) row[7 + e] = src[e];
             }
         }
+        carry += s_nkept;
+        __syncthreads();
     }
+    const int n_rows_out = min(carry, a.max_det);
     if (tid == 0) o[0] = (float)n_rows_out;
     // rows >= count are zero (the reference memsets its decode buffer, yolov8_det.cpp:106)
     for (int i = n_rows_out * R + tid; i < a.max_det * R; i += kNmsThreads) o[1 + i] = 0.0f;
@@ -435,7 +552,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 
 static size_t nms_smem_bytes(int pre_topk) {
     const size_t S = pre_topk <= 1024 ? 1024 : kMaxSort;
-    return S * (8 + 8 + 16 + 4 + 4 + 4 + 4 + 4);
+    return S * (8 + 8 + 16 + 4 + 4 + 4 + 4 + 2 + 1) + 64;
 }
 
 static int nms_validate(const trtx_nms_params* q) {

@@ -1,10 +1,12 @@
 // yolo_scan_pipe.cu -- the YoloLayer scan as a persistent, TMA-fed pipeline (sm_100a).
 //
-// One CTA per SM, resident for the whole launch.  A producer warp streams tiles of the level tensors
-// (all C channel rows x 128 anchors, 43 KB for YOLOv8 fp32) into a ring of shared-memory stages with
-// bulk asynchronous copies (cp.async.bulk.shared::cluster.global, one per channel row, completion
-// counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and ~170 KB per
-// SM are in flight from the first cycle).  NCONS consumer warps each scan a slice of the class rows
+// One CTA per SM, resident for the whole launch.  A producer thread streams tiles of the level tensors
+// (all C channel rows x 128 anchors, 43 KB for YOLOv8 fp32) into a ring of shared-memory stages with ONE
+// TMA tensor copy per tile (cp.async.bulk.tensor.3d over a [B, C, g] tensor map, box [1, C, 128],
+// completion counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and
+// ~170 KB per SM are in flight from the first cycle; columns past the end of a level are zero-filled
+// by the engine).  (A first version issued one 512-byte cp.async.bulk per channel row: 84 descriptors
+// per tile throttled the copy engine to 1.7 TB/s -- profiles/r01b_sweep.log.)  NCONS consumer warps each scan a slice of the class rows
 // out of shared memory (conflict-free 128-bit LDS), hand their partial (max sigmoid, first argmax) to
 // the tile's epilogue warp through shared memory + a named barrier, and release the stage through
 // an "empty" mbarrier.  The epilogue (gate, warp-scan compaction, box decode from the 4 box rows that
@@ -13,6 +15,8 @@
 //
 // The arithmetic is the same bit-exact running-max scheme as yolo_decode.cu::scan_classes.
 // HBM traffic = algorithmic bytes (every row is read exactly once); candidates add <= 4%.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "yolo_layout.cuh"
 
 namespace trtx {
@@ -46,13 +50,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                 : "memory");
     } while (!done);
 }
-// global -> shared bulk copy, bytes counted on `bar` (size and both addresses multiples of 16)
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+// TMA: global [B, C, g] box -> shared, bytes counted on `bar`
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                    smem_u32(dst_smem)),
+            "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+            : "memory");
 }
+struct alignas(64) TmaMaps {
+    CUtensorMap m[TRTX_MAX_LEVELS];
+};
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -101,7 +109,8 @@ struct StageScratch {
 
 template <typename T, int NCONS>
 __global__ void __launch_bounds__(32 * (NCONS + 1), 1)
-        yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, int total_tiles, int stages, int stage_bytes) {
+        yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, const __grid_constant__ TmaMaps maps, int total_tiles,
+                                 int stages, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -120,21 +129,19 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), 1)
     __syncthreads();
 
     if (warp == NCONS) {
-        // ------------------------------ producer warp ------------------------------
-        int it = 0;
-        for (int Tg = blockIdx.x; Tg < total_tiles; Tg += gridDim.x, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = (uint32_t)(it / stages) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            const TileRef r = tile_ref(a, Tg);
-            const LevelArg& L = a.lv[r.l];
-            const uint32_t row_bytes = (uint32_t)r.ncols * sizeof(T);
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], row_bytes * (uint32_t)a.C);
-            __syncwarp();
-            const T* src = reinterpret_cast<const T*>(L.in) + ((size_t)r.b * a.C) * L.g + r.col0;
-            unsigned char* dst = stage_base + (size_t)s * stage_bytes;
-            for (int row = lane; row < a.C; row += 32)
-                bulk_g2s(dst + (size_t)row * kTileAnchors * sizeof(T), src + (size_t)row * L.g, row_bytes, &full_bar[s]);
+        // ------------------------------ producer (one elected thread) ------------------------------
+        if (lane == 0) {
+            int it = 0;
+            for (int Tg = blockIdx.x; Tg < total_tiles; Tg += gridDim.x, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                const TileRef r = tile_ref(a, Tg);
+                unsigned char* dst = stage_base + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);  // OOB columns are zero-filled and counted
+                for (int ch = 0; ch < a.C; ch += 256)                          // TMA box dims are limited to 256
+                    tma_load_3d(dst + (size_t)ch * kTileAnchors * sizeof(T), &maps.m[r.l], r.col0, ch, r.b, &full_bar[s]);
+            }
         }
         return;
     }
@@ -254,8 +261,25 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), 1)
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encoder() {
+    static EncodeTiledFn fn = nullptr;  // process-wide driver entry point; resolving it twice is harmless
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
 template <typename T, int NCONS>
 static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaStream_t st) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return TRTX_ERR_UNSUPPORTED;
     int dev = 0, sms = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -266,11 +290,23 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     while (stages >= 2 && (size_t)stages * (stage_bytes + sizeof(StageScratch<NCONS>)) + fixed + 128 > (size_t)max_smem) --stages;
     if (stages < 2) return TRTX_ERR_UNSUPPORTED;
     const size_t smem = (size_t)stages * (stage_bytes + sizeof(StageScratch<NCONS>)) + fixed;
+    TmaMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int l = 0; l < a.num_levels; ++l) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)a.lv[l].g, (cuuint64_t)a.C, (cuuint64_t)batch};
+        const cuuint64_t gstr[2] = {(cuuint64_t)a.lv[l].g * sizeof(T), (cuuint64_t)a.C * a.lv[l].g * sizeof(T)};
+        const cuuint32_t box[3] = {(cuuint32_t)kTileAnchors, (cuuint32_t)(a.C < 256 ? a.C : 256), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = enc(&maps.m[l], sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                               const_cast<void*>(a.lv[l].in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return TRTX_ERR_UNSUPPORTED;  // caller falls back to the register-path scan
+    }
     const int total_tiles = batch * L.tiles_per_image;
     const int grid = total_tiles < sms ? total_tiles : sms;
     auto kern = yolo_v8_scan_pipe_kernel<T, NCONS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 32 * (NCONS + 1), smem, st>>>(a, total_tiles, stages, stage_bytes);
+    kern<<<grid, 32 * (NCONS + 1), smem, st>>>(a, maps, total_tiles, stages, stage_bytes);
     return check_launch();
 }
 
@@ -279,11 +315,12 @@ void yolo_pipe_set_consumers(int n) { g_pipe_consumers = n; }
 
 int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
     if (a.variant != TRTX_YOLO_V8 || L.vec != 4 || L.tile_cells != kTileAnchors) return TRTX_ERR_UNSUPPORTED;
-    // bulk copies need 16-byte rows: fp32 rows are (g % 4 == 0 => ok); fp16 rows need g % 8 == 0
+    // TMA needs 16-byte aligned bases and strides: fp32 rows are (g % 4 == 0 => ok); fp16 rows need g % 8 == 0
     for (int l = 0; l < a.num_levels; ++l) {
-        if (in_dtype == TRTX_F16 && (a.lv[l].g % 8 != 0 || reinterpret_cast<uintptr_t>(a.lv[l].in) % 16 != 0))
-            return TRTX_ERR_UNSUPPORTED;
+        if (reinterpret_cast<uintptr_t>(a.lv[l].in) % 16 != 0) return TRTX_ERR_UNSUPPORTED;
+        if (in_dtype == TRTX_F16 && a.lv[l].g % 8 != 0) return TRTX_ERR_UNSUPPORTED;
     }
+    if (a.C > 256 && (a.C % 256) != 0) return TRTX_ERR_UNSUPPORTED;  // keep the expect_tx byte count exact
     if (in_dtype == TRTX_F32) {
         if (g_pipe_consumers == 4) return launch_pipe<float, 4>(a, L, batch, st);
         return launch_pipe<float, 8>(a, L, batch, st);
