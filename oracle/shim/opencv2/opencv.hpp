@@ -6,6 +6,7 @@
 // Drawing / resizing entry points are declared and abort if ever called.
 #pragma once
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <numeric>
 #include <memory>

@@ -5,13 +5,17 @@
 // TMA tensor copy per tile (cp.async.bulk.tensor.3d over a [B, C, g] tensor map, box [1, C, 128],
 // completion counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and
 // ~170 KB per SM are in flight from the first cycle; columns past the end of a level are zero-filled
-// by the engine).  (A first version issued one 512-byte cp.async.bulk per channel row: 84 descriptors
-// per tile throttled the copy engine to 1.7 TB/s -- profiles/r01b_sweep.log.)  NCONS consumer warps each scan a slice of the class rows
-// out of shared memory (conflict-free 128-bit LDS), hand their partial (max sigmoid, first argmax) to
-// the tile's epilogue warp through shared memory + a named barrier, and release the stage through
-// an "empty" mbarrier.  The epilogue (gate, warp-scan compaction, box decode from the 4 box rows that
-// are already in shared memory, 32-byte candidate records) rotates over the consumer warps so no
-// single warp becomes the per-tile bottleneck.
+// by the engine).  Every stage has its OWN consumer warp: warp w waits for stage w, scans all class
+// rows of its 128 anchors out of shared memory (conflict-free 128-bit LDS, 4 anchors per lane), gates,
+// compacts with a warp scan, decodes the boxes from the 4 box rows that are already in the stage, writes
+// the 32-byte candidate records and releases the stage.  Consumers never synchronise with each other, so
+// the stages are processed concurrently and the TMA latency of one stage hides behind the others.
+//
+// Two earlier layouts are kept in the history for the record (profiles/r01b_sweep.log, r01c_sweep.log):
+// one 512-byte cp.async.bulk per channel row (84 descriptors per tile throttle the copy engine to
+// 1.7 TB/s) and one tensor copy per tile but all consumer warps cooperating on each tile (tiles are
+// then processed strictly one after another and the per-tile latency chain caps it at 2.2 TB/s).
+// tools/tma_bench.cu measures the copy-engine ceiling of this access pattern: 5.3 TB/s.
 //
 // The arithmetic is the same bit-exact running-max scheme as yolo_decode.cu::scan_classes.
 // HBM traffic = algorithmic bytes (every row is read exactly once); candidates add <= 4%.
@@ -61,13 +65,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* m
 struct alignas(64) TmaMaps {
     CUtensorMap m[TRTX_MAX_LEVELS];
 };
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 template <typename T>
 __device__ __forceinline__ float4 lds4(const T* p);
 template <>
@@ -98,37 +95,27 @@ __device__ __forceinline__ TileRef tile_ref(const YoloArgs& a, int T) {
     return r;
 }
 
-// scratch per stage: partial results of every consumer warp
-template <int NCONS>
-struct StageScratch {
-    float p[NCONS][kTileAnchors];
-    int c[NCONS][kTileAnchors];
-    int any[NCONS];
-    int pad[4];
-};
-
-template <typename T, int NCONS>
-__global__ void __launch_bounds__(32 * (NCONS + 1), 1)
+template <typename T>
+__global__ void __launch_bounds__(32 * (kMaxStages + 1), 1)
         yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, const __grid_constant__ TmaMaps maps, int total_tiles,
                                  int stages, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
-    StageScratch<NCONS>* scratch = reinterpret_cast<StageScratch<NCONS>*>(empty_bar + kMaxStages);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);       // producer's arrive.expect_tx
-            mbar_init(&empty_bar[s], NCONS);  // one arrive per consumer warp
+            mbar_init(&full_bar[s], 1);   // producer's arrive.expect_tx
+            mbar_init(&empty_bar[s], 1);  // the stage's consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == NCONS) {
+    if (warp == stages) {
         // ------------------------------ producer (one elected thread) ------------------------------
         if (lane == 0) {
             int it = 0;
@@ -146,20 +133,15 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), 1)
         return;
     }
 
-    // ------------------------------ consumer warps ------------------------------
-    const int per = (a.nc + NCONS - 1) / NCONS;
-    const int c0 = min(a.nc, warp * per);
-    const int c1 = min(a.nc, c0 + per);
-    int it = 0;
-    for (int Tg = blockIdx.x; Tg < total_tiles; Tg += gridDim.x, ++it) {
-        const int s = it % stages;
+    // ------------------------------ consumer warp `warp` owns stage `warp` ------------------------------
+    const int s = warp;
+    const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * stage_bytes);
+    int it = s;
+    for (int Tg = blockIdx.x + s * gridDim.x; Tg < total_tiles; Tg += stages * gridDim.x, it += stages) {
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         const TileRef r = tile_ref(a, Tg);
         const LevelArg& L = a.lv[r.l];
         const bool active = lane * 4 < r.ncols;
-        const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * stage_bytes);
-        StageScratch<NCONS>& sc = scratch[s];
-        const int epi = it % NCONS;  // this tile's epilogue warp
 
         mbar_wait(&full_bar[s], ph);
         Best<4> st;
@@ -170,96 +152,69 @@ __global__ void __launch_bounds__(32 * (NCONS + 1), 1)
             st.bc[j] = 0;
         }
         if (active) {
-            const T* p = tile + (size_t)(4 + c0) * kTileAnchors + lane * 4;
-#pragma unroll 4
-            for (int c = c0; c < c1; ++c, p += kTileAnchors) {
-                const float4 v = lds4<T>(p);
-                const bool any = (v.x > st.bx[0]) | (v.y > st.bx[1]) | (v.z > st.bx[2]) | (v.w > st.bx[3]);
-                if (any) {
-                    update_one<4>(st, 0, v.x, c);
-                    update_one<4>(st, 1, v.y, c);
-                    update_one<4>(st, 2, v.z, c);
-                    update_one<4>(st, 3, v.w, c);
+            const T* p = tile + (size_t)4 * kTileAnchors + lane * 4;
+            constexpr int U = 8;
+            int c = 0;
+            for (; c + U <= a.nc; c += U, p += U * kTileAnchors) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = lds4<T>(p + u * kTileAnchors);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool any = (v[u].x > st.bx[0]) | (v[u].y > st.bx[1]) | (v[u].z > st.bx[2]) | (v[u].w > st.bx[3]);
+                    if (any) {
+                        update_one<4>(st, 0, v[u].x, c + u);
+                        update_one<4>(st, 1, v[u].y, c + u);
+                        update_one<4>(st, 2, v[u].z, c + u);
+                        update_one<4>(st, 3, v[u].w, c + u);
+                    }
                 }
             }
+            for (; c < a.nc; ++c, p += kTileAnchors) {
+                const float4 v = lds4<T>(p);
+                update_one<4>(st, 0, v.x, c);
+                update_one<4>(st, 1, v.y, c);
+                update_one<4>(st, 2, v.z, c);
+                update_one<4>(st, 3, v.w, c);
+            }
         }
-        bool mine = false;
+        unsigned flags = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mine |= !(st.bp[j] < a.gate);
-        const bool warp_any = __any_sync(0xffffffffu, mine);
-        if (warp_any) {
+        for (int j = 0; j < 4; ++j)
+            if (active && !(st.bp[j] < a.gate)) flags |= 1u << j;  // yololayer.cu:203
+        int total;
+        int off = warp_excl_scan(__popc(flags), lane, &total);
+        if (lane == 0) a.tile_count[(size_t)r.b * a.tiles_per_image + r.t] = total;
+        if (flags) {
+            const float4 d0 = lds4<T>(tile + 0 * kTileAnchors + lane * 4);
+            const float4 d1 = lds4<T>(tile + 1 * kTileAnchors + lane * 4);
+            const float4 d2 = lds4<T>(tile + 2 * kTileAnchors + lane * 4);
+            const float4 d3 = lds4<T>(tile + 3 * kTileAnchors + lane * 4);
+            const float dd[4][4] = {{d0.x, d0.y, d0.z, d0.w}, {d1.x, d1.y, d1.z, d1.w},
+                                    {d2.x, d2.y, d2.z, d2.w}, {d3.x, d3.y, d3.z, d3.w}};
+            const size_t slot0 = (size_t)r.b * a.slots_per_image + L.slot_begin + (size_t)r.col0;
+            const float fs = (float)L.stride;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                sc.p[warp][lane * 4 + j] = st.bp[j];
-                sc.c[warp][lane * 4 + j] = st.bc[j];
-            }
-        }
-        if (lane == 0) sc.any[warp] = warp_any ? 1 : 0;
-
-        if (warp != epi) {
-            named_bar_arrive(1 + s, NCONS * 32);  // publish partials; do not wait for the epilogue
-        } else {
-            named_bar_sync(1 + s, NCONS * 32);
-            int any_mask = 0;
-#pragma unroll
-            for (int w = 0; w < NCONS; ++w) any_mask |= sc.any[w] << w;
-            unsigned flags = 0;
-            if (any_mask) {
-                // combine in ascending class-slice order; strict > keeps the FIRST class with the max prob
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    st.bp[j] = 0.0f;
-                    st.bc[j] = 0;
-                }
-#pragma unroll
-                for (int w = 0; w < NCONS; ++w) {
-                    if ((any_mask >> w) & 1) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float p2 = sc.p[w][lane * 4 + j];
-                            if (p2 > st.bp[j]) {
-                                st.bp[j] = p2;
-                                st.bc[j] = sc.c[w][lane * 4 + j];
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (active && !(st.bp[j] < a.gate)) flags |= 1u << j;  // yololayer.cu:203
-            }
-            int total;
-            int off = warp_excl_scan(__popc(flags), lane, &total);
-            if (lane == 0) a.tile_count[(size_t)r.b * a.tiles_per_image + r.t] = total;
-            if (flags) {
-                const float4 d0 = lds4<T>(tile + 0 * kTileAnchors + lane * 4);
-                const float4 d1 = lds4<T>(tile + 1 * kTileAnchors + lane * 4);
-                const float4 d2 = lds4<T>(tile + 2 * kTileAnchors + lane * 4);
-                const float4 d3 = lds4<T>(tile + 3 * kTileAnchors + lane * 4);
-                const float dd[4][4] = {{d0.x, d0.y, d0.z, d0.w}, {d1.x, d1.y, d1.z, d1.w},
-                                        {d2.x, d2.y, d2.z, d2.w}, {d3.x, d3.y, d3.z, d3.w}};
-                const size_t slot0 = (size_t)r.b * a.slots_per_image + L.slot_begin + (size_t)r.col0;
-                const float fs = (float)L.stride;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (flags & (1u << j)) {
-                        const int e = r.col0 + lane * 4 + j;
-                        const int row = e / L.gw, col = e - row * L.gw;
-                        // yololayer.cu:217-220
-                        const float x1 = ((float)col + 0.5f - dd[0][j]) * fs;
-                        const float y1 = ((float)row + 0.5f - dd[1][j]) * fs;
-                        const float x2 = ((float)col + 0.5f + dd[2][j]) * fs;
-                        const float y2 = ((float)row + 0.5f + dd[3][j]) * fs;
-                        store_record(a.cand, slot0 + off, x1, y1, x2, y2, st.bp[j], st.bc[j], L.slot_begin + e);
-                        ++off;
-                    }
+                if (flags & (1u << j)) {
+                    const int e = r.col0 + lane * 4 + j;
+                    const int row = e / L.gw, col = e - row * L.gw;
+                    // yololayer.cu:217-220
+                    const float x1 = ((float)col + 0.5f - dd[0][j]) * fs;
+                    const float y1 = ((float)row + 0.5f - dd[1][j]) * fs;
+                    const float x2 = ((float)col + 0.5f + dd[2][j]) * fs;
+                    const float y2 = ((float)row + 0.5f + dd[3][j]) * fs;
+                    store_record(a.cand, slot0 + off, x1, y1, x2, y2, st.bp[j], st.bc[j], L.slot_begin + e);
+                    ++off;
                 }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage (and its scratch)
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // stage free: the producer may refill it
     }
 }
+
+static int g_pipe_max_stages = kMaxStages;  // tuning knob 3: cap on stages (= consumer warps)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -276,7 +231,7 @@ static EncodeTiledFn get_encoder() {
     return fn;
 }
 
-template <typename T, int NCONS>
+template <typename T>
 static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaStream_t st) {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return TRTX_ERR_UNSUPPORTED;
@@ -286,10 +241,10 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int stage_bytes = a.C * kTileAnchors * (int)sizeof(T);
     const int fixed = 2 * kMaxStages * (int)sizeof(uint64_t);
-    int stages = kMaxStages;
-    while (stages >= 2 && (size_t)stages * (stage_bytes + sizeof(StageScratch<NCONS>)) + fixed + 128 > (size_t)max_smem) --stages;
+    int stages = g_pipe_max_stages < kMaxStages ? g_pipe_max_stages : kMaxStages;
+    while (stages >= 2 && (size_t)stages * stage_bytes + fixed + 128 > (size_t)max_smem) --stages;
     if (stages < 2) return TRTX_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)stages * (stage_bytes + sizeof(StageScratch<NCONS>)) + fixed;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
     TmaMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int l = 0; l < a.num_levels; ++l) {
@@ -304,14 +259,13 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     }
     const int total_tiles = batch * L.tiles_per_image;
     const int grid = total_tiles < sms ? total_tiles : sms;
-    auto kern = yolo_v8_scan_pipe_kernel<T, NCONS>;
+    auto kern = yolo_v8_scan_pipe_kernel<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 32 * (NCONS + 1), smem, st>>>(a, maps, total_tiles, stages, stage_bytes);
+    kern<<<grid, 32 * (stages + 1), smem, st>>>(a, maps, total_tiles, stages, stage_bytes);
     return check_launch();
 }
 
-static int g_pipe_consumers = 8;
-void yolo_pipe_set_consumers(int n) { g_pipe_consumers = n; }
+void yolo_pipe_set_consumers(int n) { g_pipe_max_stages = n < 2 ? 2 : n; }
 
 int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
     if (a.variant != TRTX_YOLO_V8 || L.vec != 4 || L.tile_cells != kTileAnchors) return TRTX_ERR_UNSUPPORTED;
@@ -321,12 +275,8 @@ int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, 
         if (in_dtype == TRTX_F16 && a.lv[l].g % 8 != 0) return TRTX_ERR_UNSUPPORTED;
     }
     if (a.C > 256 && (a.C % 256) != 0) return TRTX_ERR_UNSUPPORTED;  // keep the expect_tx byte count exact
-    if (in_dtype == TRTX_F32) {
-        if (g_pipe_consumers == 4) return launch_pipe<float, 4>(a, L, batch, st);
-        return launch_pipe<float, 8>(a, L, batch, st);
-    }
-    if (g_pipe_consumers == 4) return launch_pipe<__half, 4>(a, L, batch, st);
-    return launch_pipe<__half, 8>(a, L, batch, st);
+    if (in_dtype == TRTX_F32) return launch_pipe<float>(a, L, batch, st);
+    return launch_pipe<__half>(a, L, batch, st);
 }
 
 }  // namespace trtx

@@ -10,6 +10,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <cassert>
+#include <cfloat>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -17,11 +19,24 @@
 #include <string>
 #include <utility>
 
-#define NV_TENSORRT_MAJOR 8
+// The reference's rcnn plugins override some virtuals WITHOUT noexcept (rcnn/BatchedNmsPlugin.h:46), i.e.
+// they only compile against the TensorRT 7 flavour of the interfaces; everything else targets TensorRT 8.
+// -DTRTX_MOCK_TRT_MAJOR=7 selects the pre-noexcept / non-const-enqueue flavour.
+#ifndef TRTX_MOCK_TRT_MAJOR
+#define TRTX_MOCK_TRT_MAJOR 8
+#endif
+#define NV_TENSORRT_MAJOR TRTX_MOCK_TRT_MAJOR
 #define NV_TENSORRT_MINOR 6
 #define NV_TENSORRT_PATCH 1
-#define NV_TENSORRT_VERSION 8601
+#define NV_TENSORRT_VERSION (TRTX_MOCK_TRT_MAJOR * 1000 + 601)
 #define TRTX_MOCK_TENSORRT 1
+#if TRTX_MOCK_TRT_MAJOR >= 8
+#define TRTX_NX noexcept
+#define TRTX_CE const
+#else
+#define TRTX_NX
+#define TRTX_CE
+#endif
 
 struct cudnnContext;
 struct cublasContext;
@@ -107,7 +122,7 @@ class PluginField {
     PluginFieldType type;
     int32_t length;
     PluginField(const AsciiChar* const name_ = nullptr, const void* const data_ = nullptr,
-                const PluginFieldType type_ = PluginFieldType::kUNKNOWN, int32_t length_ = 0) noexcept
+                const PluginFieldType type_ = PluginFieldType::kUNKNOWN, int32_t length_ = 0) TRTX_NX
         : name(name_), data(data_), type(type_), length(length_) {}
 };
 struct PluginFieldCollection {
@@ -117,23 +132,49 @@ struct PluginFieldCollection {
 
 class IGpuAllocator;
 
+// --- just enough of the builder API for the reference helper headers that are included by the files
+//     under test (retinaface/common.hpp: loadWeights / addBatchNorm2d) to COMPILE; never instantiated ---
+class Weights {
+   public:
+    DataType type;
+    const void* values;
+    int64_t count;
+};
+enum class ScaleMode : int32_t { kUNIFORM = 0, kCHANNEL = 1, kELEMENTWISE = 2 };
+class ITensor;
+class ILayer {
+   public:
+    virtual ITensor* getOutput(int32_t index) const TRTX_NX = 0;
+
+   protected:
+    virtual ~ILayer() TRTX_NX = default;
+};
+class IScaleLayer : public ILayer {};
+class INetworkDefinition {
+   public:
+    virtual IScaleLayer* addScale(ITensor& input, ScaleMode mode, Weights shift, Weights scale, Weights power) TRTX_NX = 0;
+
+   protected:
+    virtual ~INetworkDefinition() TRTX_NX = default;
+};
+
 enum class DimensionOperation : int32_t { kSUM = 0, kPROD = 1, kMAX = 2, kMIN = 3, kSUB = 4, kEQUAL = 5, kLESS = 6, kFLOOR_DIV = 7, kCEIL_DIV = 8 };
 class IDimensionExpr {
    public:
-    virtual bool isConstant() const noexcept = 0;
-    virtual int32_t getConstantValue() const noexcept = 0;
+    virtual bool isConstant() const TRTX_NX = 0;
+    virtual int32_t getConstantValue() const TRTX_NX = 0;
 
    protected:
-    virtual ~IDimensionExpr() noexcept = default;
+    virtual ~IDimensionExpr() TRTX_NX = default;
 };
 class IExprBuilder {
    public:
-    virtual const IDimensionExpr* constant(int32_t value) noexcept = 0;
+    virtual const IDimensionExpr* constant(int32_t value) TRTX_NX = 0;
     virtual const IDimensionExpr* operation(DimensionOperation op, const IDimensionExpr& first,
-                                            const IDimensionExpr& second) noexcept = 0;
+                                            const IDimensionExpr& second) TRTX_NX = 0;
 
    protected:
-    virtual ~IExprBuilder() noexcept = default;
+    virtual ~IExprBuilder() TRTX_NX = default;
 };
 class DimsExprs {
    public:
@@ -144,97 +185,97 @@ class DimsExprs {
 // ---------------------------------------------------------------------------------------------
 class IPluginV2 {
    public:
-    virtual int32_t getTensorRTVersion() const noexcept { return NV_TENSORRT_VERSION; }
-    virtual const AsciiChar* getPluginType() const noexcept = 0;
-    virtual const AsciiChar* getPluginVersion() const noexcept = 0;
-    virtual int32_t getNbOutputs() const noexcept = 0;
-    virtual Dims getOutputDimensions(int32_t index, const Dims* inputs, int32_t nbInputDims) noexcept = 0;
-    virtual bool supportsFormat(DataType type, PluginFormat format) const noexcept = 0;
+    virtual int32_t getTensorRTVersion() const TRTX_NX { return NV_TENSORRT_VERSION; }
+    virtual const AsciiChar* getPluginType() const TRTX_NX = 0;
+    virtual const AsciiChar* getPluginVersion() const TRTX_NX = 0;
+    virtual int32_t getNbOutputs() const TRTX_NX = 0;
+    virtual Dims getOutputDimensions(int32_t index, const Dims* inputs, int32_t nbInputDims) TRTX_NX = 0;
+    virtual bool supportsFormat(DataType type, PluginFormat format) const TRTX_NX = 0;
     virtual void configureWithFormat(const Dims* inputDims, int32_t nbInputs, const Dims* outputDims, int32_t nbOutputs,
-                                     DataType type, PluginFormat format, int32_t maxBatchSize) noexcept = 0;
-    virtual int32_t initialize() noexcept = 0;
-    virtual void terminate() noexcept = 0;
-    virtual size_t getWorkspaceSize(int32_t maxBatchSize) const noexcept = 0;
-    virtual int32_t enqueue(int32_t batchSize, const void* const* inputs, void* const* outputs, void* workspace,
-                            cudaStream_t stream) noexcept = 0;
-    virtual size_t getSerializationSize() const noexcept = 0;
-    virtual void serialize(void* buffer) const noexcept = 0;
-    virtual void destroy() noexcept = 0;
-    virtual IPluginV2* clone() const noexcept = 0;
-    virtual void setPluginNamespace(const AsciiChar* pluginNamespace) noexcept = 0;
-    virtual const AsciiChar* getPluginNamespace() const noexcept = 0;
+                                     DataType type, PluginFormat format, int32_t maxBatchSize) TRTX_NX = 0;
+    virtual int32_t initialize() TRTX_NX = 0;
+    virtual void terminate() TRTX_NX = 0;
+    virtual size_t getWorkspaceSize(int32_t maxBatchSize) const TRTX_NX = 0;
+    virtual int32_t enqueue(int32_t batchSize, const void* const* inputs, void* TRTX_CE* outputs, void* workspace,
+                            cudaStream_t stream) TRTX_NX = 0;
+    virtual size_t getSerializationSize() const TRTX_NX = 0;
+    virtual void serialize(void* buffer) const TRTX_NX = 0;
+    virtual void destroy() TRTX_NX = 0;
+    virtual IPluginV2* clone() const TRTX_NX = 0;
+    virtual void setPluginNamespace(const AsciiChar* pluginNamespace) TRTX_NX = 0;
+    virtual const AsciiChar* getPluginNamespace() const TRTX_NX = 0;
 
     IPluginV2() = default;
-    virtual ~IPluginV2() noexcept = default;
+    virtual ~IPluginV2() TRTX_NX = default;
 };
 
 class IPluginV2Ext : public IPluginV2 {
    public:
-    virtual DataType getOutputDataType(int32_t index, const DataType* inputTypes, int32_t nbInputs) const noexcept = 0;
+    virtual DataType getOutputDataType(int32_t index, const DataType* inputTypes, int32_t nbInputs) const TRTX_NX = 0;
     virtual bool isOutputBroadcastAcrossBatch(int32_t outputIndex, const bool* inputIsBroadcasted,
-                                              int32_t nbInputs) const noexcept = 0;
-    virtual bool canBroadcastInputAcrossBatch(int32_t inputIndex) const noexcept = 0;
+                                              int32_t nbInputs) const TRTX_NX = 0;
+    virtual bool canBroadcastInputAcrossBatch(int32_t inputIndex) const TRTX_NX = 0;
     virtual void configurePlugin(const Dims* inputDims, int32_t nbInputs, const Dims* outputDims, int32_t nbOutputs,
                                  const DataType* inputTypes, const DataType* outputTypes, const bool* inputIsBroadcast,
-                                 const bool* outputIsBroadcast, PluginFormat floatFormat, int32_t maxBatchSize) noexcept = 0;
-    virtual void attachToContext(cudnnContext*, cublasContext*, IGpuAllocator*) noexcept {}
-    virtual void detachFromContext() noexcept {}
-    IPluginV2Ext* clone() const noexcept override = 0;
+                                 const bool* outputIsBroadcast, PluginFormat floatFormat, int32_t maxBatchSize) TRTX_NX = 0;
+    virtual void attachToContext(cudnnContext*, cublasContext*, IGpuAllocator*) TRTX_NX {}
+    virtual void detachFromContext() TRTX_NX {}
+    IPluginV2Ext* clone() const TRTX_NX override = 0;
 
    protected:
-    void configureWithFormat(const Dims*, int32_t, const Dims*, int32_t, DataType, PluginFormat, int32_t) noexcept override {}
+    void configureWithFormat(const Dims*, int32_t, const Dims*, int32_t, DataType, PluginFormat, int32_t) TRTX_NX override {}
 };
 
 class IPluginV2IOExt : public IPluginV2Ext {
    public:
     virtual void configurePlugin(const PluginTensorDesc* in, int32_t nbInput, const PluginTensorDesc* out,
-                                 int32_t nbOutput) noexcept = 0;
+                                 int32_t nbOutput) TRTX_NX = 0;
     virtual bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* inOut, int32_t nbInputs,
-                                           int32_t nbOutputs) const noexcept = 0;
+                                           int32_t nbOutputs) const TRTX_NX = 0;
 
    private:
     void configurePlugin(const Dims*, int32_t, const Dims*, int32_t, const DataType*, const DataType*, const bool*,
-                         const bool*, PluginFormat, int32_t) noexcept final {}
-    bool supportsFormat(DataType, PluginFormat) const noexcept final { return false; }
+                         const bool*, PluginFormat, int32_t) TRTX_NX final {}
+    bool supportsFormat(DataType, PluginFormat) const TRTX_NX final { return false; }
 };
 
 class IPluginV2DynamicExt : public IPluginV2Ext {
    public:
-    IPluginV2DynamicExt* clone() const noexcept override = 0;
+    IPluginV2DynamicExt* clone() const TRTX_NX override = 0;
     virtual DimsExprs getOutputDimensions(int32_t outputIndex, const DimsExprs* inputs, int32_t nbInputs,
-                                          IExprBuilder& exprBuilder) noexcept = 0;
+                                          IExprBuilder& exprBuilder) TRTX_NX = 0;
     virtual bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* inOut, int32_t nbInputs,
-                                           int32_t nbOutputs) noexcept = 0;
+                                           int32_t nbOutputs) TRTX_NX = 0;
     virtual void configurePlugin(const DynamicPluginTensorDesc* in, int32_t nbInputs, const DynamicPluginTensorDesc* out,
-                                 int32_t nbOutputs) noexcept = 0;
+                                 int32_t nbOutputs) TRTX_NX = 0;
     virtual size_t getWorkspaceSize(const PluginTensorDesc* inputs, int32_t nbInputs, const PluginTensorDesc* outputs,
-                                    int32_t nbOutputs) const noexcept = 0;
+                                    int32_t nbOutputs) const TRTX_NX = 0;
     virtual int32_t enqueue(const PluginTensorDesc* inputDesc, const PluginTensorDesc* outputDesc,
-                            const void* const* inputs, void* const* outputs, void* workspace,
-                            cudaStream_t stream) noexcept = 0;
+                            const void* const* inputs, void* TRTX_CE* outputs, void* workspace,
+                            cudaStream_t stream) TRTX_NX = 0;
 
    private:
     // implicit-batch entry points are sealed off, as in TensorRT
-    Dims getOutputDimensions(int32_t, const Dims*, int32_t) noexcept final { return Dims{-1, {}}; }
-    bool isOutputBroadcastAcrossBatch(int32_t, const bool*, int32_t) const noexcept final { return false; }
-    bool canBroadcastInputAcrossBatch(int32_t) const noexcept final { return true; }
-    bool supportsFormat(DataType, PluginFormat) const noexcept final { return false; }
+    Dims getOutputDimensions(int32_t, const Dims*, int32_t) TRTX_NX final { return Dims{-1, {}}; }
+    bool isOutputBroadcastAcrossBatch(int32_t, const bool*, int32_t) const TRTX_NX final { return false; }
+    bool canBroadcastInputAcrossBatch(int32_t) const TRTX_NX final { return true; }
+    bool supportsFormat(DataType, PluginFormat) const TRTX_NX final { return false; }
     void configurePlugin(const Dims*, int32_t, const Dims*, int32_t, const DataType*, const DataType*, const bool*,
-                         const bool*, PluginFormat, int32_t) noexcept final {}
-    size_t getWorkspaceSize(int32_t) const noexcept final { return 0; }
-    int32_t enqueue(int32_t, const void* const*, void* const*, void*, cudaStream_t) noexcept final { return 1; }
+                         const bool*, PluginFormat, int32_t) TRTX_NX final {}
+    size_t getWorkspaceSize(int32_t) const TRTX_NX final { return 0; }
+    int32_t enqueue(int32_t, const void* const*, void* TRTX_CE*, void*, cudaStream_t) TRTX_NX final { return 1; }
 };
 
 class IPluginCreator {
    public:
-    virtual int32_t getTensorRTVersion() const noexcept { return NV_TENSORRT_VERSION; }
-    virtual const AsciiChar* getPluginName() const noexcept = 0;
-    virtual const AsciiChar* getPluginVersion() const noexcept = 0;
-    virtual const PluginFieldCollection* getFieldNames() noexcept = 0;
-    virtual IPluginV2* createPlugin(const AsciiChar* name, const PluginFieldCollection* fc) noexcept = 0;
-    virtual IPluginV2* deserializePlugin(const AsciiChar* name, const void* serialData, size_t serialLength) noexcept = 0;
-    virtual void setPluginNamespace(const AsciiChar* pluginNamespace) noexcept = 0;
-    virtual const AsciiChar* getPluginNamespace() const noexcept = 0;
+    virtual int32_t getTensorRTVersion() const TRTX_NX { return NV_TENSORRT_VERSION; }
+    virtual const AsciiChar* getPluginName() const TRTX_NX = 0;
+    virtual const AsciiChar* getPluginVersion() const TRTX_NX = 0;
+    virtual const PluginFieldCollection* getFieldNames() TRTX_NX = 0;
+    virtual IPluginV2* createPlugin(const AsciiChar* name, const PluginFieldCollection* fc) TRTX_NX = 0;
+    virtual IPluginV2* deserializePlugin(const AsciiChar* name, const void* serialData, size_t serialLength) TRTX_NX = 0;
+    virtual void setPluginNamespace(const AsciiChar* pluginNamespace) TRTX_NX = 0;
+    virtual const AsciiChar* getPluginNamespace() const TRTX_NX = 0;
     IPluginCreator() = default;
     virtual ~IPluginCreator() = default;
 };
@@ -242,12 +283,12 @@ class IPluginCreator {
 // minimal in-process registry (TensorRT's lives in libnvinfer)
 class IPluginRegistry {
    public:
-    bool registerCreator(IPluginCreator& creator, const AsciiChar* pluginNamespace) noexcept {
+    bool registerCreator(IPluginCreator& creator, const AsciiChar* pluginNamespace) TRTX_NX {
         creators()[key(creator.getPluginName(), creator.getPluginVersion(), pluginNamespace)] = &creator;
         return true;
     }
     IPluginCreator* getPluginCreator(const AsciiChar* pluginName, const AsciiChar* pluginVersion,
-                                     const AsciiChar* pluginNamespace = "") noexcept {
+                                     const AsciiChar* pluginNamespace = "") TRTX_NX {
         auto it = creators().find(key(pluginName, pluginVersion, pluginNamespace));
         return it == creators().end() ? nullptr : it->second;
     }
@@ -273,7 +314,7 @@ class PluginRegistrar {
 
 }  // namespace nvinfer1
 
-inline nvinfer1::IPluginRegistry* getPluginRegistry() noexcept {
+inline nvinfer1::IPluginRegistry* getPluginRegistry() TRTX_NX {
     static nvinfer1::IPluginRegistry r;
     return &r;
 }
@@ -285,6 +326,10 @@ PluginRegistrar<T>::PluginRegistrar() {
 }
 }  // namespace nvinfer1
 
+#ifdef TRTX_MOCK_NO_REGISTRAR  // host-only builds that include a plugin header without its .cu
+#define REGISTER_TENSORRT_PLUGIN(name) static_assert(true, "")
+#else
 #define REGISTER_TENSORRT_PLUGIN(name) static nvinfer1::PluginRegistrar<name> pluginRegistrar##name {}
+#endif
 
 #endif  // TRTX_MOCK_NVINFER_H

@@ -1,0 +1,106 @@
+"""Pins the oracle's NMS restatements against the REFERENCE's OWN host code: oracle/_ref/libref_*_host.so are
+built by oracle/Makefile from /root/reference/{yolov8,yolov5}/src/postprocess.cpp and retinaface/common.hpp,
+compiled where they lie (with header shims for the OpenCV / TensorRT includes those files pull in).
+The prebuilt libraries travel with the repo snapshot; these tests skip only if they were never built."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tensorrtx_b200 import synth
+
+REF = Path(__file__).resolve().parents[1] / "oracle" / "_ref"
+
+
+def _load(name):
+    p = REF / name
+    if not p.exists():
+        pytest.skip(f"{p} not built (run `make -C oracle` where /root/reference is mounted)")
+    return C.CDLL(str(p))
+
+
+def _ref_nms(fn, buf, F, *thr):
+    out = np.zeros((buf.shape[0] // F + 1) * F, np.float32)
+    b = np.ascontiguousarray(buf, np.float32)
+    n = fn(b.ctypes.data_as(C.c_void_p), *[C.c_float(t) for t in thr], out.ctypes.data_as(C.c_void_p))
+    return out[:n * F].reshape(n, F).copy()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_v8_nms_equals_reference(oracle, seed):
+    lib = _load("libref_yolov8_host.so")
+    assert lib.ref_v8_det_floats() == 90
+    heads = synth.yolov8_heads(2, seed=100 + seed)
+    out, _ = oracle.yolov8_decode(heads)
+    for b in range(2):
+        mine, _ = oracle.nms(0, out[b], 1000, 90, 0.5, 0.45)
+        ref = _ref_nms(lib.ref_v8_nms, out[b], 90, 0.5, 0.45)
+        assert len(ref) > 20
+        assert np.array_equal(mine, ref)  # same rows, same order (class asc, conf desc), bit for bit
+
+
+def test_v8_nms_ties_broken_by_bbox0_like_reference(oracle):
+    lib = _load("libref_yolov8_host.so")
+    rng = np.random.default_rng(1)
+    n = 400
+    buf = np.zeros(1 + 1000 * 90, np.float32)
+    rows = buf[1:1 + n * 90].reshape(n, 90)
+    xy = rng.uniform(0, 600, (n, 2))
+    wh = rng.uniform(10, 60, (n, 2))
+    rows[:, :2], rows[:, 2:4] = xy, xy + wh
+    rows[:, 4] = np.round(rng.uniform(0.5, 1.0, n), 2)  # many equal confidences, distinct bbox[0]
+    rows[:, 5] = rng.integers(0, 3, n)
+    buf[0] = n
+    mine, _ = oracle.nms(0, buf, 1000, 90, 0.5, 0.45)
+    ref = _ref_nms(lib.ref_v8_nms, buf, 90, 0.5, 0.45)
+    assert np.array_equal(mine, ref)
+
+
+def test_v8_batch_nms_and_thresholds(oracle):
+    lib = _load("libref_yolov8_host.so")
+    heads = synth.yolov8_heads(3, seed=7)
+    out, _ = oracle.yolov8_decode(heads)
+    res = np.zeros((3, 1000, 90), np.float32)
+    cnt = np.zeros(3, np.int32)
+    lib.ref_v8_batch_nms(np.ascontiguousarray(out).ctypes.data_as(C.c_void_p), 3, out.shape[1], C.c_float(0.3),
+                         C.c_float(0.6), res.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), 1000)
+    for b in range(3):
+        mine, _ = oracle.nms(0, out[b], 1000, 90, 0.3, 0.6)
+        assert cnt[b] == len(mine) and np.array_equal(res[b, :cnt[b]], mine)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_v5_nms_equals_reference(oracle, seed):
+    lib = _load("libref_yolov5_host.so")
+    assert lib.ref_v5_det_floats() == 38
+    heads = synth.yolov5_heads(1, seed=200 + seed, n_obj=200)
+    out, _ = oracle.yolov5_decode(heads, synth.V5_ANCHORS)
+    mine, _ = oracle.nms(1, out[0], 1000, 38, 0.5, 0.45)
+    ref = _ref_nms(lib.ref_v5_nms, out[0], 38, 0.5, 0.45)
+    assert len(ref) > 50 and np.array_equal(mine, ref)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_retina_nms_equals_reference(oracle, seed):
+    lib = _load("libref_retina_host.so")
+    heads = synth.retina_heads(1, seed=300 + seed, in_h=480, in_w=640, n_obj=60)
+    out, _ = oracle.retina_decode(heads, in_h=480, in_w=640)
+    tp = oracle.retina_total_priors(480, 640)
+    mine, _ = oracle.nms(2, out[0], tp, 15, 0.1, 0.4)
+    ref = _ref_nms(lib.ref_retina_nms, out[0], 15, 0.4)
+    assert len(ref) > 20 and np.array_equal(mine, ref)
+
+
+def test_retina_conf_threshold_is_a_double_compare(oracle):
+    """`output[..] <= 0.1` compares against the DOUBLE 0.1: conf == 0.1f (> 0.1) is kept (common.hpp:113)."""
+    lib = _load("libref_retina_host.so")
+    tp = oracle.retina_total_priors(480, 640)
+    buf = np.zeros(1 + tp * 15, np.float32)
+    buf[0] = 3
+    for i, c in enumerate([np.float32(0.1), np.nextafter(np.float32(0.1), np.float32(0)), np.float32(0.5)]):
+        buf[1 + i * 15:1 + i * 15 + 4] = [100 * i, 0, 100 * i + 50, 50]
+        buf[1 + i * 15 + 4] = c
+    mine, _ = oracle.nms(2, buf, tp, 15, 0.1, 0.4)
+    ref = _ref_nms(lib.ref_retina_nms, buf, 15, 0.4)
+    assert len(ref) == 2 and np.array_equal(mine, ref)

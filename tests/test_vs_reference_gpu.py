@@ -1,0 +1,228 @@
+"""Parity against the REFERENCE'S OWN CUDA KERNELS run on the same GPU: oracle/_ref/libref_*.so are the
+reference's plugin / helper sources compiled from /root/reference (oracle/Makefile) against the mock
+NvInfer.h and the OpenCV shim; tests/ only calls their public entry points (plugin enqueue(), free
+functions).  These are the strongest parity checks of the suite: same inputs, the reference's code vs ours.
+The reference's slot order is atomicAdd arrival, so decode outputs are compared as canonically sorted sets."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tensorrtx_b200 import _lib as L
+from tensorrtx_b200 import plugins as P
+from tensorrtx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+REF = Path(__file__).resolve().parents[1] / "oracle" / "_ref"
+
+
+def _load(name):
+    p = REF / name
+    if not p.exists():
+        pytest.skip(f"{p} not built")
+    return C.CDLL(str(p))
+
+
+def _ptrs(ts):
+    a = (C.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        a[i] = t.data_ptr()
+    return a
+
+
+def _canon(rows):
+    order = np.lexsort(tuple(rows[:, k] for k in range(rows.shape[1] - 1, -1, -1)))
+    return rows[order]
+
+
+def _ours_decode(plug, hd, B, dev):
+    out = torch.zeros((B, plug.output_elems()), dtype=torch.float32, device=dev)
+    ws = torch.empty(plug.getWorkspaceSize(B), dtype=torch.uint8, device=dev)
+    assert plug.enqueue(B, hd, [out], ws) == 0
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("seed,B", [(0, 1), (1, 8)])
+def test_yolov8_plugin_vs_reference_kernel(dev, seed, B):
+    lib = _load("libref_yolov8.so")
+    heads = synth.yolov8_heads(B, seed=400 + seed)
+    hd = [torch.from_numpy(h).to(dev) for h in heads]
+    ref = torch.zeros((B, 1 + 1000 * 90), dtype=torch.float32, device=dev)
+    strides = (C.c_int * 3)(8, 16, 32)
+    rc = lib.ref_v8_plugin_enqueue(80, 17, C.c_float(0.0), 640, 640, 1000, 0, 0, 0, strides, 3, B, _ptrs(hd),
+                                   C.c_void_p(ref.data_ptr()), None)
+    assert rc == 0
+    ref = ref.cpu().numpy()
+    got = _ours_decode(P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32)), hd, B, dev)
+    assert np.array_equal(ref[:, 0], got[:, 0]) and ref[:, 0].min() > 100
+    for b in range(B):
+        n = int(ref[b, 0])
+        r = _canon(ref[b, 1:1 + n * 90].reshape(n, 90)[:, :6])
+        g = _canon(got[b, 1:1 + n * 90].reshape(n, 90)[:, :6])
+        assert np.array_equal(r, g)  # same CUDA expf, same operation order: bit-exact
+
+
+@pytest.mark.parametrize("mode", ["seg", "pose", "obb"])
+def test_yolov8_plugin_extras_vs_reference_kernel(dev, mode):
+    lib = _load("libref_yolov8.so")
+    seg, pose, obb = mode == "seg", mode == "pose", mode == "obb"
+    nc = 1 if pose else (15 if obb else 80)
+    extra = 32 if seg else (51 if pose else 1)
+    B = 2
+    heads = synth.yolov8_heads(B, seed=410, nc=nc, extra=extra, n_obj=20)
+    hd = [torch.from_numpy(h).to(dev) for h in heads]
+    ref = torch.zeros((B, 1 + 1000 * 90), dtype=torch.float32, device=dev)
+    strides = (C.c_int * 3)(8, 16, 32)
+    assert lib.ref_v8_plugin_enqueue(nc, 17, C.c_float(0.3), 640, 640, 1000, int(seg), int(pose), int(obb), strides, 3, B,
+                                     _ptrs(hd), C.c_void_p(ref.data_ptr()), None) == 0
+    ref = ref.cpu().numpy()
+    got = _ours_decode(P.YoloLayerPlugin(nc, 17, 0.3, 640, 640, 1000, seg, pose, obb, (8, 16, 32)), hd, B, dev)
+    assert np.array_equal(ref[:, 0], got[:, 0])
+    cols = list(range(6)) + (list(range(6, 38)) if seg else []) + (list(range(38, 89)) if pose else []) + ([89] if obb else [])
+    for b in range(B):
+        n = int(ref[b, 0])
+        r = _canon(ref[b, 1:1 + n * 90].reshape(n, 90)[:, cols])
+        g = _canon(got[b, 1:1 + n * 90].reshape(n, 90)[:, cols])
+        np.testing.assert_allclose(g, r, rtol=1e-6, atol=1e-6)  # obb/pose use fp64 sin/cos/mul in both
+
+
+def test_yolov5_plugin_vs_reference_kernel(dev):
+    lib = _load("libref_yolov5.so")
+    B = 4
+    heads = synth.yolov5_heads(B, seed=420)
+    hd = [torch.from_numpy(h).to(dev) for h in heads]
+    ks = np.zeros((3, 8), np.float32)
+    ki = ks.view(np.int32)
+    for l, (s, a) in enumerate(zip((8, 16, 32), synth.V5_ANCHORS)):
+        ki[l, 0], ki[l, 1] = 640 // s, 640 // s
+        ks[l, 2:] = a
+    ref = torch.zeros((B, 1 + 1000 * 38), dtype=torch.float32, device=dev)
+    assert lib.ref_v5_plugin_enqueue(80, 640, 640, 1000, 0, ks.ctypes.data_as(C.c_void_p), 3, B, _ptrs(hd),
+                                     C.c_void_p(ref.data_ptr()), None) == 0
+    ref = ref.cpu().numpy()
+    kern = [P.YoloKernel(640 // s, 640 // s, a) for s, a in zip((8, 16, 32), synth.V5_ANCHORS)]
+    got = _ours_decode(P.YoloLayerPluginV5(80, 640, 640, 1000, False, kern), hd, B, dev)
+    assert np.array_equal(ref[:, 0], got[:, 0]) and ref[:, 0].min() > 100
+    for b in range(B):
+        n = int(ref[b, 0])
+        r = _canon(ref[b, 1:1 + n * 38].reshape(n, 38)[:, :6])
+        g = _canon(got[b, 1:1 + n * 38].reshape(n, 38)[:, :6])
+        np.testing.assert_allclose(g, r, rtol=3e-7, atol=0)  # FMA contraction of the reference build: <= 2 ulp
+
+
+def test_retina_plugin_vs_reference_kernel(dev):
+    lib = _load("libref_retina.so")
+    h, w = lib.ref_retina_input_h(), lib.ref_retina_input_w()
+    assert (h, w) == (480, 640)
+    B = 4
+    heads = synth.retina_heads(B, seed=430, in_h=h, in_w=w)
+    hd = [torch.from_numpy(x).to(dev) for x in heads]
+    plug = P.DecodePlugin(h, w)
+    ref = torch.zeros((B, plug.output_elems()), dtype=torch.float32, device=dev)
+    assert lib.ref_retina_plugin_enqueue(B, _ptrs(hd), C.c_void_p(ref.data_ptr()), None) == 0
+    ref = ref.cpu().numpy()
+    out = torch.zeros_like(torch.from_numpy(ref)).to(dev)
+    assert plug.enqueue(B, hd, [out], torch.empty(plug.getWorkspaceSize(B), dtype=torch.uint8, device=dev)) == 0
+    got = out.cpu().numpy()
+    assert np.array_equal(ref[:, 0], got[:, 0]) and ref[:, 0].min() > 50
+    for b in range(B):
+        n = int(ref[b, 0])
+        r = _canon(ref[b, 1:1 + n * 15].reshape(n, 15))
+        g = _canon(got[b, 1:1 + n * 15].reshape(n, 15))
+        np.testing.assert_allclose(g, r, rtol=3e-7, atol=1e-5)
+
+
+def test_cuda_decode_nms_vs_reference_kernels(dev, oracle):
+    lib = _load("libref_yolov8.so")
+    heads = synth.yolov8_heads(1, seed=440)
+    plugin_out, _ = oracle.yolov8_decode(heads)
+    pd = torch.from_numpy(plugin_out).to(dev)
+    parray = torch.zeros(1 + 1000 * 7, dtype=torch.float32, device=dev)
+    assert lib.ref_v8_cuda_decode_nms(C.c_void_p(pd.data_ptr()), 1000, C.c_float(0.5), C.c_void_p(parray.data_ptr()), 1000,
+                                      C.c_float(0.45), None) == 0
+    ref = parray.cpu().numpy()
+    cnt = int(ref[0])
+    rr = ref[1:1 + cnt * 7].reshape(cnt, 7)
+    rr = rr[rr[:, 4] > 0]          # holes (rows below conf) stay zero
+    comp = P.batch_nms(pd, 1, plugin_out.shape[1], 0.5, 0.45, mode=L.NMS_ONESHOT).cpu().numpy()
+    n = int(comp[0, 0])
+    gg = comp[0, 1:1 + n * 7].reshape(n, 7)
+    assert n == len(rr)
+    assert np.array_equal(_canon(rr), _canon(gg))   # identical rows AND identical keep flags
+
+
+def test_preprocess_vs_reference_kernel(dev):
+    lib = _load("libref_yolov8.so")
+    for (h, w) in [(640, 640), (1080, 1920), (375, 500)]:
+        img = synth.frames(1, seed=h, h=h, w=w)[0]
+        ref = torch.zeros((3, 640, 640), dtype=torch.float32, device=dev)
+        assert lib.ref_v8_preprocess(img.ctypes.data_as(C.c_void_p), w, h, C.c_void_p(ref.data_ptr()), 640, 640, None) == 0
+        dst = torch.zeros((1, 3, 640, 640), dtype=torch.float32, device=dev)
+        P.cuda_batch_preprocess([torch.from_numpy(img).to(dev)], dst, 640, 640)
+        torch.cuda.synchronize()
+        # the reference build contracts a*b+c into FMA; ours (and the oracle) round every product
+        np.testing.assert_allclose(dst[0].cpu().numpy(), ref.cpu().numpy(), atol=2e-6, rtol=0)
+
+
+def test_rcnn_vs_reference_functions(dev):
+    lib = _load("libref_rcnn.so")
+    B, A, H, W, top_n = 2, 15, 50, 67, 6000
+    scores, deltas = synth.rpn_inputs(B, seed=450, A=A, H=H, W=W)
+    anchors = synth.rcnn_anchors()
+    sd, dd = torch.from_numpy(scores).to(dev), torch.from_numpy(deltas).to(dev)
+    rs, rb = torch.zeros((B, top_n), device=dev), torch.zeros((B, top_n, 4), device=dev)
+    assert lib.ref_rpn_decode(B, C.c_void_p(sd.data_ptr()), C.c_void_p(dd.data_ptr()), C.c_void_p(rs.data_ptr()),
+                              C.c_void_p(rb.data_ptr()), H, W, 800, 1067, C.c_float(16.0),
+                              anchors.ctypes.data_as(C.c_void_p), A, top_n) == 0
+    plug = P.RpnDecodePlugin(top_n, anchors, 16.0, 800, 1067, H, W)
+    os_, ob = torch.zeros((B, top_n), device=dev), torch.zeros((B, top_n, 4), device=dev)
+    ws = torch.empty(256, dtype=torch.uint8, device=dev)
+    assert plug.enqueue(B, [sd, dd], [os_, ob], ws) == 0
+    assert torch.equal(os_, rs)                                            # same ordered top-6000
+    np.testing.assert_allclose(ob.cpu().numpy(), rb.cpu().numpy(), rtol=3e-7, atol=1e-4)
+
+    # RpnNms on <= 1024 boxes (the reference kernel is only race-free within one block)
+    pre, post = 1000, 300
+    s1, b1 = rs[:, :pre].contiguous(), rb[:, :pre].contiguous()
+    rnb = torch.zeros((B, post, 4), device=dev)
+    assert lib.ref_rpn_nms(B, C.c_void_p(s1.data_ptr()), C.c_void_p(b1.data_ptr()), C.c_void_p(rnb.data_ptr()), pre, post,
+                           C.c_float(0.7)) == 0
+    onb = torch.zeros((B, post, 4), device=dev)
+    assert P.RpnNmsPlugin(0.7, post, pre).enqueue(B, [s1, b1], [onb], ws) == 0
+    from oracle import oracle as O
+    orc = O.rpn_nms(s1.cpu().numpy(), b1.cpu().numpy(), post, 0.7)
+    d_ours = int((onb.cpu().numpy() != orc).any(-1).sum()), int((rnb.cpu().numpy() != orc).any(-1).sum())
+    assert torch.equal(onb, rnb), f"rows differing from the oracle: ours {d_ours[0]}, reference {d_ours[1]}; first diff " \
+        f"{int((onb != rnb).any(-1).float().argmax())}"
+
+
+
+def test_rcnn_predictor_and_batched_nms_vs_reference_functions(dev):
+    lib = _load("libref_rcnn.so")
+    B = 2
+    ws = torch.empty(256, dtype=torch.uint8, device=dev)
+    # PredictorDecode + BatchedNms (count = 1000: one block)
+    N, Cc = 1000, 80
+    sc, dl, pr = synth.predictor_inputs(B, seed=451, N=N, Ccls=Cc)
+    scd, dld, prd = (torch.from_numpy(x).to(dev) for x in (sc, dl, pr))
+    w4 = (C.c_float * 4)(10.0, 10.0, 5.0, 5.0)
+    r1, r2, r3 = torch.zeros((B, N), device=dev), torch.zeros((B, N, 4), device=dev), torch.zeros((B, N), device=dev)
+    assert lib.ref_predictor_decode(B, C.c_void_p(scd.data_ptr()), C.c_void_p(dld.data_ptr()), C.c_void_p(prd.data_ptr()),
+                                    C.c_void_p(r1.data_ptr()), C.c_void_p(r2.data_ptr()), C.c_void_p(r3.data_ptr()), N, Cc,
+                                    800, 1067, w4) == 0
+    o1, o2, o3 = torch.zeros_like(r1), torch.zeros_like(r2), torch.zeros_like(r3)
+    assert P.PredictorDecodePlugin(N, 800, 1067, (10.0, 10.0, 5.0, 5.0), Cc).enqueue(B, [scd, dld, prd], [o1, o2, o3], ws) == 0
+    assert torch.equal(o1, r1) and torch.equal(o3, r3)
+    np.testing.assert_allclose(o2.cpu().numpy(), r2.cpu().numpy(), rtol=3e-7, atol=1e-4)
+    for method in (0, 1, 2):
+        q1, q2, q3 = torch.zeros((B, 100), device=dev), torch.zeros((B, 100, 4), device=dev), torch.zeros((B, 100), device=dev)
+        assert lib.ref_batched_nms(method, B, C.c_void_p(r1.data_ptr()), C.c_void_p(r2.data_ptr()), C.c_void_p(r3.data_ptr()),
+                                   C.c_void_p(q1.data_ptr()), C.c_void_p(q2.data_ptr()), C.c_void_p(q3.data_ptr()), N, 100,
+                                   C.c_float(0.5)) == 0
+        p1, p2, p3 = torch.zeros_like(q1), torch.zeros_like(q2), torch.zeros_like(q3)
+        assert P.BatchedNmsPlugin(method, 0.5, 100, N).enqueue(B, [r1, r2, r3], [p1, p2, p3], ws) == 0
+        np.testing.assert_allclose(p1.cpu().numpy(), q1.cpu().numpy(), rtol=1e-6, atol=0)
+        assert torch.equal(p2, q2) and torch.equal(p3, q3)
