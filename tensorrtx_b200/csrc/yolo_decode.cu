@@ -501,7 +501,11 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
     for (int l = 0; l < p->num_levels; ++l)
         if (!inputs_dev[l]) return TRTX_ERR_INVALID;
     const int vec = yolo_pick_vec(p, inputs_dev);
-    YoloLayout L = yolo_layout(p, batch, vec);
+    // The TMA pipeline scan splits every 128-anchor stage over four warps of 32 anchors, i.e. it runs on the
+    // 32-cell tile layout (the same one as the scalar kernels, which are its fallback).
+    const bool pipe = g_use_pipe && p->variant == TRTX_YOLO_V8 && vec == 4 && yolo_pipe_supported(p, inputs_dev);
+    YoloLayout L = yolo_layout(p, batch, pipe ? 1 : vec);
+    L.pipe = pipe ? 1 : 0;
     if (workspace_bytes < L.total_bytes) return TRTX_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0) return TRTX_ERR_INVALID;
     memset(a, 0, sizeof(*a));
@@ -576,9 +580,9 @@ static void launch_v8(const YoloArgs& a, int grid, cudaStream_t st) {
 
 int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
     const int grid = batch * L.tiles_per_image;
-    if (g_use_pipe && a.variant == TRTX_YOLO_V8) {
+    if (L.pipe) {
         const int rc = yolo_scan_pipe_launch(a, L, in_dtype, batch, st);
-        if (rc != TRTX_ERR_UNSUPPORTED) return rc;
+        if (rc != TRTX_ERR_UNSUPPORTED) return rc;  // else: scalar kernels on the same 32-cell layout
     }
     if (a.variant == TRTX_YOLO_V8) {
         if (in_dtype == TRTX_F32) {

@@ -50,6 +50,7 @@ struct YoloArgs {
 
 struct YoloLayout {
     int vec;
+    int pipe;  // 1: the TMA pipeline scan runs on this layout (tile_cells = 32, four tiles per 128-anchor stage)
     int tile_cells;
     int apc;
     int tiles_per_image;
@@ -117,5 +118,6 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
 int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t stream);
 // TMA-pipelined scan (yolo_scan_pipe.cu); returns TRTX_ERR_UNSUPPORTED when the shape does not fit it
 int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t stream);
+bool yolo_pipe_supported(const trtx_yolo_params* p, const void* const* inputs_dev);
 
 }  // namespace trtx

@@ -1,20 +1,20 @@
 // yolo_scan_pipe.cu -- the YoloLayer scan as a persistent, TMA-fed pipeline (sm_100a).
 //
-// One CTA per SM, resident for the whole launch.  A producer thread streams tiles of the level tensors
-// (all C channel rows x 128 anchors, 43 KB for YOLOv8 fp32) into a ring of shared-memory stages with ONE
-// TMA tensor copy per tile (cp.async.bulk.tensor.3d over a [B, C, g] tensor map, box [1, C, 128],
-// completion counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and
-// ~170 KB per SM are in flight from the first cycle; columns past the end of a level are zero-filled
-// by the engine).  Every stage has its OWN consumer warp: warp w waits for stage w, scans all class
-// rows of its 128 anchors out of shared memory (conflict-free 128-bit LDS, 4 anchors per lane), gates,
-// compacts with a warp scan, decodes the boxes from the 4 box rows that are already in the stage, writes
-// the 32-byte candidate records and releases the stage.  Consumers never synchronise with each other, so
-// the stages are processed concurrently and the TMA latency of one stage hides behind the others.
+// One CTA per SM, resident for the whole launch.  A producer thread streams 128-anchor tiles of the level
+// tensors (all C channel rows, 43 KB for YOLOv8 fp32) into a ring of shared-memory stages with ONE TMA
+// tensor copy per stage (cp.async.bulk.tensor.3d over a [B, C, g] tensor map, box [1, C, 128], completion
+// counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and ~200 KB per SM
+// are in flight from the first cycle; columns past the end of a level are zero-filled by the engine).
+// Every stage is consumed by FOUR warps, each owning 32 of its anchors (one anchor per lane, conflict-free
+// 128-byte LDS per channel row): scan of all class rows, gate, warp-scan compaction, box decode from the 4
+// box rows already in the stage, 32-byte candidate records, then one arrive on the stage's "empty" mbarrier.
+// Warps never synchronise with each other; with 5 stages that is 20 consumer warps per SM, enough
+// thread-level parallelism to hide the LDS/ALU latency of the scan while TMA refills the other stages.
 //
-// Two earlier layouts are kept in the history for the record (profiles/r01b_sweep.log, r01c_sweep.log):
-// one 512-byte cp.async.bulk per channel row (84 descriptors per tile throttle the copy engine to
-// 1.7 TB/s) and one tensor copy per tile but all consumer warps cooperating on each tile (tiles are
-// then processed strictly one after another and the per-tile latency chain caps it at 2.2 TB/s).
+// Layouts tried before this one, kept for the record (profiles/r01b..r01d sweep logs): one 512-byte
+// cp.async.bulk per channel row (84 descriptors per tile throttle the copy engine: 1.7 TB/s); one tensor
+// copy per tile with all consumer warps cooperating on each tile (tiles strictly one after another:
+// 2.2 TB/s); one consumer warp per stage (5 warps per SM are latency-bound: 2.7 TB/s).
 // tools/tma_bench.cu measures the copy-engine ceiling of this access pattern: 5.3 TB/s.
 //
 // The arithmetic is the same bit-exact running-max scheme as yolo_decode.cu::scan_classes.
@@ -79,26 +79,28 @@ __device__ __forceinline__ float4 lds4<__half>(const __half* p) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-struct TileRef {
-    int b, t, l, tile, col0, ncols;
+constexpr int kSubWarps = 4;  // consumer warps per stage (32 anchors each)
+
+struct PipeGeom {
+    int stile_begin[TRTX_MAX_LEVELS];  // first 128-anchor stage tile of each level within an image
+    int stiles_per_image;
 };
-__device__ __forceinline__ TileRef tile_ref(const YoloArgs& a, int T) {
-    TileRef r;
-    r.b = T / a.tiles_per_image;
-    r.t = T - r.b * a.tiles_per_image;
-    int l = 0;
-    while (l + 1 < a.num_levels && r.t >= a.lv[l + 1].tile_begin) ++l;
-    r.l = l;
-    r.tile = r.t - a.lv[l].tile_begin;
-    r.col0 = r.tile * kTileAnchors;
-    r.ncols = min(kTileAnchors, a.lv[l].g - r.col0);
-    return r;
+
+template <typename T>
+__device__ __forceinline__ float lds1(const T* p);
+template <>
+__device__ __forceinline__ float lds1<float>(const float* p) {
+    return *p;
+}
+template <>
+__device__ __forceinline__ float lds1<__half>(const __half* p) {
+    return __half2float(*p);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32 * (kMaxStages + 1), 1)
-        yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, const __grid_constant__ TmaMaps maps, int total_tiles,
-                                 int stages, int stage_bytes) {
+__global__ void __launch_bounds__(1024, 1)
+        yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, const __grid_constant__ TmaMaps maps,
+                                 const __grid_constant__ PipeGeom geo, int total_stiles, int stages, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -108,109 +110,85 @@ __global__ void __launch_bounds__(32 * (kMaxStages + 1), 1)
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);   // producer's arrive.expect_tx
-            mbar_init(&empty_bar[s], 1);  // the stage's consumer warp
+            mbar_init(&full_bar[s], 1);           // producer's arrive.expect_tx
+            mbar_init(&empty_bar[s], kSubWarps);  // the stage's four consumer warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == stages) {
+    if (warp == stages * kSubWarps) {
         // ------------------------------ producer (one elected thread) ------------------------------
         if (lane == 0) {
             int it = 0;
-            for (int Tg = blockIdx.x; Tg < total_tiles; Tg += gridDim.x, ++it) {
+            for (int Tg = blockIdx.x; Tg < total_stiles; Tg += gridDim.x, ++it) {
                 const int s = it % stages;
                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                const TileRef r = tile_ref(a, Tg);
+                const int b = Tg / geo.stiles_per_image, t = Tg - b * geo.stiles_per_image;
+                int l = 0;
+                while (l + 1 < a.num_levels && t >= geo.stile_begin[l + 1]) ++l;
+                const int col0 = (t - geo.stile_begin[l]) * kTileAnchors;
                 unsigned char* dst = stage_base + (size_t)s * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);  // OOB columns are zero-filled and counted
                 for (int ch = 0; ch < a.C; ch += 256)                          // TMA box dims are limited to 256
-                    tma_load_3d(dst + (size_t)ch * kTileAnchors * sizeof(T), &maps.m[r.l], r.col0, ch, r.b, &full_bar[s]);
+                    tma_load_3d(dst + (size_t)ch * kTileAnchors * sizeof(T), &maps.m[l], col0, ch, b, &full_bar[s]);
             }
         }
         return;
     }
 
-    // ------------------------------ consumer warp `warp` owns stage `warp` ------------------------------
-    const int s = warp;
-    const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * stage_bytes);
+    // ------------------------------ consumers: warp = stage * 4 + quarter ------------------------------
+    const int s = warp / kSubWarps;
+    const int sub = warp - s * kSubWarps;
+    const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * stage_bytes) + sub * 32 + lane;
     int it = s;
-    for (int Tg = blockIdx.x + s * gridDim.x; Tg < total_tiles; Tg += stages * gridDim.x, it += stages) {
+    for (int Tg = blockIdx.x + s * gridDim.x; Tg < total_stiles; Tg += stages * gridDim.x, it += stages) {
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
-        const TileRef r = tile_ref(a, Tg);
-        const LevelArg& L = a.lv[r.l];
-        const bool active = lane * 4 < r.ncols;
+        const int b = Tg / geo.stiles_per_image, t = Tg - b * geo.stiles_per_image;
+        int l = 0;
+        while (l + 1 < a.num_levels && t >= geo.stile_begin[l + 1]) ++l;
+        const LevelArg& L = a.lv[l];
+        const int cell0 = (t - geo.stile_begin[l]) * kTileAnchors + sub * 32;  // first cell of this warp's 32-cell tile
+        const int e = cell0 + lane;
+        const bool active = e < L.g;
 
         mbar_wait(&full_bar[s], ph);
-        Best<4> st;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            st.bx[j] = a.x_lo;
-            st.bp[j] = 0.0f;
-            st.bc[j] = 0;
-        }
-        if (active) {
-            const T* p = tile + (size_t)4 * kTileAnchors + lane * 4;
+        Best<1> st;
+        st.bx[0] = active ? a.x_lo : INFINITY;  // TMA zero-fills columns past the level: never let them reach the sigmoid path
+        st.bp[0] = 0.0f;
+        st.bc[0] = 0;
+        if (cell0 < L.g) {
+            const T* p = tile + (size_t)4 * kTileAnchors;
             constexpr int U = 8;
             int c = 0;
             for (; c + U <= a.nc; c += U, p += U * kTileAnchors) {
-                float4 v[U];
+                float v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = lds4<T>(p + u * kTileAnchors);
+                for (int u = 0; u < U; ++u) v[u] = lds1<T>(p + u * kTileAnchors);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool any = (v[u].x > st.bx[0]) | (v[u].y > st.bx[1]) | (v[u].z > st.bx[2]) | (v[u].w > st.bx[3]);
-                    if (any) {
-                        update_one<4>(st, 0, v[u].x, c + u);
-                        update_one<4>(st, 1, v[u].y, c + u);
-                        update_one<4>(st, 2, v[u].z, c + u);
-                        update_one<4>(st, 3, v[u].w, c + u);
-                    }
-                }
+                for (int u = 0; u < U; ++u) update_one<1>(st, 0, v[u], c + u);
             }
-            for (; c < a.nc; ++c, p += kTileAnchors) {
-                const float4 v = lds4<T>(p);
-                update_one<4>(st, 0, v.x, c);
-                update_one<4>(st, 1, v.y, c);
-                update_one<4>(st, 2, v.z, c);
-                update_one<4>(st, 3, v.w, c);
-            }
-        }
-        unsigned flags = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (active && !(st.bp[j] < a.gate)) flags |= 1u << j;  // yololayer.cu:203
-        int total;
-        int off = warp_excl_scan(__popc(flags), lane, &total);
-        if (lane == 0) a.tile_count[(size_t)r.b * a.tiles_per_image + r.t] = total;
-        if (flags) {
-            const float4 d0 = lds4<T>(tile + 0 * kTileAnchors + lane * 4);
-            const float4 d1 = lds4<T>(tile + 1 * kTileAnchors + lane * 4);
-            const float4 d2 = lds4<T>(tile + 2 * kTileAnchors + lane * 4);
-            const float4 d3 = lds4<T>(tile + 3 * kTileAnchors + lane * 4);
-            const float dd[4][4] = {{d0.x, d0.y, d0.z, d0.w}, {d1.x, d1.y, d1.z, d1.w},
-                                    {d2.x, d2.y, d2.z, d2.w}, {d3.x, d3.y, d3.z, d3.w}};
-            const size_t slot0 = (size_t)r.b * a.slots_per_image + L.slot_begin + (size_t)r.col0;
-            const float fs = (float)L.stride;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (flags & (1u << j)) {
-                    const int e = r.col0 + lane * 4 + j;
-                    const int row = e / L.gw, col = e - row * L.gw;
-                    // yololayer.cu:217-220
-                    const float x1 = ((float)col + 0.5f - dd[0][j]) * fs;
-                    const float y1 = ((float)row + 0.5f - dd[1][j]) * fs;
-                    const float x2 = ((float)col + 0.5f + dd[2][j]) * fs;
-                    const float y2 = ((float)row + 0.5f + dd[3][j]) * fs;
-                    store_record(a.cand, slot0 + off, x1, y1, x2, y2, st.bp[j], st.bc[j], L.slot_begin + e);
-                    ++off;
-                }
+            for (; c < a.nc; ++c, p += kTileAnchors) update_one<1>(st, 0, lds1<T>(p), c);
+            const bool keep = active && !(st.bp[0] < a.gate);  // yololayer.cu:203
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + L.tile_begin + (cell0 >> 5)] = __popc(bal);
+            if (keep) {
+                const float d0 = lds1<T>(tile + 0 * kTileAnchors), d1 = lds1<T>(tile + 1 * kTileAnchors);
+                const float d2 = lds1<T>(tile + 2 * kTileAnchors), d3 = lds1<T>(tile + 3 * kTileAnchors);
+                const int row = e / L.gw, col = e - row * L.gw;
+                const float fs = (float)L.stride;
+                // yololayer.cu:217-220
+                const float x1 = ((float)col + 0.5f - d0) * fs;
+                const float y1 = ((float)row + 0.5f - d1) * fs;
+                const float x2 = ((float)col + 0.5f + d2) * fs;
+                const float y2 = ((float)row + 0.5f + d3) * fs;
+                const size_t slot = (size_t)b * a.slots_per_image + L.slot_begin + cell0 + __popc(bal & ((1u << lane) - 1u));
+                store_record(a.cand, slot, x1, y1, x2, y2, st.bp[0], st.bc[0], L.slot_begin + e);
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);  // stage free: the producer may refill it
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // one of the four releases the producer waits for
     }
 }
 
@@ -242,6 +220,7 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     const int stage_bytes = a.C * kTileAnchors * (int)sizeof(T);
     const int fixed = 2 * kMaxStages * (int)sizeof(uint64_t);
     int stages = g_pipe_max_stages < kMaxStages ? g_pipe_max_stages : kMaxStages;
+    if (stages * kSubWarps + 1 > 32) stages = 31 / kSubWarps;  // 1024-thread CTA limit
     while (stages >= 2 && (size_t)stages * stage_bytes + fixed + 128 > (size_t)max_smem) --stages;
     if (stages < 2) return TRTX_ERR_UNSUPPORTED;
     const size_t smem = (size_t)stages * stage_bytes + fixed;
@@ -257,24 +236,37 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return TRTX_ERR_UNSUPPORTED;  // caller falls back to the register-path scan
     }
-    const int total_tiles = batch * L.tiles_per_image;
-    const int grid = total_tiles < sms ? total_tiles : sms;
+    PipeGeom geo;
+    memset(&geo, 0, sizeof(geo));
+    for (int l = 0; l < a.num_levels; ++l) {
+        geo.stile_begin[l] = geo.stiles_per_image;
+        geo.stiles_per_image += (a.lv[l].g + kTileAnchors - 1) / kTileAnchors;
+    }
+    const int total_stiles = batch * geo.stiles_per_image;
+    const int grid = total_stiles < sms ? total_stiles : sms;
     auto kern = yolo_v8_scan_pipe_kernel<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 32 * (stages + 1), smem, st>>>(a, maps, total_tiles, stages, stage_bytes);
+    kern<<<grid, 32 * (stages * kSubWarps + 1), smem, st>>>(a, maps, geo, total_stiles, stages, stage_bytes);
     return check_launch();
 }
 
 void yolo_pipe_set_consumers(int n) { g_pipe_max_stages = n < 2 ? 2 : n; }
 
-int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
-    if (a.variant != TRTX_YOLO_V8 || L.vec != 4 || L.tile_cells != kTileAnchors) return TRTX_ERR_UNSUPPORTED;
-    // TMA needs 16-byte aligned bases and strides: fp32 rows are (g % 4 == 0 => ok); fp16 rows need g % 8 == 0
-    for (int l = 0; l < a.num_levels; ++l) {
-        if (reinterpret_cast<uintptr_t>(a.lv[l].in) % 16 != 0) return TRTX_ERR_UNSUPPORTED;
-        if (in_dtype == TRTX_F16 && a.lv[l].g % 8 != 0) return TRTX_ERR_UNSUPPORTED;
+bool yolo_pipe_supported(const trtx_yolo_params* p, const void* const* inputs_dev) {
+    if (p->variant != TRTX_YOLO_V8) return false;
+    const int C = 4 + p->num_classes + (p->is_seg ? 32 : 0) + (p->is_pose ? p->num_kpts * 3 : 0) + (p->is_obb ? 1 : 0);
+    if (C > 256 && (C % 256) != 0) return false;  // keeps the expect_tx byte count exact
+    for (int l = 0; l < p->num_levels; ++l) {
+        const int g = p->grid_h[l] * p->grid_w[l];
+        // TMA needs 16-byte aligned bases and strides
+        if (inputs_dev && reinterpret_cast<uintptr_t>(inputs_dev[l]) % 16 != 0) return false;
+        if (g % (p->in_dtype == TRTX_F16 ? 8 : 4) != 0) return false;
     }
-    if (a.C > 256 && (a.C % 256) != 0) return TRTX_ERR_UNSUPPORTED;  // keep the expect_tx byte count exact
+    return get_encoder() != nullptr;
+}
+
+int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
+    if (a.variant != TRTX_YOLO_V8 || !L.pipe || L.tile_cells != 32) return TRTX_ERR_UNSUPPORTED;
     if (in_dtype == TRTX_F32) return launch_pipe<float>(a, L, batch, st);
     return launch_pipe<__half>(a, L, batch, st);
 }

@@ -188,8 +188,11 @@ def test_rcnn_vs_reference_functions(dev):
     pre, post = 1000, 300
     s1, b1 = rs[:, :pre].contiguous(), rb[:, :pre].contiguous()
     rnb = torch.zeros((B, post, 4), device=dev)
-    assert lib.ref_rpn_nms(B, C.c_void_p(s1.data_ptr()), C.c_void_p(b1.data_ptr()), C.c_void_p(rnb.data_ptr()), pre, post,
-                           C.c_float(0.7)) == 0
+    # The reference is only correct for batch 1: its second sort overwrites the iota `indices` buffer that the next
+    # image's first sort uses as payload (RpnNms.cu:100 vs :112-113) -- call it once per image.
+    for b in range(B):
+        assert lib.ref_rpn_nms(1, C.c_void_p(s1[b].data_ptr()), C.c_void_p(b1[b].data_ptr()), C.c_void_p(rnb[b].data_ptr()),
+                               pre, post, C.c_float(0.7)) == 0
     onb = torch.zeros((B, post, 4), device=dev)
     assert P.RpnNmsPlugin(0.7, post, pre).enqueue(B, [s1, b1], [onb], ws) == 0
     from oracle import oracle as O
