@@ -24,6 +24,7 @@ static int g_slices = 4;
 static int g_unroll = 10;
 static int g_use_pipe = 1;  // TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
 void yolo_pipe_set_consumers(int n);
+void yolo_pipe_set_debug(int v);
 
 // --------------------------------------------------------------------------------------------
 // scan_classes: running (max sigmoid, first argmax) over `nrows` channel rows for VEC adjacent
@@ -49,15 +50,26 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
                 else
                     v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
             }
+            // one max per anchor over the U rows and ONE branch per group (fmaxf ignores NaN, like `p > max`)
+            float4 m = v[0];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                bool any = (v[u].x > s.bx[0]) | (v[u].y > s.bx[1]) | (v[u].z > s.bx[2]) | (v[u].w > s.bx[3]);
-                if (any) {
-                    int c = cls0 + r + u;
-                    update_one<VEC>(s, 0, v[u].x, c);
-                    update_one<VEC>(s, 1, v[u].y, c);
-                    update_one<VEC>(s, 2, v[u].z, c);
-                    update_one<VEC>(s, 3, v[u].w, c);
+            for (int u = 1; u < U; ++u) {
+                m.x = fmaxf(m.x, v[u].x);
+                m.y = fmaxf(m.y, v[u].y);
+                m.z = fmaxf(m.z, v[u].z);
+                m.w = fmaxf(m.w, v[u].w);
+            }
+            if ((m.x > s.bx[0]) | (m.y > s.bx[1]) | (m.z > s.bx[2]) | (m.w > s.bx[3])) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool any = (v[u].x > s.bx[0]) | (v[u].y > s.bx[1]) | (v[u].z > s.bx[2]) | (v[u].w > s.bx[3]);
+                    if (any) {
+                        const int c = cls0 + r + u;
+                        update_one<VEC>(s, 0, v[u].x, c);
+                        update_one<VEC>(s, 1, v[u].y, c);
+                        update_one<VEC>(s, 2, v[u].z, c);
+                        update_one<VEC>(s, 3, v[u].w, c);
+                    }
                 }
             }
         } else {
@@ -628,6 +640,7 @@ TRTX_API int trtx_tune_set(int key, int value) {
     else if (key == 1) g_unroll = value;
     else if (key == 2) g_use_pipe = value;
     else if (key == 3) yolo_pipe_set_consumers(value);
+    else if (key == 4) yolo_pipe_set_debug(value);
     else return TRTX_ERR_INVALID;
     return TRTX_OK;
 }

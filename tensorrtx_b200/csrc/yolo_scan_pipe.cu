@@ -1,14 +1,14 @@
 // yolo_scan_pipe.cu -- the YoloLayer scan as a persistent, TMA-fed pipeline (sm_100a).
 //
-// One CTA per SM, resident for the whole launch.  A producer thread streams 128-anchor tiles of the level
-// tensors (all C channel rows, 43 KB for YOLOv8 fp32) into a ring of shared-memory stages with ONE TMA
-// tensor copy per stage (cp.async.bulk.tensor.3d over a [B, C, g] tensor map, box [1, C, 128], completion
+// One CTA per SM, resident for the whole launch.  A producer thread streams 64-anchor tiles of the level
+// tensors (all C channel rows, 21.5 KB for YOLOv8 fp32) into a ring of shared-memory stages with ONE TMA
+// tensor copy per stage (cp.async.bulk.tensor.3d over a [B, C, g] tensor map, box [1, C, 64], completion
 // counted on an mbarrier -- the TMA engine moves the bytes, no registers are tied up and ~200 KB per SM
 // are in flight from the first cycle; columns past the end of a level are zero-filled by the engine).
-// Every stage is consumed by FOUR warps, each owning 32 of its anchors (one anchor per lane, conflict-free
+// Every stage is consumed by TWO warps, each owning 32 of its anchors (one anchor per lane, conflict-free
 // 128-byte LDS per channel row): scan of all class rows, gate, warp-scan compaction, box decode from the 4
 // box rows already in the stage, 32-byte candidate records, then one arrive on the stage's "empty" mbarrier.
-// Warps never synchronise with each other; with 5 stages that is 20 consumer warps per SM, enough
+// Warps never synchronise with each other; with 10 stages that is 20 consumer warps per SM, enough
 // thread-level parallelism to hide the LDS/ALU latency of the scan while TMA refills the other stages.
 //
 // Layouts tried before this one, kept for the record (profiles/r01b..r01d sweep logs): one 512-byte
@@ -25,8 +25,8 @@
 
 namespace trtx {
 
-constexpr int kTileAnchors = 128;
-constexpr int kMaxStages = 8;
+constexpr int kTileAnchors = 64;   // anchors per TMA stage (box [1, C, 64]; 256-byte rows stream as fast as 512-byte ones)
+constexpr int kMaxStages = 15;     // 2 consumer warps per stage + the producer warp <= 32 warps
 
 // ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,7 +79,7 @@ __device__ __forceinline__ float4 lds4<__half>(const __half* p) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-constexpr int kSubWarps = 4;  // consumer warps per stage (32 anchors each)
+constexpr int kSubWarps = kTileAnchors / 32;  // consumer warps per stage (32 anchors each)
 
 struct PipeGeom {
     int stile_begin[TRTX_MAX_LEVELS];  // first 128-anchor stage tile of each level within an image
@@ -100,7 +100,7 @@ __device__ __forceinline__ float lds1<__half>(const __half* p) {
 template <typename T>
 __global__ void __launch_bounds__(1024, 1)
         yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, const __grid_constant__ TmaMaps maps,
-                                 const __grid_constant__ PipeGeom geo, int total_stiles, int stages, int stage_bytes) {
+                                 const __grid_constant__ PipeGeom geo, int total_stiles, int stages, int stage_bytes, int dbg) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(1024, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);           // producer's arrive.expect_tx
-            mbar_init(&empty_bar[s], kSubWarps);  // the stage's four consumer warps
+            mbar_init(&empty_bar[s], kSubWarps);  // the stage's consumer warps
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(1024, 1)
         return;
     }
 
-    // ------------------------------ consumers: warp = stage * 4 + quarter ------------------------------
+    // ------------------------------ consumers: warp = stage * kSubWarps + part ------------------------------
     const int s = warp / kSubWarps;
     const int sub = warp - s * kSubWarps;
     const T* tile = reinterpret_cast<const T*>(stage_base + (size_t)s * stage_bytes) + sub * 32 + lane;
@@ -158,16 +158,26 @@ __global__ void __launch_bounds__(1024, 1)
         st.bx[0] = active ? a.x_lo : INFINITY;  // TMA zero-fills columns past the level: never let them reach the sigmoid path
         st.bp[0] = 0.0f;
         st.bc[0] = 0;
-        if (cell0 < L.g) {
+        if (dbg == 1) {  // profiling aid: copy engine only
+            if (lane == 0 && cell0 < L.g) a.tile_count[(size_t)b * a.tiles_per_image + L.tile_begin + (cell0 >> 5)] = 0;
+        } else if (cell0 < L.g) {
+            // Fast path: one max over a group of U class rows and ONE compare/branch per group (fmaxf ignores NaN,
+            // exactly like the reference's `p > max` never fires on NaN); the per-class update only runs for groups
+            // whose max beats the running maximum logit, i.e. around real candidates.
             const T* p = tile + (size_t)4 * kTileAnchors;
-            constexpr int U = 8;
+            constexpr int U = 10;
             int c = 0;
             for (; c + U <= a.nc; c += U, p += U * kTileAnchors) {
                 float v[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) v[u] = lds1<T>(p + u * kTileAnchors);
+                float m = v[0];
 #pragma unroll
-                for (int u = 0; u < U; ++u) update_one<1>(st, 0, v[u], c + u);
+                for (int u = 1; u < U; ++u) m = fmaxf(m, v[u]);
+                if (m > st.bx[0]) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) update_one<1>(st, 0, v[u], c + u);
+                }
             }
             for (; c < a.nc; ++c, p += kTileAnchors) update_one<1>(st, 0, lds1<T>(p), c);
             const bool keep = active && !(st.bp[0] < a.gate);  // yololayer.cu:203
@@ -188,10 +198,12 @@ __global__ void __launch_bounds__(1024, 1)
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);  // one of the four releases the producer waits for
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // one of the releases the producer waits for
     }
 }
 
+static int g_pipe_debug = 0;  // tuning knob 4 (profiling aid): 1 = consumers only release the stages
+void yolo_pipe_set_debug(int v) { g_pipe_debug = v; }
 static int g_pipe_max_stages = kMaxStages;  // tuning knob 3: cap on stages (= consumer warps)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -246,7 +258,7 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     const int grid = total_stiles < sms ? total_stiles : sms;
     auto kern = yolo_v8_scan_pipe_kernel<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 32 * (stages * kSubWarps + 1), smem, st>>>(a, maps, geo, total_stiles, stages, stage_bytes);
+    kern<<<grid, 32 * (stages * kSubWarps + 1), smem, st>>>(a, maps, geo, total_stiles, stages, stage_bytes, g_pipe_debug);
     return check_launch();
 }
 
