@@ -22,7 +22,9 @@ thread_local int g_last_cuda_error = 0;
 // tuning knobs (set through trtx_tune_set; defaults chosen from the B200 sweep in profiles/)
 static int g_slices = 4;
 static int g_unroll = 10;
-static int g_use_pipe = 1;  // TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
+static int g_use_pipe = 1;
+static int g_prefetch_box = 1;
+__constant__ int g_prefetch_box_rows_dev_dummy;  // (unused; the flag travels as a kernel argument)  // TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
 void yolo_pipe_set_consumers(int n);
 void yolo_pipe_set_debug(int v);
 
@@ -115,6 +117,12 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
     const int per = (a.nc + SLICES - 1) / SLICES;
     const int c0 = warp * per;
     const int c1 = min(a.nc, c0 + per);
+    if (a.prefetch_box && warp == 0 && active) {
+        // pull the 4 box rows of this tile towards L2 while the class rows stream: the epilogue's dependent
+        // loads then hit L2 instead of paying a second HBM round trip on every tile that has candidates
+#pragma unroll
+        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * g + a0));
+    }
     if (active && c1 > c0) scan_classes<T, VEC, U>(base + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
 
     if constexpr (SLICES > 1) {
@@ -564,6 +572,7 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
         a->x_lo = 10.0f;
     else
         a->x_lo = logf(p->gate / (1.0f - p->gate)) - 0.05f;
+    a->prefetch_box = g_prefetch_box;
     a->tile_count = reinterpret_cast<int*>(static_cast<char*>(workspace_dev) + L.off_tile_count);
     a->cand = reinterpret_cast<float4*>(static_cast<char*>(workspace_dev) + L.off_cand);
     *Lo = L;
@@ -579,15 +588,19 @@ static void launch_v8(const YoloArgs& a, int grid, cudaStream_t st) {
     }
     TRTX_V8_CASE(1, 8)
     TRTX_V8_CASE(1, 16)
+    TRTX_V8_CASE(2, 4)
+    TRTX_V8_CASE(2, 5)
+    TRTX_V8_CASE(2, 8)
     TRTX_V8_CASE(2, 10)
     TRTX_V8_CASE(2, 20)
+    TRTX_V8_CASE(4, 4)
     TRTX_V8_CASE(4, 5)
     TRTX_V8_CASE(4, 10)
     TRTX_V8_CASE(4, 20)
     TRTX_V8_CASE(8, 5)
     TRTX_V8_CASE(8, 10)
 #undef TRTX_V8_CASE
-    yolo_v8_scan_kernel<T, VEC, 4, 10><<<grid, 128, 0, st>>>(a);
+    yolo_v8_scan_kernel<T, VEC, 2, 5><<<grid, 64, 0, st>>>(a);
 }
 
 int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
@@ -641,6 +654,7 @@ TRTX_API int trtx_tune_set(int key, int value) {
     else if (key == 2) g_use_pipe = value;
     else if (key == 3) yolo_pipe_set_consumers(value);
     else if (key == 4) yolo_pipe_set_debug(value);
+    else if (key == 5) g_prefetch_box = value;
     else return TRTX_ERR_INVALID;
     return TRTX_OK;
 }

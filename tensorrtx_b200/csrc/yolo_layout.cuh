@@ -44,6 +44,7 @@ struct YoloArgs {
     float kpt_thresh;
     float gate;
     float x_lo;  // logit below which sigmoid(x) < gate for certain
+    int prefetch_box;  // register scan: L2-prefetch the 4 box rows while the class rows stream
     int* tile_count;
     float4* cand;
 };

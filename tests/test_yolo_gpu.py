@@ -122,7 +122,7 @@ def test_v8_fp16_inputs(oracle, dev):
     _check_rows(got, ref, 2, 90, 6, 1000)
 
 
-@pytest.mark.parametrize("slices,unroll", [(1, 8), (1, 16), (2, 10), (2, 20), (4, 5), (4, 20), (8, 5), (8, 10)])
+@pytest.mark.parametrize("slices,unroll", [(1, 8), (1, 16), (2, 4), (2, 8), (2, 10), (2, 20), (4, 4), (4, 5), (4, 10), (4, 20), (8, 5), (8, 10)])
 def test_v8_all_register_scan_variants(oracle, dev, slices, unroll):
     lib = L.load()
     heads = synth.yolov8_heads(2, seed=11)
@@ -134,13 +134,12 @@ def test_v8_all_register_scan_variants(oracle, dev, slices, unroll):
         lib.trtx_tune_set(1, unroll)
         got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
     finally:
-        lib.trtx_tune_set(0, 4)
-        lib.trtx_tune_set(1, 10)
-        lib.trtx_tune_set(2, 1)
+        lib.trtx_tune_set(0, 2)
+        lib.trtx_tune_set(1, 5)
     _check_rows(got, ref, 2, 90, 6, 1000)
 
 
-@pytest.mark.parametrize("consumers", [2, 3, 8])  # cap on pipeline stages (= consumer warps)
+@pytest.mark.parametrize("consumers", [2, 3, 15])  # cap on pipeline stages
 @pytest.mark.parametrize("dtype", ["f32", "f16"])
 @pytest.mark.parametrize("B", [1, 7, 40])
 def test_v8_tma_pipeline_scan(oracle, dev, consumers, dtype, B):
@@ -157,7 +156,8 @@ def test_v8_tma_pipeline_scan(oracle, dev, consumers, dtype, B):
         lib.trtx_tune_set(3, consumers)
         got = _decode_gpu(plug, _to_dev(heads, dev, torch.float16 if dtype == "f16" else torch.float32), B, dev)
     finally:
-        lib.trtx_tune_set(3, 8)
+        lib.trtx_tune_set(3, 15)
+        lib.trtx_tune_set(2, 0)
     _check_rows(got, ref, B, 90, 6, 1000)
 
 

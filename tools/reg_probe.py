@@ -1,4 +1,4 @@
-"""Probe the TMA pipeline scan: copy-only mode vs full, stages sweep, background-only vs dense data."""
+"""Probe register-path scan variants (slices, unroll, box prefetch) on dense and background data."""
 import json, sys
 from pathlib import Path
 import torch
@@ -16,14 +16,15 @@ def timeit(fused, ss):
     for i in range(K): fused.enqueue_scan(B, ss[i % R])
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / K * 1e3
-for name, nobj in (("dense(64 obj)", 64), ("background only", 0)):
+for name, nobj in (("dense", 64), ("typical(8 obj)", 8), ("background", 0)):
     sets = [[torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=i, n_obj=nobj)] for i in range(R)]
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-    for dbg in (1, 0):
-        for stages in (5, 8, 10, 12, 15):
-            lib.trtx_tune_set(2, 1); lib.trtx_tune_set(3, stages); lib.trtx_tune_set(4, dbg)
-            print(json.dumps({"data": name, "copy_only": dbg, "stages": stages, "us": round(timeit(fused, sets), 2)}), flush=True)
-    lib.trtx_tune_set(4, 0); lib.trtx_tune_set(3, 8); lib.trtx_tune_set(2, 0); lib.trtx_tune_set(0, 4); lib.trtx_tune_set(1, 5)
-    print(json.dumps({"data": name, "register_kernel_4x5_us": round(timeit(fused, sets), 2)}), flush=True)
-    lib.trtx_tune_set(2, 1)
+    lib.trtx_tune_set(2, 0)
+    for pf in (0, 1):
+        lib.trtx_tune_set(5, pf)
+        for sl, u in ((4, 5), (4, 4), (2, 4), (2, 5), (2, 8), (2, 10)):
+            lib.trtx_tune_set(0, sl); lib.trtx_tune_set(1, u)
+            print(json.dumps({"data": name, "prefetch": pf, "slices": sl, "unroll": u, "us": round(timeit(fused, sets), 2)}), flush=True)
+    lib.trtx_tune_set(2, 1); lib.trtx_tune_set(3, 15)
+    print(json.dumps({"data": name, "pipe_us": round(timeit(fused, sets), 2)}), flush=True)

@@ -22,7 +22,7 @@ res = []
 for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32), in_dtype=dt)
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-    for slices, unroll in [(-1, 2), (-1, 3), (-1, 4), (-1, 8), (4, 5), (4, 10)]:
+    for slices, unroll in [(-1, 15), (2, 5), (4, 5), (2, 8)]:
         if slices < 0:   # TMA pipeline kernel, `unroll` = cap on stages (= consumer warps)
             lib.trtx_tune_set(2, 1)
             lib.trtx_tune_set(3, unroll)
@@ -44,10 +44,10 @@ for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
              "GBps": round(nb / us / 1e3, 1)}
         res.append(r)
         print(json.dumps(r), flush=True)
-lib.trtx_tune_set(0, 4)
-lib.trtx_tune_set(1, 10)
-lib.trtx_tune_set(2, 1)
-lib.trtx_tune_set(3, 8)
+lib.trtx_tune_set(0, 2)
+lib.trtx_tune_set(1, 5)
+lib.trtx_tune_set(2, 0)
+lib.trtx_tune_set(3, 15)
 # NMS alone and preprocess alone
 plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
 fused = P.FusedYoloDecodeNms(plug, B, device=dev)
