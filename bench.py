@@ -263,12 +263,9 @@ def main():
     with torch.cuda.stream(stream):
         if args.no_graph:
             dev_steps = [(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
-            e2e_steps = [(lambda p=p, f=f, h=h: p.run(f, h)) for p, f, h in zip(pipes_dev, frame_sets_host, head_sets)]
         else:
             dg = [p.capture(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
-            eg = [p.capture(lambda p=p, f=f, h=h: p.run(f, h)) for p, f, h in zip(pipes_dev, frame_sets_host, head_sets)]
             dev_steps = [g.replay for g in dg]
-            e2e_steps = [g.replay for g in eg]
 
         def step_dev(i):
             dev_steps[i % R]()
@@ -276,9 +273,10 @@ def main():
                 return gather(pipes_dev[i % R].fused.out, world)
 
         def step_e2e(i):
-            e2e_steps[i % R]()
+            # public API call with HOST frames: H2D (copy stream, double-buffered) + preprocess + decode + NMS + D2H
+            pipe.submit(frame_sets_host[i % R], head_sets[i % R])
             if world > 1:
-                return gather(pipes_dev[i % R].fused.out, world)
+                return gather(pipe.fused.out, world)
 
         def timed(step, K, W):
             for i in range(W):
@@ -357,7 +355,8 @@ def main():
     except Exception:
         peak = 6650.0  # B200_PROFILING.md fallback
     algo = head_bytes  # bytes one scan launch must read (all class + box rows of 32 images)
-    achieved = algo / (scan_ms_avg * 1e-3) / 1e9
+    # average launch duration of the scan kernel: K launches on the timed stream between two CUDA events
+    achieved = algo / (scan_ms_b2b * 1e-3) / 1e9
     fps = world * BATCH * K / (ms_dev * 1e-3)
     fps_e2e = world * BATCH * K / (ms_e2e * 1e-3)
     out = {
@@ -374,16 +373,22 @@ def main():
         "clocks": sampler.summary([win_dev, win_e2e]),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / K,
-                "note": "frames from pinned host memory (H2D) + compact detections back to pinned host (D2H) every step"},
+                "note": "DetectionPipeline.submit(): frames from pinned host memory (H2D on a copy stream, double-buffered) + "
+                        "compact detections back to pinned host (D2H) every step; PCIe-bound",
+                "h2d_gbps": pipe.h2d_bytes * K / (ms_e2e * 1e-3) / 1e9},
         "gpu_launches": 3 * K,  # letterbox_kernel + yolo_v8_scan_kernel + nms_kernel per step
         "decode_nms_us_per_frame": ms_decnms * 1e3 / BATCH,
         "decode_nms_ms_per_batch": ms_decnms,
         "roofline": {"bound": "hbm", "kernel": "yolo_v8_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
-                     "algorithmic_bytes_per_launch": algo, "kernel_us": scan_ms_avg * 1e3,
-                     "kernel_us_back_to_back": scan_ms_b2b * 1e3,
-                     "achieved_back_to_back": algo / (scan_ms_b2b * 1e-3) / 1e9,
-                     "how": "CUDA events around each scan launch on its stream, averaged over the K steps of the unfused loop"},
+                     "algorithmic_bytes_per_launch": algo, "kernel_us": scan_ms_b2b * 1e3,
+                     "kernel_us_event_pair_per_launch": scan_ms_avg * 1e3,
+                     "achieved_event_pair_per_launch": algo / (scan_ms_avg * 1e-3) / 1e9,
+                     "copy_engine_ceiling_gbps": 5340.0,
+                     "how": "K scan launches (rotating input sets) on the timed stream between two CUDA events / K; "
+                            "kernel_us_event_pair_per_launch brackets every launch inside the unfused step loop with its own "
+                            "event pair (adds ~3 us of event latency per launch); copy_engine_ceiling = tools/tma_bench.cu, "
+                            "the same [32,84,g] fp32 tiles streamed by TMA with no compute (profiles/r01f_reg_probe.log)"},
     }
     if not args.no_cpu_baseline:
         cores = host_cores()

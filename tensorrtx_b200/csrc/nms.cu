@@ -161,21 +161,29 @@ __device__ __forceinline__ void pick_bucket(const int* hist, bool descending, in
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // carve-up (S = sort capacity, power of two >= pre_topk)
+    // carve-up (S = row capacity, power of two >= pre_topk)
     const int S = a.pre_topk <= 1024 ? 1024 : kMaxSort;
-    unsigned long long* k_hi = reinterpret_cast<unsigned long long*>(smem_raw);  // S
-    unsigned long long* k_lo = k_hi + S;                                         // S
-    float4* s_box = reinterpret_cast<float4*>(k_lo + S);                         // S
-    float* s_conf = reinterpret_cast<float*>(s_box + S);                         // S
+    float4* u_box = reinterpret_cast<float4*>(smem_raw);                         // S  stash in arrival order
+    float4* s_box = u_box + S;                                                   // S  sorted rows
+    unsigned long long* k64 = reinterpret_cast<unsigned long long*>(s_box + S);  // S  64-bit sort keys (fast path)
+    float* u_conf = reinterpret_cast<float*>(k64 + S);                           // S
+    int* u_cls = reinterpret_cast<int*>(u_conf + S);                             // S
+    uint32_t* u_id = reinterpret_cast<uint32_t*>(u_cls + S);                     // S
+    float* s_conf = reinterpret_cast<float*>(u_id + S);                          // S
     int* s_cls = reinterpret_cast<int*>(s_conf + S);                             // S
     uint32_t* s_id = reinterpret_cast<uint32_t*>(s_cls + S);                     // S
-    int* s_seg = reinterpret_cast<int*>(s_id + S);                               // S  short class segments (start<<16 | len)
+    int* s_seg = reinterpret_cast<int*>(s_id + S);                               // S   short class segments (start<<16 | len)
     int* s_long = s_seg + S;                                                     // S/2 long class segments
-    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_long + S / 2);    // S  keep flags
-    float4* s_kbox = reinterpret_cast<float4*>(k_hi);  // aliases the sort keys (dead after phase D)
+    unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_long + S / 2);   // S   slow path: stash position riding along
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_pos + S);         // S   keep flags
+    int* s_tpre = reinterpret_cast<int*>(s_keep + S);                            // tiles_per_image + 1 (fused path)
+    float4* s_kbox = u_box;  // kept boxes of a segment: aliases the stash (dead once the rows are permuted)
+    // slow path only: 128-bit keys live in the (not yet filled) sorted-row area
+    unsigned long long* k_hi = reinterpret_cast<unsigned long long*>(s_box);
+    unsigned long long* k_lo = k_hi + S;
 
     __shared__ int s_hist[256];
-    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nlong, s_cursor;
+    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nlong, s_cursor, s_bad;
     __shared__ unsigned s_rem;
     __shared__ unsigned s_sup[32];
     __shared__ int s_wsum[32];
@@ -184,47 +192,81 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2* list = a.list + (size_t)b * a.list_stride;
 
-    // ---------------- A: collect rows above conf_thresh ----------------
-    if (tid == 0) s_n = 0;
-    __syncthreads();
+    // ---------------- A: collect rows above conf_thresh, stash them in shared memory ----------------
+    // greedy: `conf <= thr -> skip` (postprocess.cpp:99; false for NaN, which v8 skips too);
+    // one-shot: `conf < thr -> skip` (postprocess.cu:57)
+    if (tid == 0) {
+        s_n = 0;
+        s_bad = 0;
+    }
+    auto stash = [&](const Row& r, uint32_t id) {
+        const int pos = atomicAdd(&s_n, 1);
+        list[pos] = make_uint2(float_key(r.conf), id);  // only read back if more than pre_topk rows survive
+        if (pos < S) {
+            const int c = a.class_aware ? (int)r.cls : 0;
+            u_box[pos] = r.box;
+            u_conf[pos] = r.conf;
+            u_cls[pos] = c;
+            u_id[pos] = id;
+            if (c < 0 || c > 0xffff) s_bad = 1;  // class does not fit the packed 64-bit key: generic sort
+        }
+    };
     if (a.from_tiles) {
-        const int* cnt = a.tile_count + (size_t)b * a.tiles_per_image;
-        for (int t = warp; t < a.tiles_per_image; t += kNmsThreads / 32) {
-            const int n = cnt[t];
-            if (n == 0) continue;
+        // prefix over the per-tile candidate counts, then one thread per candidate (binary search for its tile)
+        const int T = a.tiles_per_image;
+        const int* cnt = a.tile_count + (size_t)b * T;
+        int carry = 0;
+        for (int base = 0; base < T; base += kNmsThreads) {
+            const int t = base + tid;
+            const int v = t < T ? cnt[t] : 0;
+            int tot;
+            const int ex = warp_excl_scan(v, lane, &tot);
+            if (lane == 0) s_wsum[warp] = tot;
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_wsum[lane], wt;
+                const int wex = warp_excl_scan(w, lane, &wt);
+                s_wsum[lane] = wex;
+                if (lane == 0) s_need = wt;
+            }
+            __syncthreads();
+            if (t < T) s_tpre[t] = carry + s_wsum[warp] + ex;
+            carry += s_need;
+            __syncthreads();
+        }
+        if (tid == 0) s_tpre[T] = carry;
+        __syncthreads();
+        const int n_in = carry;
+        for (int r = tid; r < n_in; r += kNmsThreads) {
+            int lo = 0, hi = T;  // largest t with s_tpre[t] <= r
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_tpre[mid] <= r) lo = mid; else hi = mid;
+            }
+            const int t = lo;
             int l = 0;
             while (l + 1 < a.num_levels && t >= a.lv_tile_begin[l + 1]) ++l;
-            const uint32_t slot0 = a.lv_slot_begin[l] + (uint32_t)(t - a.lv_tile_begin[l]) * a.tile_slots;
-            for (int j = lane; j < n; j += 32) {
-                const uint32_t id = slot0 + j;
-                const float conf = a.cand[2 * ((size_t)b * a.slots_per_image + id) + 1].x;
-                // greedy: `conf <= thr -> skip` (postprocess.cpp:99; false for NaN, which v8 skips too);
-                // one-shot: `conf < thr -> skip` (postprocess.cu:57)
-                if (a.mode == TRTX_NMS_ONESHOT ? conf >= a.conf_thresh : conf > a.conf_thresh) {
-                    int pos = atomicAdd(&s_n, 1);
-                    list[pos] = make_uint2(float_key(conf), id);
-                }
-            }
+            const uint32_t id = a.lv_slot_begin[l] + (uint32_t)(t - a.lv_tile_begin[l]) * a.tile_slots + (uint32_t)(r - s_tpre[t]);
+            const Row row = fetch_row(a, b, id);
+            if (a.mode == TRTX_NMS_ONESHOT ? row.conf >= a.conf_thresh : row.conf > a.conf_thresh) stash(row, id);
         }
     } else {
+        __syncthreads();
         const float* img = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats);
         int n_in = (int)img[0];  // `i < output[0]`
         n_in = max(0, min(n_in, a.max_rows));
         for (int i = tid; i < n_in; i += kNmsThreads) {
-            const float conf = img[1 + (size_t)i * a.det_floats + 4];
-            if (a.mode == TRTX_NMS_ONESHOT ? conf >= a.conf_thresh : conf > a.conf_thresh) {
-                int pos = atomicAdd(&s_n, 1);
-                list[pos] = make_uint2(float_key(conf), (uint32_t)i);
-            }
+            const Row row = fetch_row(a, b, (uint32_t)i);
+            if (a.mode == TRTX_NMS_ONESHOT ? row.conf >= a.conf_thresh : row.conf > a.conf_thresh) stash(row, (uint32_t)i);
         }
     }
     __syncthreads();
     const int n_valid = s_n;
-    int M = min(n_valid, a.pre_topk);
+    const int M = min(n_valid, a.pre_topk);
 
-    // ---------------- B: radix select when more than pre_topk rows survive ----------------
-    uint32_t key_cut = 0, id_cut = 0xffffffffu;  // take key > key_cut, or key == key_cut && id <= id_cut
+    // ---------------- B: radix select when more than pre_topk rows survive (rare) ----------------
     if (n_valid > a.pre_topk) {
+        uint32_t key_cut = 0, id_cut = 0xffffffffu;  // take key > key_cut, or key == key_cut && id <= id_cut
         uint32_t prefix = 0, mask = 0;
         if (tid == 0) s_need = a.pre_topk;
         for (int pass = 0; pass < 4; ++pass) {
@@ -248,8 +290,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         }
         key_cut = prefix;
         const int need_eq = s_need;  // how many rows with key == key_cut are taken
-        // ties at the cut: take the need_eq smallest ids
-        uint32_t ip = 0, im = 0;
+        uint32_t ip = 0, im = 0;     // ties at the cut: take the need_eq smallest ids
         __syncthreads();
         if (tid == 0) s_need = need_eq;
         for (int pass = 0; pass < 4; ++pass) {
@@ -272,66 +313,96 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             im |= 255u << shift;
         }
         id_cut = ip;
-        __syncthreads();
-    }
-
-    // ---------------- C: build sort keys, bitonic sort ----------------
-    int S_eff = 32;
-    while (S_eff < M) S_eff <<= 1;
-    if (tid == 0) s_n = 0;
-    for (int i = tid; i < S_eff; i += kNmsThreads) {
-        k_hi[i] = ~0ull;
-        k_lo[i] = ~0ull;
-    }
-    __syncthreads();
-    for (int i = tid; i < n_valid; i += kNmsThreads) {
-        const uint2 e = list[i];
-        const bool take = (n_valid <= a.pre_topk) || e.x > key_cut || (e.x == key_cut && e.y <= id_cut);
-        if (take) {
-            const Row r = fetch_row(a, b, e.y);
-            const int pos = atomicAdd(&s_n, 1);
-            const uint32_t cls_u = a.class_aware ? (uint32_t)(int)r.cls : 0u;
-            const uint32_t x0k = a.tie_break_x0 ? float_key(r.box.x) : 0u;
-            k_hi[pos] = ((unsigned long long)cls_u << 32) | (uint32_t)(~e.x);  // class asc, conf desc
-            k_lo[pos] = ((unsigned long long)x0k << 32) | e.y;                 // box[0] asc, id asc
+        // re-stash exactly the selected rows
+        if (tid == 0) {
+            s_n = 0;
+            s_bad = 0;
         }
-    }
-    __syncthreads();
-    if (S_eff <= kNmsThreads) {
-        // one key per thread in registers; shuffles for partner distance < 32, smem ping-pong otherwise
-        unsigned long long* ex_hi = reinterpret_cast<unsigned long long*>(s_box);  // scratch: s_box.. are not live yet
-        unsigned long long* ex_lo = ex_hi + 2 * kNmsThreads;
-        unsigned long long mh = tid < S_eff ? k_hi[tid] : ~0ull, ml = tid < S_eff ? k_lo[tid] : ~0ull;
-        int pp = 0;
-        for (int k = 2; k <= S_eff; k <<= 1) {
-            for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                unsigned long long oh, ol;
-                if (jj >= 32) {
-                    ex_hi[pp * kNmsThreads + tid] = mh;
-                    ex_lo[pp * kNmsThreads + tid] = ml;
-                    __syncthreads();
-                    oh = ex_hi[pp * kNmsThreads + (tid ^ jj)];
-                    ol = ex_lo[pp * kNmsThreads + (tid ^ jj)];
-                    pp ^= 1;
-                } else {
-                    oh = __shfl_xor_sync(0xffffffffu, mh, jj);
-                    ol = __shfl_xor_sync(0xffffffffu, ml, jj);
-                }
-                const bool other_less = oh < mh || (oh == mh && ol < ml);
-                const bool want_min = (((tid & k) == 0) == ((tid & jj) == 0));
-                if (want_min == other_less) {
-                    mh = oh;
-                    ml = ol;
-                }
+        __syncthreads();
+        for (int i = tid; i < n_valid; i += kNmsThreads) {
+            const uint2 e = list[i];
+            if (e.x > key_cut || (e.x == key_cut && e.y <= id_cut)) {
+                const Row r = fetch_row(a, b, e.y);
+                const int pos = atomicAdd(&s_n, 1);
+                const int c = a.class_aware ? (int)r.cls : 0;
+                u_box[pos] = r.box;
+                u_conf[pos] = r.conf;
+                u_cls[pos] = c;
+                u_id[pos] = e.y;
+                if (c < 0 || c > 0xffff) s_bad = 1;
             }
         }
         __syncthreads();
-        if (tid < S_eff) {
-            k_hi[tid] = mh;
-            k_lo[tid] = ml;
+    }
+
+    // ---------------- C: sort by (class asc, conf desc, box[0] asc, id asc) ----------------
+    int S_eff = 32;
+    while (S_eff < M) S_eff <<= 1;
+    // fast path: packed key = class(16) | ~conf key(32) | stash position(16); exact unless two rows share
+    // (class, conf) -- detected below, then the generic 128-bit sort decides by (box[0], id).
+    bool generic = s_bad != 0;
+    if (!generic) {
+        for (int i = tid; i < S_eff; i += kNmsThreads)
+            k64[i] = i < M ? ((unsigned long long)(uint32_t)u_cls[i] << 48) | ((unsigned long long)(uint32_t)(~float_key(u_conf[i])) << 16) | (uint32_t)i
+                           : ~0ull;
+        __syncthreads();
+        if (S_eff <= kNmsThreads) {
+            // one key per thread in registers; shuffles for partner distance < 32, smem ping-pong otherwise
+            unsigned long long* ex = reinterpret_cast<unsigned long long*>(s_box);  // 2 x 1024 u64 scratch (rows not staged yet)
+            unsigned long long mk = tid < S_eff ? k64[tid] : ~0ull;
+            int pp = 0;
+            for (int k = 2; k <= S_eff; k <<= 1) {
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    unsigned long long ok;
+                    if (jj >= 32) {
+                        ex[pp * kNmsThreads + tid] = mk;
+                        __syncthreads();
+                        ok = ex[pp * kNmsThreads + (tid ^ jj)];
+                        pp ^= 1;
+                    } else {
+                        ok = __shfl_xor_sync(0xffffffffu, mk, jj);
+                    }
+                    const bool want_min = (((tid & k) == 0) == ((tid & jj) == 0));
+                    if (want_min == (ok < mk)) mk = ok;
+                }
+            }
+            __syncthreads();
+            if (tid < S_eff) k64[tid] = mk;
+            __syncthreads();
+        } else {
+            for (int k = 2; k <= S_eff; k <<= 1) {
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (int i = tid; i < S_eff; i += kNmsThreads) {
+                        const int ixj = i ^ jj;
+                        if (ixj > i) {
+                            const unsigned long long x = k64[i], y = k64[ixj];
+                            if ((x > y) == ((i & k) == 0)) {
+                                k64[i] = y;
+                                k64[ixj] = x;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        bool tie = false;
+        for (int i = tid; i < M; i += kNmsThreads)
+            if (i > 0 && (k64[i] >> 16) == (k64[i - 1] >> 16)) tie = true;
+        generic = __syncthreads_or(tie ? 1 : 0) != 0;
+    }
+    if (generic) {
+        for (int i = tid; i < S_eff; i += kNmsThreads) {
+            if (i < M) {
+                k_hi[i] = ((unsigned long long)(uint32_t)u_cls[i] << 32) | (uint32_t)(~float_key(u_conf[i]));
+                k_lo[i] = ((unsigned long long)(a.tie_break_x0 ? float_key(u_box[i].x) : 0u) << 32) | u_id[i];
+            } else {
+                k_hi[i] = ~0ull;
+                k_lo[i] = ~0ull;
+            }
+            s_pos[i] = (unsigned short)i;
         }
         __syncthreads();
-    } else {
         for (int k = 2; k <= S_eff; k <<= 1) {
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
                 for (int i = tid; i < S_eff; i += kNmsThreads) {
@@ -339,36 +410,32 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                     if (ixj > i) {
                         const unsigned long long ah = k_hi[i], al = k_lo[i], bh = k_hi[ixj], bl = k_lo[ixj];
                         const bool gt = ah > bh || (ah == bh && al > bl);
-                        const bool asc = (i & k) == 0;
-                        if (gt == asc) {
+                        if (gt == ((i & k) == 0)) {
                             k_hi[i] = bh;
                             k_lo[i] = bl;
                             k_hi[ixj] = ah;
                             k_lo[ixj] = al;
+                            const unsigned short t0 = s_pos[i];
+                            s_pos[i] = s_pos[ixj];
+                            s_pos[ixj] = t0;
                         }
                     }
                 }
                 __syncthreads();
             }
         }
+        for (int i = tid; i < M; i += kNmsThreads) k64[i] = s_pos[i];  // permutation in the low 16 bits, like the fast path
+        __syncthreads();  // the 128-bit keys (in the sorted-row area) are dead from here on
     }
 
-    // ---------------- D: stage sorted rows ----------------
-    {
-        uint32_t ids[2];
-        int cnt = 0;
-        for (int i = tid; i < M; i += kNmsThreads) ids[cnt++] = (uint32_t)(k_lo[i] & 0xffffffffull);
-        __syncthreads();  // all keys read: the key area / exchange scratch may be overwritten from here on
-        cnt = 0;
-        for (int i = tid; i < M; i += kNmsThreads) {
-            const uint32_t id = ids[cnt++];
-            const Row r = fetch_row(a, b, id);
-            s_box[i] = r.box;
-            s_conf[i] = r.conf;
-            s_cls[i] = a.class_aware ? (int)r.cls : 0;
-            s_id[i] = id;
-            s_keep[i] = 0;
-        }
+    // ---------------- D: permute the stash into sorted order ----------------
+    for (int i = tid; i < M; i += kNmsThreads) {
+        const int pos = (int)(k64[i] & 0xffffull);
+        s_box[i] = u_box[pos];
+        s_conf[i] = u_conf[pos];
+        s_cls[i] = u_cls[pos];
+        s_id[i] = u_id[pos];
+        s_keep[i] = 0;
     }
     if (tid == 0) {
         s_nkept = 0;
@@ -550,9 +617,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         for (int i = n_rows_out + tid; i < a.max_det; i += kNmsThreads) oidx[i] = -1;
 }
 
-static size_t nms_smem_bytes(int pre_topk) {
+static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
     const size_t S = pre_topk <= 1024 ? 1024 : kMaxSort;
-    return S * (8 + 8 + 16 + 4 + 4 + 4 + 4 + 2 + 1) + 64;
+    return S * (16 + 16 + 8 + 6 * 4 + 4 + 2 + 2 + 1) + 64 + sizeof(int) * (size_t)(tiles + 1);
 }
 
 static int nms_validate(const trtx_nms_params* q) {
@@ -565,9 +632,10 @@ static int nms_validate(const trtx_nms_params* q) {
 
 static int nms_launch(NmsArgs& a, int batch, cudaStream_t st) {
     if (a.pre_topk > kMaxSort) return TRTX_ERR_UNSUPPORTED;
-    const size_t smem = nms_smem_bytes(a.pre_topk);
+    const size_t smem = nms_smem_bytes(a.pre_topk, a.from_tiles ? a.tiles_per_image : 0);
+    if (smem > 220 * 1024) return TRTX_ERR_UNSUPPORTED;
     // per-device function attribute; cheap and idempotent, so set on every call (no global state)
-    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes(kMaxSort));
+    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     nms_kernel<<<batch, kNmsThreads, smem, st>>>(a);
     return check_launch();
 }

@@ -55,6 +55,44 @@ class DetectionPipeline:
         out, _ = self.fused.enqueue(self.batch, heads, stream)
         return out
 
+    # ---- overlapped host pipeline: H2D of batch i+1 runs on a copy stream while batch i is decoded ----
+    def _make_slots(self, n: int) -> None:
+        self._slots = []
+        for _ in range(n):
+            fd = torch.empty_like(self.frames_dev)
+            self._slots.append({
+                "frames": fd,
+                "pre": PreprocessPlan(list(fd.unbind(0)), self.net_input, self.net_w, self.net_h),
+                "out_host": torch.empty_like(self.out_host).pin_memory(),
+                "h2d": torch.cuda.Event(), "done": torch.cuda.Event(),
+            })
+            self._slots[-1]["done"].record(torch.cuda.current_stream(self.device))
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._next = 0
+
+    def submit(self, frames_host: torch.Tensor, heads: Sequence[torch.Tensor] | None = None, slots: int = 2):
+        """Asynchronous step with double buffering: returns (pinned host result, event); the result is valid
+        once the event has completed.  The H2D copy is issued on a dedicated copy stream so that it overlaps
+        the kernels of the previous submit() (the reference serialises memcpy -> H2D -> kernel -> sync per
+        image, yolov8/src/preprocess.cu:89-127)."""
+        if not hasattr(self, "_slots"):
+            self._make_slots(slots)
+        sl = self._slots[self._next]
+        self._next = (self._next + 1) % len(self._slots)
+        compute = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_event(sl["done"])           # slot buffers are free again
+        with torch.cuda.stream(self._copy_stream):
+            sl["frames"].copy_(frames_host, non_blocking=True)
+            sl["h2d"].record(self._copy_stream)
+        compute.wait_event(sl["h2d"])
+        sl["pre"].enqueue()
+        if self.backbone is not None:
+            heads = self.backbone(self.net_input)
+        out, _ = self.fused.enqueue(self.batch, heads)
+        sl["out_host"].copy_(out, non_blocking=True)
+        sl["done"].record(compute)
+        return sl["out_host"], sl["done"]
+
     # ---- CUDA graphs: the step is launch-bound (4 kernels of 10-30 us), so replaying a captured graph
     # removes the per-launch host cost (guide: "capture launch-bound inner loops in CUDA graphs") ----
     def capture(self, fn: Callable[[], object]) -> "torch.cuda.CUDAGraph":
