@@ -80,27 +80,48 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ 
                 const float lx = __fsub_rn(src_x, (float)x_low), hx = __fsub_rn(1.0f, lx);
                 const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
                 const bool xl = x_low >= 0, xh = x_high < im.sw;
-                const int o1 = (xl ? x_low : 0) * 3, o2 = (xh ? x_high : 0) * 3;
-                float v1[3] = {cv, cv, cv}, v2[3] = {cv, cv, cv}, v3[3] = {cv, cv, cv}, v4[3] = {cv, cv, cv};
-                if (r0ok && xl) {
-                    v1[0] = __ldg(row0 + o1);
-                    v1[1] = __ldg(row0 + o1 + 1);
-                    v1[2] = __ldg(row0 + o1 + 2);
-                }
-                if (r0ok && xh) {
-                    v2[0] = __ldg(row0 + o2);
-                    v2[1] = __ldg(row0 + o2 + 1);
-                    v2[2] = __ldg(row0 + o2 + 2);
-                }
-                if (r1ok && xl) {
-                    v3[0] = __ldg(row1 + o1);
-                    v3[1] = __ldg(row1 + o1 + 1);
-                    v3[2] = __ldg(row1 + o1 + 2);
-                }
-                if (r1ok && xh) {
-                    v4[0] = __ldg(row1 + o2);
-                    v4[1] = __ldg(row1 + o2 + 1);
-                    v4[2] = __ldg(row1 + o2 + 2);
+                float v1[3], v2[3], v3[3], v4[3];
+                if (r0ok && r1ok && xl && xh) {
+                    // interior pixel (all but the letterbox border): the two source pixels of a row are 6 contiguous
+                    // bytes -> one address per row, immediate offsets
+                    const uint8_t* p0 = row0 + x_low * 3;
+                    const uint8_t* p1 = row1 + x_low * 3;
+                    v1[0] = __ldg(p0);
+                    v1[1] = __ldg(p0 + 1);
+                    v1[2] = __ldg(p0 + 2);
+                    v2[0] = __ldg(p0 + 3);
+                    v2[1] = __ldg(p0 + 4);
+                    v2[2] = __ldg(p0 + 5);
+                    v3[0] = __ldg(p1);
+                    v3[1] = __ldg(p1 + 1);
+                    v3[2] = __ldg(p1 + 2);
+                    v4[0] = __ldg(p1 + 3);
+                    v4[1] = __ldg(p1 + 4);
+                    v4[2] = __ldg(p1 + 5);
+                } else {
+                    const int o1 = (xl ? x_low : 0) * 3, o2 = (xh ? x_high : 0) * 3;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) v1[k] = v2[k] = v3[k] = v4[k] = cv;
+                    if (r0ok && xl) {
+                        v1[0] = __ldg(row0 + o1);
+                        v1[1] = __ldg(row0 + o1 + 1);
+                        v1[2] = __ldg(row0 + o1 + 2);
+                    }
+                    if (r0ok && xh) {
+                        v2[0] = __ldg(row0 + o2);
+                        v2[1] = __ldg(row0 + o2 + 1);
+                        v2[2] = __ldg(row0 + o2 + 2);
+                    }
+                    if (r1ok && xl) {
+                        v3[0] = __ldg(row1 + o1);
+                        v3[1] = __ldg(row1 + o1 + 1);
+                        v3[2] = __ldg(row1 + o1 + 2);
+                    }
+                    if (r1ok && xh) {
+                        v4[0] = __ldg(row1 + o2);
+                        v4[1] = __ldg(row1 + o2 + 1);
+                        v4[2] = __ldg(row1 + o2 + 2);
+                    }
                 }
                 // :59-61, left-to-right sums
                 c0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1[0]), __fmul_rn(w2, v2[0])), __fmul_rn(w3, v3[0])), __fmul_rn(w4, v4[0]));

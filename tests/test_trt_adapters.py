@@ -1,0 +1,38 @@
+"""include/trtx_plugins.h (header-only TensorRT adapters) compiled against the mock NvInfer.h and driven the way an
+engine builder / the TensorRT runtime drives plugins.  Host-only part runs without a GPU; --gpu enqueues on the device."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _build(tmp_path):
+    from tensorrtx_b200 import _lib as L
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cuda = Path(nvcc).resolve().parents[1]
+    exe = tmp_path / "trt_adapter_check"
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-I", str(ROOT / "include"), "-I", str(ROOT / "tests" / "mock_trt"),
+           "-I", str(cuda / "include"), str(ROOT / "tests" / "trt_adapter_check.cpp"), "-o", str(exe),
+           str(L.LIB_PATH), f"-Wl,-rpath,{L.LIB_PATH.parent}", "-L", str(cuda / "lib64"), "-lcudart", f"-Wl,-rpath,{cuda / 'lib64'}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_trt_adapters_host_surface(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "trt adapter check ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_trt_adapters_enqueue_on_gpu(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([str(exe), "--gpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "gpu enqueue ok" in r.stdout
