@@ -183,11 +183,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     unsigned long long* k_lo = k_hi + S;
 
     __shared__ int s_hist[256];
-    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nlong, s_cursor, s_bad;
+    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nmed, s_nlong, s_cursor, s_bad;
     __shared__ unsigned s_rem;
     __shared__ unsigned s_sup[32];
     __shared__ int s_wsum[32];
     __shared__ unsigned s_wsup[32 * 32];  // per-warp suppressor bitmaps of the short-segment path
+    __shared__ unsigned s_wrem[32];       // per-warp "removed by an already kept row" bits
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         s_nkept = 0;
         s_rem = 0;
         s_nshort = 0;
+        s_nmed = 0;
         s_nlong = 0;
         s_cursor = 0;
     }
@@ -460,6 +462,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 const int m = e - i;
                 if (m > kShortSeg)
                     s_long[atomicAdd(&s_nlong, 1)] = (i << 16) | m;  // M <= 2048: start and length fit 16 bits
+                else if (m > 32)
+                    s_seg[S - 1 - atomicAdd(&s_nmed, 1)] = (i << 16) | m;  // medium segments: taken first (longest-first scheduling)
                 else
                     s_seg[atomicAdd(&s_nshort, 1)] = (i << 16) | m;
             }
@@ -510,13 +514,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             }
         }
         // ---- short segments: one warp each, shuffles + ballots only ----
-        const int n_short = s_nshort;
+        const int n_short = s_nshort, n_med = s_nmed;
         for (;;) {
             int sidx = 0;
             if (lane == 0) sidx = atomicAdd(&s_cursor, 1);
             sidx = __shfl_sync(0xffffffffu, sidx, 0);
-            if (sidx >= n_short) break;
-            const int p0 = s_seg[sidx] >> 16, m = s_seg[sidx] & 0xffff;
+            if (sidx >= n_med + n_short) break;
+            const int ent = sidx < n_med ? s_seg[S - 1 - sidx] : s_seg[sidx - n_med];
+            const int p0 = ent >> 16, m = ent & 0xffff;
             if (m == 1) {
                 if (lane == 0) s_keep[p0] = 1;
                 continue;
@@ -546,33 +551,36 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 __syncwarp();
                 continue;
             }
+            // 33..kShortSeg rows: chunks of 32, every IoU pair (chunk x kept, chunk x chunk) spread over the lanes
+            unsigned* sup = s_wsup + warp * 32;
             int nk = 0;
             for (int c0 = 0; c0 < m; c0 += 32) {
                 const int nchunk = min(32, m - c0);
-                const bool in = lane < nchunk;
-                const float4 mybox = in ? s_box[p0 + c0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-                bool removed = false;
-                for (int k = 0; k < nk; ++k) {
-                    const float4 kb = s_kbox[p0 + k];  // broadcast read
-                    if (in && !removed && iou_any(a.box_format, kb, mybox) > a.nms_thresh) removed = true;
+                sup[lane] = 0;
+                if (lane == 0) s_wrem[warp] = 0;
+                __syncwarp();
+                for (int pr = lane; pr < nk * nchunk; pr += 32) {
+                    const int k = pr / nchunk, i = pr - k * nchunk;
+                    if (iou_any(a.box_format, s_kbox[p0 + k], s_box[p0 + c0 + i]) > a.nms_thresh) atomicOr(&s_wrem[warp], 1u << i);
                 }
-                unsigned mymask = 0;
-                for (int jx = 0; jx + 1 < nchunk; ++jx) {
-                    float4 bj;
-                    bj.x = __shfl_sync(0xffffffffu, mybox.x, jx);
-                    bj.y = __shfl_sync(0xffffffffu, mybox.y, jx);
-                    bj.z = __shfl_sync(0xffffffffu, mybox.z, jx);
-                    bj.w = __shfl_sync(0xffffffffu, mybox.w, jx);
-                    if (in && !removed && lane > jx && iou_any(a.box_format, bj, mybox) > a.nms_thresh) mymask |= 1u << jx;
+                const int npairs = nchunk * (nchunk - 1) / 2;
+                for (int pr = lane; pr < npairs; pr += 32) {
+                    int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f);
+                    while (i * (i - 1) / 2 > pr) --i;
+                    while ((i + 1) * i / 2 <= pr) ++i;
+                    const int jx = pr - i * (i - 1) / 2;
+                    if (iou_any(a.box_format, s_box[p0 + c0 + jx], s_box[p0 + c0 + i]) > a.nms_thresh) atomicOr(&sup[i], 1u << jx);
                 }
-                unsigned alive = __ballot_sync(0xffffffffu, in && !removed);
+                __syncwarp();
+                const unsigned mymask = sup[lane];
+                unsigned alive = ~s_wrem[warp] & (nchunk == 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
                 for (int jx = 0; jx < nchunk; ++jx) {
                     const unsigned kill = __ballot_sync(0xffffffffu, (mymask >> jx) & 1u);
                     if ((alive >> jx) & 1u) alive &= ~kill;
                 }
                 if ((alive >> lane) & 1u) {
                     const int pos = nk + __popc(alive & ((1u << lane) - 1u));
-                    s_kbox[p0 + pos] = mybox;
+                    s_kbox[p0 + pos] = s_box[p0 + c0 + lane];
                     s_keep[p0 + c0 + lane] = 1;
                 }
                 nk += __popc(alive);

@@ -37,6 +37,13 @@ __device__ __forceinline__ float div255(float x) {
     return __fmaf_rn(__fmaf_rn(-255.0f, q0, x), r, q0);
 }
 
+// int -> float without the XU (conversion) pipe: for 0 <= i < 2^23, (2^23 + i) is exactly representable with the
+// integer sitting in the mantissa, so OR-ing i into the bits of 2^23 and subtracting 2^23 gives float(i) exactly.
+// ncu showed the first version of this kernel bound by the quarter-rate XU pipe (12 u8->f32 conversions per
+// pixel, sm__inst_executed_pipe_xu at its peak); these run on the full-rate ALU/FMA pipes instead.
+__device__ __forceinline__ float u23_to_float(uint32_t i) { return __uint_as_float(0x4B000000u | i) - 8388608.0f; }
+__device__ __forceinline__ float ldg_u8f(const uint8_t* p) { return u23_to_float((uint32_t)__ldg(p)); }
+
 // One thread = 4 horizontally adjacent destination pixels of one row.  The letterbox matrix has no
 // rotation (m[1] = m[3] = -0.0f, preprocess.cu:99-104), so the source row pair, the vertical weights
 // and the row validity are computed once per thread; `m3*dx` only contributes a signed zero.
@@ -71,13 +78,13 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ 
         const int dx = dx0 + i;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         if (dx < a.dw) {
-            const float src_x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(im.m[0], (float)dx), ym), im.m[2]), 0.5f);  // :22
+            const float src_x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(im.m[0], u23_to_float((uint32_t)dx)), ym), im.m[2]), 0.5f);  // :22
             if (y_out || src_x <= -1 || src_x >= im.sw) {
                 c0 = c1 = c2 = cv;
             } else {
                 const int x_low = (int)floorf(src_x);
                 const int x_high = x_low + 1;
-                const float lx = __fsub_rn(src_x, (float)x_low), hx = __fsub_rn(1.0f, lx);
+                const float lx = __fsub_rn(src_x, u23_to_float((uint32_t)(x_low + 1)) - 1.0f), hx = __fsub_rn(1.0f, lx);  // x_low >= -1
                 const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
                 const bool xl = x_low >= 0, xh = x_high < im.sw;
                 float v1[3], v2[3], v3[3], v4[3];
@@ -86,41 +93,41 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ 
                     // bytes -> one address per row, immediate offsets
                     const uint8_t* p0 = row0 + x_low * 3;
                     const uint8_t* p1 = row1 + x_low * 3;
-                    v1[0] = __ldg(p0);
-                    v1[1] = __ldg(p0 + 1);
-                    v1[2] = __ldg(p0 + 2);
-                    v2[0] = __ldg(p0 + 3);
-                    v2[1] = __ldg(p0 + 4);
-                    v2[2] = __ldg(p0 + 5);
-                    v3[0] = __ldg(p1);
-                    v3[1] = __ldg(p1 + 1);
-                    v3[2] = __ldg(p1 + 2);
-                    v4[0] = __ldg(p1 + 3);
-                    v4[1] = __ldg(p1 + 4);
-                    v4[2] = __ldg(p1 + 5);
+                    v1[0] = ldg_u8f(p0);
+                    v1[1] = ldg_u8f(p0 + 1);
+                    v1[2] = ldg_u8f(p0 + 2);
+                    v2[0] = ldg_u8f(p0 + 3);
+                    v2[1] = ldg_u8f(p0 + 4);
+                    v2[2] = ldg_u8f(p0 + 5);
+                    v3[0] = ldg_u8f(p1);
+                    v3[1] = ldg_u8f(p1 + 1);
+                    v3[2] = ldg_u8f(p1 + 2);
+                    v4[0] = ldg_u8f(p1 + 3);
+                    v4[1] = ldg_u8f(p1 + 4);
+                    v4[2] = ldg_u8f(p1 + 5);
                 } else {
                     const int o1 = (xl ? x_low : 0) * 3, o2 = (xh ? x_high : 0) * 3;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) v1[k] = v2[k] = v3[k] = v4[k] = cv;
                     if (r0ok && xl) {
-                        v1[0] = __ldg(row0 + o1);
-                        v1[1] = __ldg(row0 + o1 + 1);
-                        v1[2] = __ldg(row0 + o1 + 2);
+                        v1[0] = ldg_u8f(row0 + o1);
+                        v1[1] = ldg_u8f(row0 + o1 + 1);
+                        v1[2] = ldg_u8f(row0 + o1 + 2);
                     }
                     if (r0ok && xh) {
-                        v2[0] = __ldg(row0 + o2);
-                        v2[1] = __ldg(row0 + o2 + 1);
-                        v2[2] = __ldg(row0 + o2 + 2);
+                        v2[0] = ldg_u8f(row0 + o2);
+                        v2[1] = ldg_u8f(row0 + o2 + 1);
+                        v2[2] = ldg_u8f(row0 + o2 + 2);
                     }
                     if (r1ok && xl) {
-                        v3[0] = __ldg(row1 + o1);
-                        v3[1] = __ldg(row1 + o1 + 1);
-                        v3[2] = __ldg(row1 + o1 + 2);
+                        v3[0] = ldg_u8f(row1 + o1);
+                        v3[1] = ldg_u8f(row1 + o1 + 1);
+                        v3[2] = ldg_u8f(row1 + o1 + 2);
                     }
                     if (r1ok && xh) {
-                        v4[0] = __ldg(row1 + o2);
-                        v4[1] = __ldg(row1 + o2 + 1);
-                        v4[2] = __ldg(row1 + o2 + 2);
+                        v4[0] = ldg_u8f(row1 + o2);
+                        v4[1] = ldg_u8f(row1 + o2 + 1);
+                        v4[2] = ldg_u8f(row1 + o2 + 2);
                     }
                 }
                 // :59-61, left-to-right sums
