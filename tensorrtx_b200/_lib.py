@@ -101,7 +101,7 @@ SYMBOLS = {
     "trtx_letterbox_matrix": (None, [_i, _i, _i, _i, C.POINTER(C.c_float)]),
 }
 # tuning knob exported for the bench sweep; not part of the drop-in ABI
-_EXTRA = {"trtx_tune_set": (_i, [_i, _i])}
+_EXTRA = {"trtx_tune_set": (_i, [_i, _i]), "trtx_tune_set_ptr": (_i, [_vp])}
 
 _lib = None
 

@@ -29,6 +29,9 @@
 
 namespace trtx {
 
+static long long* g_nms_dbg = nullptr;
+#define TRTX_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxSort = 2048;  // rows entering NMS per image (>= kMaxNumOutputBbox = 1000)
 constexpr int kShortSeg = 96;  // class segments up to this many rows are resolved by a single warp
@@ -55,6 +58,7 @@ struct NmsArgs {
     int pre_topk;  // rows entering NMS (<= kMaxSort)
     int max_det;
     int extra_floats, extra_offset;
+    long long* dbg;       // profiling aid (trtx_tune_set_ptr): 8 clock64 stamps per image, or null
     float* out;           // [B, 1 + max_det*(7+extra)]
     int32_t* keep_index;  // [B, max_det] or null
 };
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2* list = a.list + (size_t)b * a.list_stride;
 
+    TRTX_STAMP(0);
     // ---------------- A: collect rows above conf_thresh, stash them in shared memory ----------------
     // greedy: `conf <= thr -> skip` (postprocess.cpp:99; false for NaN, which v8 skips too);
     // one-shot: `conf < thr -> skip` (postprocess.cu:57)
@@ -337,6 +342,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         __syncthreads();
     }
 
+    TRTX_STAMP(1);
     // ---------------- C: sort by (class asc, conf desc, box[0] asc, id asc) ----------------
     int S_eff = 32;
     while (S_eff < M) S_eff <<= 1;
@@ -430,6 +436,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         __syncthreads();  // the 128-bit keys (in the sorted-row area) are dead from here on
     }
 
+    TRTX_STAMP(2);
     // ---------------- D: permute the stash into sorted order ----------------
     for (int i = tid; i < M; i += kNmsThreads) {
         const int pos = (int)(k64[i] & 0xffffull);
@@ -469,6 +476,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             }
         }
         __syncthreads();
+        TRTX_STAMP(3);
         // ---- long segments: whole CTA, chunks of 32 ----
         const int n_long = s_nlong;
         for (int ls = 0; ls < n_long; ++ls) {
@@ -513,6 +521,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 n_kept = s_nkept;
             }
         }
+        TRTX_STAMP(4);
         // ---- short segments: one warp each, shuffles + ballots only ----
         const int n_short = s_nshort, n_med = s_nmed;
         for (;;) {
@@ -605,6 +614,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         __syncthreads();
     }
 
+    TRTX_STAMP(5);
     // ---------------- F: block scan of the output flags, rows in sorted (class, conf) order ----------------
     // greedy: only kept rows are emitted; one-shot: every row is emitted with its keep flag
     int carry = 0;
@@ -649,6 +659,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     for (int i = n_rows_out * R + tid; i < a.max_det * R; i += kNmsThreads) o[1 + i] = 0.0f;
     if (oidx)
         for (int i = n_rows_out + tid; i < a.max_det; i += kNmsThreads) oidx[i] = -1;
+    TRTX_STAMP(6);
 }
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
@@ -665,6 +676,7 @@ static int nms_validate(const trtx_nms_params* q) {
 }
 
 static int nms_launch(NmsArgs& a, int batch, cudaStream_t st) {
+    a.dbg = g_nms_dbg;
     if (a.pre_topk > kMaxSort) return TRTX_ERR_UNSUPPORTED;
     const size_t smem = nms_smem_bytes(a.pre_topk, a.from_tiles ? a.tiles_per_image : 0);
     if (smem > 220 * 1024) return TRTX_ERR_UNSUPPORTED;
@@ -679,6 +691,12 @@ static int nms_launch(NmsArgs& a, int batch, cudaStream_t st) {
 using namespace trtx;
 
 extern "C" {
+
+// profiling aid (not part of the drop-in ABI): device buffer of 8*batch int64 receiving clock64 phase stamps of nms_kernel
+TRTX_API int trtx_tune_set_ptr(void* p) {
+    g_nms_dbg = static_cast<long long*>(p);
+    return TRTX_OK;
+}
 
 TRTX_API size_t trtx_nms_workspace_size(const trtx_nms_params* p, int batch, int max_rows) {
     if (nms_validate(p) || batch <= 0 || max_rows <= 0) return 0;

@@ -2,10 +2,10 @@
 // Replaces warpaffine_kernel / cuda_preprocess / cuda_batch_preprocess, yolov8/src/preprocess.cu:7-127
 // (identical bodies in yolov5/7/9/10/11/12/13/26), which launch once per image and synchronise the
 // stream after every image (:119-127).  Here: ONE launch for the whole batch, per-image descriptors
-// and affine matrices in the kernel parameter block (no H2D copy of metadata), each thread produces 4
-// horizontally adjacent destination pixels so that the three planar stores are 128-bit (fp32) or
-// 64-bit (fp16) and fully coalesced.  Layouts that were measured and rejected (profiles/r01j_sweep.log):
-// staging the source band in shared memory (2x slower), one column x four rows per thread (10 % slower).
+// and affine matrices in the kernel parameter block (no H2D copy of metadata); a warp covers 32
+// adjacent destination columns and every thread produces 4 rows of its column.  Measured and rejected
+// (profiles/r01j_sweep.log): 4 adjacent pixels per lane (L1 sector-bound), staging the source band in
+// shared memory (2x slower).
 //
 // Roofline: HBM-bound; algorithmic bytes per image = src_w*src_h*3 (u8 read once) +
 // 3*dst_w*dst_h*sizeof(out) (6 144 000 B for 640x640 -> 640x640 fp32).
@@ -45,60 +45,62 @@ __device__ __forceinline__ float div255(float x) {
 __device__ __forceinline__ float u23_to_float(uint32_t i) { return __uint_as_float(0x4B000000u | i) - 8388608.0f; }
 __device__ __forceinline__ float ldg_u8f(const uint8_t* p) { return u23_to_float((uint32_t)__ldg(p)); }
 
-// One thread = 4 horizontally adjacent destination pixels of one row (vector planar stores).  The letterbox matrix
-// has no rotation (m[1] = m[3] = -0.0f, preprocess.cu:99-104), so the source row pair, the vertical weights and the row
-// validity are computed once per thread; `m3*dx` / `m1*dy` only contribute signed zeros.
+// One thread = ONE destination column x FOUR destination rows; the 32 lanes of a warp are 32 adjacent columns, so a
+// warp-level byte load spans 32 px * 3 B = 96 B = 3-4 sectors (with 4 adjacent pixels per lane it was 11.8 sectors per
+// request and the kernel sat on the L1 sector throughput: 59.5 M sectors for 39 MB of pixels), and the planar stores are
+// 128 contiguous bytes per warp.  The letterbox matrix has no rotation (m[1] = m[3] = -0.0f, preprocess.cu:99-104), so
+// everything that depends on the column only (src_x, x taps, horizontal weights, byte offsets, validity) is computed once
+// for the 4 rows; `m1*dy` / `m3*dx` only contribute signed zeros.
 //
-// The kernel is instruction-issue bound (ncu: 83 % issue-slot utilisation, DRAM < 25 %), so the code is shaped for few
-// instructions per pixel: source coordinates are CLAMPED into the image and the 12 bytes are always loaded through
-// 32-bit offsets from the block-uniform image base (no per-load 64-bit address arithmetic, no divergent border path);
-// out-of-image taps are then replaced by the border value with selects, which is what the reference's pointer
-// redirection to `const_value` does (preprocess.cu:38-57).  u8 -> f32 is a single I2FP; the bilinear sum is written as
-// the reference writes it and left to nvcc's default FMA contraction, exactly like the reference's own build.
+// Few instructions per pixel: source coordinates are CLAMPED into the image and the 12 bytes are always loaded (one
+// address per tap, channels through immediate offsets, no divergent border path); out-of-image taps are then replaced
+// by the border value with selects, which is what the reference's pointer redirection to `const_value` does
+// (preprocess.cu:38-57).  The bilinear sum is written as the reference writes it and left to nvcc's default FMA
+// contraction, exactly like the reference's own build: the output is BIT-IDENTICAL to the reference kernel's
+// (tests/test_vs_reference_gpu.py::test_preprocess_vs_reference_kernel).
 template <typename OutT>
 __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
                                                         int first_image) {
     const int b = blockIdx.z;
     const PreImage& im = a.img[b];
-    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (dy >= a.dh || dx0 >= a.dw) return;
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dy0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
+    if (dx >= a.dw || dy0 >= a.dh) return;
     const size_t area = (size_t)a.dw * a.dh;
-    OutT* base = dst + (size_t)(first_image + b) * 3 * area + (size_t)dy * a.dw + dx0;
+    OutT* base = dst + (size_t)(first_image + b) * 3 * area + (size_t)dy0 * a.dw + dx;
     const float cv = 128.0f;  // const_value_st (:115)
     const uint8_t* __restrict__ img = im.src;
 
-    // preprocess.cu:23 (src_y), evaluated with the thread's first dx: m[3]*dx is +-0 for every dx
-    const float src_y = im.m[3] * (float)dx0 + im.m[4] * (float)dy + im.m[5] + 0.5f;
-    const bool y_out = src_y <= -1 || src_y >= im.sh;
-    const int y_low = (int)floorf(src_y);
-    const int y_high = y_low + 1;
-    const float ly = src_y - (float)y_low;
-    const float hy = 1 - ly;
-    const bool r0ok = y_low >= 0, r1ok = y_high < im.sh;
-    const uint32_t row0 = (uint32_t)min(max(y_low, 0), im.sh - 1) * (uint32_t)im.pitch;   // images < 4 GiB
-    const uint32_t row1 = (uint32_t)min(max(y_high, 0), im.sh - 1) * (uint32_t)im.pitch;
-    const float ym = im.m[1] * (float)dy;
+    // preprocess.cu:22 (src_x), evaluated with the thread's first dy: m[1]*dy is +-0 for every dy
+    const float src_x = im.m[0] * (float)dx + im.m[1] * (float)dy0 + im.m[2] + 0.5f;
+    const bool x_out = src_x <= -1 || src_x >= im.sw;
+    const int x_low = (int)floorf(src_x);
+    const int x_high = x_low + 1;
+    const float lx = src_x - (float)x_low, hx = 1 - lx;
+    const bool xl = x_low >= 0, xh = x_high < im.sw;
+    const uint32_t o1 = (uint32_t)min(max(x_low, 0), im.sw - 1) * 3u, o2 = (uint32_t)min(max(x_high, 0), im.sw - 1) * 3u;
+    const float xm = im.m[3] * (float)dx;
 
-    float r[4], g[4], bl[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int dx = dx0 + i;
+    for (int r = 0; r < 4; ++r) {
+        const int dy = dy0 + r;
+        if (dy >= a.dh) break;
+        const float src_y = xm + im.m[4] * (float)dy + im.m[5] + 0.5f;  // :23
         float c0 = cv, c1 = cv, c2 = cv;
-        const float src_x = im.m[0] * (float)dx + ym + im.m[2] + 0.5f;  // :22
-        if (!(y_out || src_x <= -1 || src_x >= im.sw)) {
-            const int x_low = (int)floorf(src_x);
-            const int x_high = x_low + 1;
-            const float lx = src_x - (float)x_low, hx = 1 - lx;
+        if (!(x_out || src_y <= -1 || src_y >= im.sh)) {
+            const int y_low = (int)floorf(src_y);
+            const int y_high = y_low + 1;
+            const float ly = src_y - (float)y_low, hy = 1 - ly;
             const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-            const bool xl = x_low >= 0, xh = x_high < im.sw;
-            const uint32_t o1 = (uint32_t)max(x_low, 0) * 3u, o2 = (uint32_t)min(x_high, im.sw - 1) * 3u;
+            const bool r0ok = y_low >= 0, r1ok = y_high < im.sh;
+            const uint32_t row0 = (uint32_t)max(y_low, 0) * (uint32_t)im.pitch;               // images < 4 GiB
+            const uint32_t row1 = (uint32_t)min(y_high, im.sh - 1) * (uint32_t)im.pitch;
             const bool k1 = r0ok && xl, k2 = r0ok && xh, k3 = r1ok && xl, k4 = r1ok && xh;
-            float v1[3], v2[3], v3[3], v4[3];
             const uint8_t* p1 = img + (row0 + o1);  // one address per tap, channels through immediate offsets
             const uint8_t* p2 = img + (row0 + o2);
             const uint8_t* p3 = img + (row1 + o1);
             const uint8_t* p4 = img + (row1 + o2);
+            float v1[3], v2[3], v3[3], v4[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const float t1 = (float)(uint32_t)__ldg(p1 + k);
@@ -115,41 +117,16 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ 
             c1 = w1 * v1[1] + w2 * v2[1] + w3 * v3[1] + w4 * v4[1];
             c2 = w1 * v1[2] + w2 * v2[2] + w3 * v3[2] + w4 * v4[2];
         }
-        // bgr -> rgb, /255 (:64-74)
-        r[i] = div255(c2);
-        g[i] = div255(c1);
-        bl[i] = div255(c0);
-    }
-    const bool vec_ok = (dx0 + 3 < a.dw) && (a.dw % 4 == 0);
-    if constexpr (sizeof(OutT) == 4) {
-        if (vec_ok) {
-            *reinterpret_cast<float4*>(base) = make_float4(r[0], r[1], r[2], r[3]);
-            *reinterpret_cast<float4*>(base + area) = make_float4(g[0], g[1], g[2], g[3]);
-            *reinterpret_cast<float4*>(base + 2 * area) = make_float4(bl[0], bl[1], bl[2], bl[3]);
+        // bgr -> rgb, /255 (:64-74); planar stores, 128 B per warp and plane
+        OutT* o = base + (size_t)r * a.dw;
+        if constexpr (sizeof(OutT) == 4) {
+            o[0] = div255(c2);
+            o[area] = div255(c1);
+            o[2 * area] = div255(c0);
         } else {
-            for (int i = 0; i < 4 && dx0 + i < a.dw; ++i) {
-                base[i] = r[i];
-                base[area + i] = g[i];
-                base[2 * area + i] = bl[i];
-            }
-        }
-    } else {
-        if (vec_ok && (area % 4 == 0)) {
-            __half2 r01 = __floats2half2_rn(r[0], r[1]), r23 = __floats2half2_rn(r[2], r[3]);
-            __half2 g01 = __floats2half2_rn(g[0], g[1]), g23 = __floats2half2_rn(g[2], g[3]);
-            __half2 b01 = __floats2half2_rn(bl[0], bl[1]), b23 = __floats2half2_rn(bl[2], bl[3]);
-            uint2 pr = make_uint2(*reinterpret_cast<uint32_t*>(&r01), *reinterpret_cast<uint32_t*>(&r23));
-            uint2 pg = make_uint2(*reinterpret_cast<uint32_t*>(&g01), *reinterpret_cast<uint32_t*>(&g23));
-            uint2 pb = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
-            *reinterpret_cast<uint2*>(base) = pr;
-            *reinterpret_cast<uint2*>(base + area) = pg;
-            *reinterpret_cast<uint2*>(base + 2 * area) = pb;
-        } else {
-            for (int i = 0; i < 4 && dx0 + i < a.dw; ++i) {
-                base[i] = __float2half_rn(r[i]);
-                base[area + i] = __float2half_rn(g[i]);
-                base[2 * area + i] = __float2half_rn(bl[i]);
-            }
+            o[0] = __float2half_rn(div255(c2));
+            o[area] = __float2half_rn(div255(c1));
+            o[2 * area] = __float2half_rn(div255(c0));
         }
     }
 }
@@ -211,8 +188,8 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
             a.img[i].pitch = d.pitch;
             trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, a.img[i].m);
         }
-        dim3 block(64, 4, 1);
-        dim3 grid((dst_w + 4 * 64 - 1) / (4 * 64), (dst_h + 3) / 4, n);
+        dim3 block(128, 2, 1);  // 128 columns x (2 x 4) rows per block
+        dim3 grid((dst_w + 127) / 128, (dst_h + 7) / 8, n);
         if (out_dtype == TRTX_F32)
             letterbox_kernel<float><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
         else
