@@ -5,14 +5,19 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it, and there only as the checker / the CPU comparator.
  *
- * PARITY STATUS: the reference (wang-xinyu/tensorrtx) ships NO tests, golden vectors
- * or fixtures for this path.  The decode restatements below
- * are therefore "parity unpinned" against golden vectors; they are pinned instead
- *   (a) for the CPU NMS functions: against the reference's own nms()/iou()/cmp()
- *       compiled from /root/reference sources with header shims (oracle/_ref,
- *       see oracle/Makefile + tests/test_oracle_vs_ref.py), and
- *   (b) for the GPU plugin kernels: against the reference .cu files compiled with a
- *       mock NvInfer.h into oracle/_ref/ and run on the GPU box (tests -m gpu).
+ * PARITY STATUS: the reference (wang-xinyu/tensorrtx) ships NO tests, golden vectors or fixtures
+ * for this path, so there is nothing of its own to check against.
+ * The restatements are PINNED against the reference itself, compiled here from /root/reference:
+ *   (a) CPU NMS functions: bit-identical rows, in identical order, to the reference's own
+ *       nms()/iou()/cmp() -- oracle/_ref/libref_{yolov8,yolov5,retina}_host.so, built by
+ *       oracle/Makefile from the reference's postprocess.cpp / common.hpp with header shims;
+ *       tests/test_oracle_vs_ref_cpu.py (runs without a GPU).
+ *   (b) GPU plugin kernels (decode, cuda_decode/cuda_nms, warpaffine, rcnn functions): the
+ *       reference's .cu files compiled against tests/mock_trt/NvInfer.h into oracle/_ref/libref_*.so
+ *       and run next to our kernels on the GPU box; tests/test_vs_reference_gpu.py.  The decode
+ *       restatements below agree with those kernels to <= 2 ulp (glibc vs CUDA expf).
+ *   (c) independent cross-checks: torchvision nms/batched_nms, cv2.invertAffineTransform, a numpy
+ *       re-derivation of the v8 decode (tests/test_oracle_cpu.py).
  *
  * Every function cites the reference file:line (relative to /root/reference) it
  * restates.  Plain C, single thread, no FMA contraction (build with
