@@ -390,7 +390,7 @@ def main():
                             "event pair (adds ~3 us of event latency per launch); copy_engine_ceiling = tools/tma_bench.cu, "
                             "the same [32,84,g] fp32 tiles streamed by TMA with no compute (profiles/r01f_reg_probe.log)"},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only (bounded sample of the same workload)
         cores = host_cores()
         total = 128 * cores  # ~0.5 s of CPU work per core: bounded sample
         cfps, _ = cpu_decode_nms_fps(heads_np0, total, cores)

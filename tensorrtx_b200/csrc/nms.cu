@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_long + S / 2);   // S   slow path: stash position riding along
     unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_pos + S);         // S   keep flags
     int* s_tpre = reinterpret_cast<int*>(s_keep + S);                            // tiles_per_image + 1 (fused path)
-    float4* s_kbox = u_box;  // kept boxes of a segment: aliases the stash (dead once the rows are permuted)
+    float4* s_kbox = u_box;  // kept boxes of a long segment: aliases the stash (dead once the rows are permuted)
+    unsigned* s_mask = reinterpret_cast<unsigned*>(u_conf);  // 3 words per row: suppressor bitmaps (aliases u_conf/u_cls/u_id)
+    int* s_rowseg = reinterpret_cast<int*>(k64);             // per row: segment start << 16 | length (aliases the sort keys)
     // slow path only: 128-bit keys live in the (not yet filled) sorted-row area
     unsigned long long* k_hi = reinterpret_cast<unsigned long long*>(s_box);
     unsigned long long* k_lo = k_hi + S;
@@ -191,8 +193,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     __shared__ unsigned s_rem;
     __shared__ unsigned s_sup[32];
     __shared__ int s_wsum[32];
-    __shared__ unsigned s_wsup[32 * 32];  // per-warp suppressor bitmaps of the short-segment path
-    __shared__ unsigned s_wrem[32];       // per-warp "removed by an already kept row" bits
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -467,6 +467,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 int e = i + 1;
                 while (e < M && s_cls[e] == s_cls[i]) ++e;
                 const int m = e - i;
+                // every row learns its segment (start << 16 | length; 0 = long segment, handled by the whole CTA)
+                for (int r = i; r < e; ++r) s_rowseg[r] = m > kShortSeg ? 0 : ((i << 16) | m);
                 if (m > kShortSeg)
                     s_long[atomicAdd(&s_nlong, 1)] = (i << 16) | m;  // M <= 2048: start and length fit 16 bits
                 else if (m > 32)
@@ -522,7 +524,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             }
         }
         TRTX_STAMP(4);
-        // ---- short segments: one warp each, shuffles + ballots only ----
+        // ---- short / medium segments (<= kShortSeg rows) ----
+        // (1) all threads: row i tests itself against the earlier rows of its segment and builds its suppressor
+        //     bitmap (bit j = row start+j overlaps it) -- every IoU of every segment in one balanced, barrier-free sweep
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const int rs = s_rowseg[i];
+            if (rs == 0) continue;
+            const int p0 = rs >> 16, li = i - p0;
+            const float4 bi = s_box[i];
+            unsigned mk[kShortSeg / 32] = {0u, 0u, 0u};
+#pragma unroll
+            for (int w = 0; w < kShortSeg / 32; ++w) {  // static word index: the bitmap stays in registers
+                const int hi = min(li, (w + 1) * 32);
+                for (int jx = w * 32; jx < hi; ++jx)
+                    if (iou_any(a.box_format, s_box[p0 + jx], bi) > a.nms_thresh) mk[w] |= 1u << (jx & 31);
+            }
+#pragma unroll
+            for (int w = 0; w < kShortSeg / 32; ++w) s_mask[i * (kShortSeg / 32) + w] = mk[w];
+        }
+        __syncthreads();
+        // (2) one warp per segment resolves the greedy order on the bitmaps: 32 rows per step, ballots only
         const int n_short = s_nshort, n_med = s_nmed;
         for (;;) {
             int sidx = 0;
@@ -531,69 +552,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             if (sidx >= n_med + n_short) break;
             const int ent = sidx < n_med ? s_seg[S - 1 - sidx] : s_seg[sidx - n_med];
             const int p0 = ent >> 16, m = ent & 0xffff;
-            if (m == 1) {
-                if (lane == 0) s_keep[p0] = 1;
-                continue;
-            }
-            if (m <= 32) {
-                // single chunk: the m(m-1)/2 pairs are spread over the 32 lanes (4 rounds for a typical 15-row
-                // segment instead of 14 dependent broadcast rounds); hits go to the warp's 32-word bitmap
-                unsigned* sup = s_wsup + warp * 32;
-                sup[lane] = 0;
-                __syncwarp();
-                const int npairs = m * (m - 1) / 2;
-                for (int pr = lane; pr < npairs; pr += 32) {
-                    int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f);  // row i > column jx, pr = i(i-1)/2 + jx
-                    while (i * (i - 1) / 2 > pr) --i;
-                    while ((i + 1) * i / 2 <= pr) ++i;
-                    const int jx = pr - i * (i - 1) / 2;
-                    if (iou_any(a.box_format, s_box[p0 + jx], s_box[p0 + i]) > a.nms_thresh) atomicOr(&sup[i], 1u << jx);
+            unsigned kept[kShortSeg / 32] = {0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c < kShortSeg / 32; ++c) {
+                if (c * 32 >= m) break;
+                const int nchunk = min(32, m - c * 32);
+                const bool in = lane < nchunk;
+                const int row = p0 + c * 32 + lane;
+                unsigned mw[kShortSeg / 32] = {0u, 0u, 0u};
+                if (in) {
+#pragma unroll
+                    for (int w = 0; w <= c; ++w) mw[w] = s_mask[row * (kShortSeg / 32) + w];
                 }
-                __syncwarp();
-                const unsigned mymask = sup[lane];
-                unsigned alive = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
-                for (int jx = 0; jx < m; ++jx) {
-                    const unsigned kill = __ballot_sync(0xffffffffu, (mymask >> jx) & 1u);
-                    if ((alive >> jx) & 1u) alive &= ~kill;
-                }
-                if ((alive >> lane) & 1u) s_keep[p0 + lane] = 1;
-                __syncwarp();
-                continue;
-            }
-            // 33..kShortSeg rows: chunks of 32, every IoU pair (chunk x kept, chunk x chunk) spread over the lanes
-            unsigned* sup = s_wsup + warp * 32;
-            int nk = 0;
-            for (int c0 = 0; c0 < m; c0 += 32) {
-                const int nchunk = min(32, m - c0);
-                sup[lane] = 0;
-                if (lane == 0) s_wrem[warp] = 0;
-                __syncwarp();
-                for (int pr = lane; pr < nk * nchunk; pr += 32) {
-                    const int k = pr / nchunk, i = pr - k * nchunk;
-                    if (iou_any(a.box_format, s_kbox[p0 + k], s_box[p0 + c0 + i]) > a.nms_thresh) atomicOr(&s_wrem[warp], 1u << i);
-                }
-                const int npairs = nchunk * (nchunk - 1) / 2;
-                for (int pr = lane; pr < npairs; pr += 32) {
-                    int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f);
-                    while (i * (i - 1) / 2 > pr) --i;
-                    while ((i + 1) * i / 2 <= pr) ++i;
-                    const int jx = pr - i * (i - 1) / 2;
-                    if (iou_any(a.box_format, s_box[p0 + c0 + jx], s_box[p0 + c0 + i]) > a.nms_thresh) atomicOr(&sup[i], 1u << jx);
-                }
-                __syncwarp();
-                const unsigned mymask = sup[lane];
-                unsigned alive = ~s_wrem[warp] & (nchunk == 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
+                bool removed = false;
+#pragma unroll
+                for (int w = 0; w < c; ++w) removed |= (mw[w] & kept[w]) != 0u;  // suppressed by a kept row of an earlier chunk
+                unsigned alive = __ballot_sync(0xffffffffu, in && !removed);
+                const unsigned mymask = mw[c];
                 for (int jx = 0; jx < nchunk; ++jx) {
                     const unsigned kill = __ballot_sync(0xffffffffu, (mymask >> jx) & 1u);
                     if ((alive >> jx) & 1u) alive &= ~kill;
                 }
-                if ((alive >> lane) & 1u) {
-                    const int pos = nk + __popc(alive & ((1u << lane) - 1u));
-                    s_kbox[p0 + pos] = s_box[p0 + c0 + lane];
-                    s_keep[p0 + c0 + lane] = 1;
-                }
-                nk += __popc(alive);
-                __syncwarp();
+                kept[c] = alive;
+                if ((alive >> lane) & 1u) s_keep[row] = 1;
             }
         }
         __syncthreads();
