@@ -30,10 +30,12 @@
 namespace trtx {
 
 static long long* g_nms_dbg = nullptr;
-#define TRTX_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#define TRTX_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 16 + (k)] = clock64(); } while (0)
 
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxSort = 2048;  // rows entering NMS per image (>= kMaxNumOutputBbox = 1000)
+constexpr int kClassBins = kNmsThreads;  // bucket sort: one histogram bin per thread
+constexpr int kMaxBucket = 256;           // rows per class the rank-by-counting pass accepts
 constexpr int kShortSeg = 96;  // class segments up to this many rows are resolved by a single warp
 
 struct NmsArgs {
@@ -180,7 +182,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     int* s_long = s_seg + S;                                                     // S/2 long class segments
     unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_long + S / 2);   // S   slow path: stash position riding along
     unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_pos + S);         // S   keep flags
-    int* s_tpre = reinterpret_cast<int*>(s_keep + S);                            // tiles_per_image + 1 (fused path)
+    unsigned short* s_unit = reinterpret_cast<unsigned short*>(s_keep + S);      // S*12 IoU work units (row << 4 | group of 8)
+    int* s_tpre = reinterpret_cast<int*>(s_unit + S * (kShortSeg / 8));          // tiles_per_image + 1 (fused path)
     float4* s_kbox = u_box;  // kept boxes of a long segment: aliases the stash (dead once the rows are permuted)
     unsigned* s_mask = reinterpret_cast<unsigned*>(u_conf);  // 3 words per row: suppressor bitmaps (aliases u_conf/u_cls/u_id)
     int* s_rowseg = reinterpret_cast<int*>(k64);             // per row: segment start << 16 | length (aliases the sort keys)
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     unsigned long long* k_lo = k_hi + S;
 
     __shared__ int s_hist[256];
-    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nmed, s_nlong, s_cursor, s_bad;
+    __shared__ int s_chist[kClassBins], s_cstart[kClassBins];  // bucket sort: rows per class, first sorted row of a class
+    __shared__ int s_n, s_need, s_bucket, s_nkept, s_nshort, s_nmed, s_nlong, s_cursor, s_bad, s_nunit;
     __shared__ unsigned s_rem;
     __shared__ unsigned s_sup[32];
     __shared__ int s_wsum[32];
@@ -349,7 +353,62 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     // fast path: packed key = class(16) | ~conf key(32) | stash position(16); exact unless two rows share
     // (class, conf) -- detected below, then the generic 128-bit sort decides by (box[0], id).
     bool generic = s_bad != 0;
+    // fastest path (the detector case: many classes, a few dozen rows each): counting sort by class, then every row
+    // ranks itself inside its class bucket by counting smaller keys -- no compare-exchange network, 5 barriers.
+    // Falls through to the bitonic paths when a class id is >= kClassBins or a bucket holds more than kMaxBucket rows.
+    bool bucketed = false;
     if (!generic) {
+        unsigned long long* kb = reinterpret_cast<unsigned long long*>(s_box);  // keys in bucket order (rows not staged yet)
+        s_chist[tid] = 0;
+        __syncthreads();
+        bool big = false;
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const int c = u_cls[i];
+            if (c < kClassBins)
+                s_pos[i] = (unsigned short)atomicAdd(&s_chist[c], 1);  // arrival order inside the bucket (any order works)
+            else
+                big = true;
+        }
+        const int any_big = __syncthreads_or(big ? 1 : 0);
+        const int h = s_chist[tid];
+        if (!any_big && !__syncthreads_or(h > kMaxBucket ? 1 : 0)) {
+            int tot;
+            const int ex = warp_excl_scan(h, lane, &tot);
+            if (lane == 0) s_wsum[warp] = tot;
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_wsum[lane], wt;
+                const int wex = warp_excl_scan(w, lane, &wt);
+                s_wsum[lane] = wex;
+            }
+            __syncthreads();
+            s_cstart[tid] = s_wsum[warp] + ex;
+            __syncthreads();
+            for (int i = tid; i < M; i += kNmsThreads) {
+                const int c = u_cls[i];
+                kb[s_cstart[c] + s_pos[i]] =
+                    ((unsigned long long)(uint32_t)c << 48) | ((unsigned long long)(uint32_t)(~float_key(u_conf[i])) << 16) | (uint32_t)i;
+            }
+            __syncthreads();
+            // thread p owns bucket slot p: neighbouring lanes share a bucket, so the key reads below are broadcasts
+            bool tie = false;
+            for (int p = tid; p < M; p += kNmsThreads) {
+                const unsigned long long mk = kb[p];
+                const int c = (int)(mk >> 48);
+                const int s0 = s_cstart[c], m = s_chist[c];
+                int rank = 0;
+                for (int k = 0; k < m; ++k) {
+                    const unsigned long long ok = kb[s0 + k];
+                    rank += ok < mk ? 1 : 0;
+                    tie |= (ok >> 16) == (mk >> 16) && ok != mk;  // same (class, conf): the generic sort decides
+                }
+                k64[s0 + rank] = mk;
+            }
+            generic = __syncthreads_or(tie ? 1 : 0) != 0;
+            bucketed = !generic;
+        }
+    }
+    if (!generic && !bucketed) {
         for (int i = tid; i < S_eff; i += kNmsThreads)
             k64[i] = i < M ? ((unsigned long long)(uint32_t)u_cls[i] << 48) | ((unsigned long long)(uint32_t)(~float_key(u_conf[i])) << 16) | (uint32_t)i
                            : ~0ull;
@@ -453,8 +512,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         s_nmed = 0;
         s_nlong = 0;
         s_cursor = 0;
+        s_nunit = 0;
     }
     __syncthreads();
+    TRTX_STAMP(8);
 
     const int R = 7 + a.extra_floats;
     float* o = a.out + (size_t)b * (1 + (size_t)a.max_det * R);
@@ -462,6 +523,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 
     if (a.mode == TRTX_NMS_GREEDY) {
         // ---------------- E: class segments ----------------
+        if (bucketed) {
+            // the class histogram already is the segment table
+            for (int i = tid; i < M; i += kNmsThreads) {
+                const int c = s_cls[i], m = s_chist[c];
+                s_rowseg[i] = m > kShortSeg ? 0 : ((s_cstart[c] << 16) | m);
+            }
+            const int m = s_chist[tid], p0 = s_cstart[tid];
+            if (m > kShortSeg)
+                s_long[atomicAdd(&s_nlong, 1)] = (p0 << 16) | m;
+            else if (m > 32)
+                s_seg[S - 1 - atomicAdd(&s_nmed, 1)] = (p0 << 16) | m;
+            else if (m > 0)
+                s_seg[atomicAdd(&s_nshort, 1)] = (p0 << 16) | m;
+        } else
         for (int i = tid; i < M; i += kNmsThreads) {
             if (i == 0 || s_cls[i] != s_cls[i - 1]) {
                 int e = i + 1;
@@ -504,10 +579,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 if (warp == 0) {
                     const unsigned my = s_sup[lane];
                     unsigned alive = ~s_rem & (nchunk == 32 ? 0xffffffffu : ((1u << nchunk) - 1u));
-#pragma unroll
-                    for (int jx = 0; jx < 32; ++jx) {
+                    for (unsigned rem = alive; rem != 0u;) {
+                        const int jx = __ffs(rem) - 1;
                         const unsigned kill = __ballot_sync(0xffffffffu, (my >> jx) & 1u);
-                        if ((alive >> jx) & 1u) alive &= ~kill;
+                        alive &= ~kill;
+                        rem = alive & ~((2u << jx) - 1u);
                     }
                     if ((alive >> lane) & 1u) {
                         const int pos = n_kept + __popc(alive & ((1u << lane) - 1u));
@@ -525,24 +601,47 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         }
         TRTX_STAMP(4);
         // ---- short / medium segments (<= kShortSeg rows) ----
-        // (1) all threads: row i tests itself against the earlier rows of its segment and builds its suppressor
-        //     bitmap (bit j = row start+j overlaps it) -- every IoU of every segment in one balanced, barrier-free sweep
-        for (int i = tid; i < M; i += kNmsThreads) {
-            const int rs = s_rowseg[i];
-            if (rs == 0) continue;
-            const int p0 = rs >> 16, li = i - p0;
-            const float4 bi = s_box[i];
-            unsigned mk[kShortSeg / 32] = {0u, 0u, 0u};
+        // (1) IoU of every row against the earlier rows of its segment -> suppressor bitmap per row (bit j = row start+j
+        //     overlaps it).  Work unit = (row, 8 earlier rows) = one byte of the bitmap; the units of all segments go
+        //     into one list so the 1024 threads share them evenly whatever the segment lengths are.
+        for (int base = 0; base < M; base += kNmsThreads) {
+            const int i = base + tid;
+            int cnt = 0;
+            if (i < M) {
+                const int rs = s_rowseg[i];
+                if (rs != 0) {
+                    cnt = (i - (rs >> 16) + 7) >> 3;
 #pragma unroll
-            for (int w = 0; w < kShortSeg / 32; ++w) {  // static word index: the bitmap stays in registers
-                const int hi = min(li, (w + 1) * 32);
-                for (int jx = w * 32; jx < hi; ++jx)
-                    if (iou_any(a.box_format, s_box[p0 + jx], bi) > a.nms_thresh) mk[w] |= 1u << (jx & 31);
+                    for (int w = 0; w < kShortSeg / 32; ++w) s_mask[i * (kShortSeg / 32) + w] = 0u;
+                }
             }
-#pragma unroll
-            for (int w = 0; w < kShortSeg / 32; ++w) s_mask[i * (kShortSeg / 32) + w] = mk[w];
+            int tot;
+            const int ex = warp_excl_scan(cnt, lane, &tot);
+            int wbase = 0;
+            if (lane == 0 && tot > 0) wbase = atomicAdd(&s_nunit, tot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            for (int g = 0; g < cnt; ++g) s_unit[wbase + ex + g] = (unsigned short)((i << 4) | g);
         }
         __syncthreads();
+        TRTX_STAMP(9);
+        {
+            const int n_unit = s_nunit;
+            unsigned char* mask_bytes = reinterpret_cast<unsigned char*>(s_mask);
+            for (int u = tid; u < n_unit; u += kNmsThreads) {
+                const int e = s_unit[u], i = e >> 4, g = e & 15;
+                const int p0 = s_rowseg[i] >> 16, li = i - p0;
+                const float4 bi = s_box[i];
+                unsigned bits = 0u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int jx = g * 8 + k;
+                    if (jx < li && iou_any(a.box_format, s_box[p0 + jx], bi) > a.nms_thresh) bits |= 1u << k;
+                }
+                mask_bytes[i * (kShortSeg / 8) + g] = (unsigned char)bits;  // little-endian: byte g of the row's 3 words
+            }
+        }
+        __syncthreads();
+        TRTX_STAMP(7);
         // (2) one warp per segment resolves the greedy order on the bitmaps: 32 rows per step, ballots only
         const int n_short = s_nshort, n_med = s_nmed;
         for (;;) {
@@ -569,9 +668,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 for (int w = 0; w < c; ++w) removed |= (mw[w] & kept[w]) != 0u;  // suppressed by a kept row of an earlier chunk
                 unsigned alive = __ballot_sync(0xffffffffu, in && !removed);
                 const unsigned mymask = mw[c];
-                for (int jx = 0; jx < nchunk; ++jx) {
-                    const unsigned kill = __ballot_sync(0xffffffffu, (mymask >> jx) & 1u);
-                    if ((alive >> jx) & 1u) alive &= ~kill;
+                for (unsigned rem = alive; rem != 0u;) {  // visit surviving rows only: one ballot per kept row
+                    const int jx = __ffs(rem) - 1;
+                    const unsigned kill = __ballot_sync(0xffffffffu, (mymask >> jx) & 1u);  // later rows that row jx suppresses
+                    alive &= ~kill;
+                    rem = alive & ~((2u << jx) - 1u);
                 }
                 kept[c] = alive;
                 if ((alive >> lane) & 1u) s_keep[row] = 1;
@@ -645,7 +746,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
     const size_t S = pre_topk <= 1024 ? 1024 : kMaxSort;
-    return S * (16 + 16 + 8 + 6 * 4 + 4 + 2 + 2 + 1) + 64 + sizeof(int) * (size_t)(tiles + 1);
+    return S * (16 + 16 + 8 + 6 * 4 + 4 + 2 + 2 + 1 + 2 * (kShortSeg / 8)) + 64 + sizeof(int) * (size_t)(tiles + 1);
 }
 
 static int nms_validate(const trtx_nms_params* q) {
@@ -660,9 +761,11 @@ static int nms_launch(NmsArgs& a, int batch, cudaStream_t st) {
     a.dbg = g_nms_dbg;
     if (a.pre_topk > kMaxSort) return TRTX_ERR_UNSUPPORTED;
     const size_t smem = nms_smem_bytes(a.pre_topk, a.from_tiles ? a.tiles_per_image : 0);
-    if (smem > 220 * 1024) return TRTX_ERR_UNSUPPORTED;
+    // 227 KB per CTA minus the kernel's static shared memory (histograms, ~18 KB)
+    constexpr size_t kMaxDynSmem = (227 - 20) * 1024;
+    if (smem > kMaxDynSmem) return TRTX_ERR_UNSUPPORTED;
     // per-device function attribute; cheap and idempotent, so set on every call (no global state)
-    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     nms_kernel<<<batch, kNmsThreads, smem, st>>>(a);
     return check_launch();
 }
@@ -673,7 +776,7 @@ using namespace trtx;
 
 extern "C" {
 
-// profiling aid (not part of the drop-in ABI): device buffer of 8*batch int64 receiving clock64 phase stamps of nms_kernel
+// profiling aid (not part of the drop-in ABI): device buffer of 16*batch int64 receiving clock64 phase stamps of nms_kernel
 TRTX_API int trtx_tune_set_ptr(void* p) {
     g_nms_dbg = static_cast<long long*>(p);
     return TRTX_OK;

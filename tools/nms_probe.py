@@ -11,17 +11,23 @@ B = 32
 heads = [torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=0)]
 plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
 fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-dbg = torch.zeros(B * 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(B * 16, dtype=torch.int64, device=dev)
 fused.enqueue(B, heads); torch.cuda.synchronize()
 lib.trtx_tune_set_ptr(dbg.data_ptr())
-acc = torch.zeros(7)
+# stamp ids in program order (nms.cu TRTX_STAMP): label = phase that ends at the stamp
+order = [(0, "start"), (1, "A collect+stash"), (2, "C sort"), (8, "D permute"), (3, "E segment table"),
+         (4, "E long segments"), (9, "E unit list"), (7, "E IoU bitmaps"), (5, "E resolve"), (6, "F output")]
 N = 20
+acc = torch.zeros(len(order))
 for _ in range(N):
     fused.enqueue(B, heads); torch.cuda.synchronize()
-    d = dbg.view(B, 8).cpu().double()
-    acc[:6] += (d[:, 1:7] - d[:, 0:6]).mean(0).float()
-    acc[6] += (d[:, 6] - d[:, 0]).max().float()
+    d = dbg.view(B, 16).cpu().double()
+    for k in range(1, len(order)):
+        acc[k] += (d[:, order[k][0]] - d[:, order[k - 1][0]]).mean().item()
+    acc[0] += (d[:, 6] - d[:, 0]).max().item()
 lib.trtx_tune_set_ptr(None)
-names = ["A collect+stash", "C sort", "D permute", "E1 segment detect", "E2 long segs", "E3 short/medium segs", "max total (cycles)"]
-for n, v in zip(names, (acc / N).tolist()):
-    print(f"{n:24s} {v:10.0f} cycles  {v / 1965.0:7.2f} us")
+for k in range(1, len(order)):
+    v = acc[k].item() / N
+    print(f"{order[k][1]:24s} {v:10.0f} cycles  {v / 1965.0:7.2f} us")
+v = acc[0].item() / N
+print(f"{'max total':24s} {v:10.0f} cycles  {v / 1965.0:7.2f} us")
