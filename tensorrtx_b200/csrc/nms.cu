@@ -66,44 +66,10 @@ struct NmsArgs {
 };
 
 // ---- IoU variants -------------------------------------------------------------------------
-// yolov8/src/postprocess.cpp:71-85 (std::max(a,b) = a<b ? b : a ; std::min(a,b) = b<a ? b : a)
-__device__ __forceinline__ float iou_ltrb(const float4 l, const float4 r) {
-    float ib0 = l.x < r.x ? r.x : l.x;
-    float ib1 = r.z < l.z ? r.z : l.z;
-    float ib2 = l.y < r.y ? r.y : l.y;
-    float ib3 = r.w < l.w ? r.w : l.w;
-    if (ib2 > ib3 || ib0 > ib1) return 0.0f;
-    float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
-    float la = __fmul_rn(__fsub_rn(l.z, l.x), __fsub_rn(l.w, l.y));
-    float ra = __fmul_rn(__fsub_rn(r.z, r.x), __fsub_rn(r.w, r.y));
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(la, ra), inter));
-}
-// yolov5/src/postprocess.cpp:30-43
-__device__ __forceinline__ float iou_cxcywh(const float4 l, const float4 r) {
-    float a0 = __fsub_rn(l.x, __fdiv_rn(l.z, 2.f)), b0 = __fsub_rn(r.x, __fdiv_rn(r.z, 2.f));
-    float a1 = __fadd_rn(l.x, __fdiv_rn(l.z, 2.f)), b1 = __fadd_rn(r.x, __fdiv_rn(r.z, 2.f));
-    float a2 = __fsub_rn(l.y, __fdiv_rn(l.w, 2.f)), b2 = __fsub_rn(r.y, __fdiv_rn(r.w, 2.f));
-    float a3 = __fadd_rn(l.y, __fdiv_rn(l.w, 2.f)), b3 = __fadd_rn(r.y, __fdiv_rn(r.w, 2.f));
-    float ib0 = a0 < b0 ? b0 : a0;
-    float ib1 = b1 < a1 ? b1 : a1;
-    float ib2 = a2 < b2 ? b2 : a2;
-    float ib3 = b3 < a3 ? b3 : a3;
-    if (ib2 > ib3 || ib0 > ib1) return 0.0f;
-    float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(__fmul_rn(l.z, l.w), __fmul_rn(r.z, r.w)), inter));
-}
-// retinaface/common.hpp:91-104
-__device__ __forceinline__ float iou_retina(const float4 l, const float4 r) {
-    float ib0 = l.x < r.x ? r.x : l.x;
-    float ib1 = r.z < l.z ? r.z : l.z;
-    float ib2 = l.y < r.y ? r.y : l.y;
-    float ib3 = r.w < l.w ? r.w : l.w;
-    if (ib2 > ib3 || ib0 > ib1) return 0.0f;
-    float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
-    float la = __fmul_rn(__fsub_rn(l.z, l.x), __fsub_rn(l.w, l.y));
-    float ra = __fmul_rn(__fsub_rn(r.z, r.x), __fsub_rn(r.w, r.y));
-    return __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(la, ra), inter), 0.000001f));
-}
+// Host IoUs restated by to_corners / box_area / overlaps below:
+//   yolov8/src/postprocess.cpp:71-85  l,t,r,b     inter / (la + ra - inter)       (std::max(a,b) = a<b ? b : a)
+//   yolov5/src/postprocess.cpp:30-43  cx,cy,w,h   corners x -/+ w/2, areas w*h
+//   retinaface/common.hpp:91-104      l,t,r,b     inter / (la + ra - inter + 0.000001f)
 // yolov8/src/postprocess.cu:74-87 (device box_iou of the one-shot path)
 __device__ __forceinline__ float iou_oneshot(const float4 a, const float4 b) {
     float cl = fmaxf(a.x, b.x), ct = fmaxf(a.y, b.y), cr = fminf(a.z, b.z), cb = fminf(a.w, b.w);
@@ -113,10 +79,41 @@ __device__ __forceinline__ float iou_oneshot(const float4 a, const float4 b) {
     float b_area = __fmul_rn(fmaxf(0.0f, __fsub_rn(b.z, b.x)), fmaxf(0.0f, __fsub_rn(b.w, b.y)));
     return __fdiv_rn(c_area, __fsub_rn(__fadd_rn(a_area, b_area), c_area));
 }
-__device__ __forceinline__ float iou_any(int fmt, const float4 l, const float4 r) {
-    if (fmt == TRTX_BOX_LTRB) return iou_ltrb(l, r);
-    if (fmt == TRTX_BOX_CXCYWH) return iou_cxcywh(l, r);
-    return iou_retina(l, r);
+// ---- greedy NMS inner loop: boxes pre-converted to corners, areas precomputed ---------------------------------
+// The three host IoUs above differ only in how corners and areas are formed and in retinaface's +1e-6; with those
+// hoisted out (phase D) one test serves all.  Every operation is the reference's, in the reference's order.
+__device__ __forceinline__ float4 to_corners(int fmt, const float4 b) {
+    if (fmt != TRTX_BOX_CXCYWH) return b;
+    // x/2 == x*0.5 exactly in binary floating point
+    const float hw = __fmul_rn(b.z, 0.5f), hh = __fmul_rn(b.w, 0.5f);
+    return make_float4(__fsub_rn(b.x, hw), __fsub_rn(b.y, hh), __fadd_rn(b.x, hw), __fadd_rn(b.y, hh));
+}
+__device__ __forceinline__ float box_area(int fmt, const float4 b) {  // b = the row as stored (before to_corners)
+    if (fmt == TRTX_BOX_CXCYWH) return __fmul_rn(b.z, b.w);
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+struct IouTest {
+    float thr;
+    bool retina;    // denominator + 0.000001f
+    bool zero_hit;  // `0.0f > thr` (disjoint boxes)
+    bool fast_ok;   // the division-free test below is proven for |thr| <= 4
+};
+// == (iou(l, r) > thr) bit for bit.  fl(inter/denom) > thr is decided by the sign of t = inter - thr*denom (one FMA
+// rounding, so sign and magnitude of t are right to 2^-24) whenever |t| > 1e-5*denom, i.e. the true quotient is at
+// least ~1e-5 away from thr -- hundreds of ulps for |thr| <= 4.  Anything closer, or a non-positive / non-finite
+// denominator, takes the IEEE division the reference takes.
+__device__ __forceinline__ bool overlaps(const IouTest& q, const float4 l, float la, const float4 r, float ra) {
+    const float ib0 = l.x < r.x ? r.x : l.x;
+    const float ib1 = r.z < l.z ? r.z : l.z;
+    const float ib2 = l.y < r.y ? r.y : l.y;
+    const float ib3 = r.w < l.w ? r.w : l.w;
+    if (ib2 > ib3 || ib0 > ib1) return q.zero_hit;
+    const float inter = __fmul_rn(__fsub_rn(ib1, ib0), __fsub_rn(ib3, ib2));
+    float denom = __fsub_rn(__fadd_rn(la, ra), inter);
+    if (q.retina) denom = __fadd_rn(denom, 0.000001f);
+    const float t = __fmaf_rn(-q.thr, denom, inter);
+    if (q.fast_ok && denom > 0.0f && fabsf(t) > __fmul_rn(1e-5f, denom)) return t > 0.0f;
+    return __fdiv_rn(inter, denom) > q.thr;
 }
 
 // ---- candidate accessors --------------------------------------------------------------------
@@ -165,6 +162,12 @@ __device__ __forceinline__ void pick_bucket(const int* hist, bool descending, in
     *bucket_out = d;
 }
 
+// IoU work units of a segment of m rows: row li (0-based inside the segment) needs ceil(li/8) of them
+__device__ __forceinline__ int seg_units(int m) {
+    const int G = (m + 6) >> 3;
+    return G * (m - 1) - 4 * G * (G - 1);
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // carve-up (S = row capacity, power of two >= pre_topk)
@@ -183,8 +186,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_long + S / 2);   // S   slow path: stash position riding along
     unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_pos + S);         // S   keep flags
     unsigned short* s_unit = reinterpret_cast<unsigned short*>(s_keep + S);      // S*12 IoU work units (row << 4 | group of 8)
-    int* s_tpre = reinterpret_cast<int*>(s_unit + S * (kShortSeg / 8));          // tiles_per_image + 1 (fused path)
-    float4* s_kbox = u_box;  // kept boxes of a long segment: aliases the stash (dead once the rows are permuted)
+    float* s_area = reinterpret_cast<float*>(s_unit + S * (kShortSeg / 8));      // S   box areas (greedy mode)
+    int* s_tpre = reinterpret_cast<int*>(s_area + S);                            // tiles_per_image + 1 (fused path)
+    unsigned short* s_krow = reinterpret_cast<unsigned short*>(u_box);  // kept rows of a long segment (the stash is dead after D)
     unsigned* s_mask = reinterpret_cast<unsigned*>(u_conf);  // 3 words per row: suppressor bitmaps (aliases u_conf/u_cls/u_id)
     int* s_rowseg = reinterpret_cast<int*>(k64);             // per row: segment start << 16 | length (aliases the sort keys)
     // slow path only: 128-bit keys live in the (not yet filled) sorted-row area
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     // (class, conf) -- detected below, then the generic 128-bit sort decides by (box[0], id).
     bool generic = s_bad != 0;
     // fastest path (the detector case: many classes, a few dozen rows each): counting sort by class, then every row
-    // ranks itself inside its class bucket by counting smaller keys -- no compare-exchange network, 5 barriers.
+    // ranks itself inside its class bucket by counting smaller keys -- no compare-exchange network.
     // Falls through to the bitonic paths when a class id is >= kClassBins or a bucket holds more than kMaxBucket rows.
     bool bucketed = false;
     if (!generic) {
@@ -362,20 +366,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         s_chist[tid] = 0;
         __syncthreads();
         bool big = false;
-        for (int i = tid; i < M; i += kNmsThreads) {
-            const int c = u_cls[i];
-            if (c < kClassBins)
-                s_pos[i] = (unsigned short)atomicAdd(&s_chist[c], 1);  // arrival order inside the bucket (any order works)
-            else
-                big = true;
+        for (int base = 0; base < M; base += kNmsThreads) {
+            // rows arrive in tile order, so neighbouring lanes often share a class: one atomic per (warp, class)
+            const int i = base + tid;
+            const int c = i < M ? u_cls[i] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            const int leader = __ffs(peers) - 1;
+            int first = 0;
+            if (c >= kClassBins) big = true;
+            if (lane == leader && c >= 0 && c < kClassBins) first = atomicAdd(&s_chist[c], __popc(peers));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            if (i < M) s_pos[i] = (unsigned short)(first + __popc(peers & ((1u << lane) - 1u)));  // slot inside the bucket (any order works)
         }
-        const int any_big = __syncthreads_or(big ? 1 : 0);
+        __syncthreads();
         const int h = s_chist[tid];
-        if (!any_big && !__syncthreads_or(h > kMaxBucket ? 1 : 0)) {
-            int tot;
-            const int ex = warp_excl_scan(h, lane, &tot);
-            if (lane == 0) s_wsum[warp] = tot;
-            __syncthreads();
+        int tot;
+        const int ex = warp_excl_scan(h, lane, &tot);
+        if (lane == 0) s_wsum[warp] = tot;
+        if (!__syncthreads_or(big || h > kMaxBucket ? 1 : 0)) {
             if (warp == 0) {
                 int w = s_wsum[lane], wt;
                 const int wex = warp_excl_scan(w, lane, &wt);
@@ -391,19 +399,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             }
             __syncthreads();
             // thread p owns bucket slot p: neighbouring lanes share a bucket, so the key reads below are broadcasts
-            bool tie = false;
             for (int p = tid; p < M; p += kNmsThreads) {
                 const unsigned long long mk = kb[p];
                 const int c = (int)(mk >> 48);
                 const int s0 = s_cstart[c], m = s_chist[c];
                 int rank = 0;
-                for (int k = 0; k < m; ++k) {
-                    const unsigned long long ok = kb[s0 + k];
-                    rank += ok < mk ? 1 : 0;
-                    tie |= (ok >> 16) == (mk >> 16) && ok != mk;  // same (class, conf): the generic sort decides
-                }
+#pragma unroll 4
+                for (int k = 0; k < m; ++k) rank += kb[s0 + k] < mk ? 1 : 0;  // keys are distinct (stash position in the low bits)
                 k64[s0 + rank] = mk;
             }
+            __syncthreads();
+            bool tie = false;  // same (class, conf) twice: the generic sort decides by (box[0], id)
+            for (int i = tid; i < M; i += kNmsThreads)
+                if (i > 0 && (k64[i] >> 16) == (k64[i - 1] >> 16)) tie = true;
             generic = __syncthreads_or(tie ? 1 : 0) != 0;
             bucketed = !generic;
         }
@@ -497,9 +505,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 
     TRTX_STAMP(2);
     // ---------------- D: permute the stash into sorted order ----------------
+    const bool greedy = a.mode == TRTX_NMS_GREEDY;
+    IouTest iq;
+    iq.thr = a.nms_thresh;
+    iq.retina = a.box_format == TRTX_BOX_RETINA;
+    iq.zero_hit = 0.0f > a.nms_thresh;
+    iq.fast_ok = fabsf(a.nms_thresh) <= 4.0f;
     for (int i = tid; i < M; i += kNmsThreads) {
         const int pos = (int)(k64[i] & 0xffffull);
-        s_box[i] = u_box[pos];
+        const float4 bx = u_box[pos];
+        if (greedy) {  // the host IoUs work on corners and areas: form both once per row instead of once per pair
+            s_box[i] = to_corners(a.box_format, bx);
+            s_area[i] = box_area(a.box_format, bx);
+        } else {
+            s_box[i] = bx;
+        }
         s_conf[i] = u_conf[pos];
         s_cls[i] = u_cls[pos];
         s_id[i] = u_id[pos];
@@ -521,7 +541,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     float* o = a.out + (size_t)b * (1 + (size_t)a.max_det * R);
     int32_t* oidx = a.keep_index ? a.keep_index + (size_t)b * a.max_det : nullptr;
 
-    if (a.mode == TRTX_NMS_GREEDY) {
+    if (greedy) {
         // ---------------- E: class segments ----------------
         if (bucketed) {
             // the class histogram already is the segment table
@@ -536,6 +556,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 s_seg[S - 1 - atomicAdd(&s_nmed, 1)] = (p0 << 16) | m;
             else if (m > 0)
                 s_seg[atomicAdd(&s_nshort, 1)] = (p0 << 16) | m;
+            if (m > 1 && m <= kShortSeg) s_pos[p0] = (unsigned short)atomicAdd(&s_nunit, seg_units(m));
         } else
         for (int i = tid; i < M; i += kNmsThreads) {
             if (i == 0 || s_cls[i] != s_cls[i - 1]) {
@@ -550,6 +571,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                     s_seg[S - 1 - atomicAdd(&s_nmed, 1)] = (i << 16) | m;  // medium segments: taken first (longest-first scheduling)
                 else
                     s_seg[atomicAdd(&s_nshort, 1)] = (i << 16) | m;
+                if (m > 1 && m <= kShortSeg) s_pos[i] = (unsigned short)atomicAdd(&s_nunit, seg_units(m));
             }
         }
         __syncthreads();
@@ -564,14 +586,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 const int P = 32 * n_kept;
                 for (int p = tid; p < P; p += kNmsThreads) {
                     const int i = p & 31, k = p >> 5;
-                    if (i < nchunk && iou_any(a.box_format, s_kbox[p0 + k], s_box[p0 + c0 + i]) > a.nms_thresh)
+                    const int kr = s_krow[k];
+                    if (i < nchunk && overlaps(iq, s_box[kr], s_area[kr], s_box[p0 + c0 + i], s_area[p0 + c0 + i]))
                         atomicOr(&s_rem, 1u << i);
                 }
                 {
                     const int i = warp, jx = lane;
                     bool hit = false;
                     if (i < nchunk && jx < i)
-                        hit = iou_any(a.box_format, s_box[p0 + c0 + jx], s_box[p0 + c0 + i]) > a.nms_thresh;
+                        hit = overlaps(iq, s_box[p0 + c0 + jx], s_area[p0 + c0 + jx], s_box[p0 + c0 + i], s_area[p0 + c0 + i]);
                     const unsigned mm = __ballot_sync(0xffffffffu, hit);
                     if (lane == 0) s_sup[i] = mm;
                 }
@@ -587,7 +610,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                     }
                     if ((alive >> lane) & 1u) {
                         const int pos = n_kept + __popc(alive & ((1u << lane) - 1u));
-                        s_kbox[p0 + pos] = s_box[p0 + c0 + lane];
+                        s_krow[pos] = (unsigned short)(p0 + c0 + lane);
                         s_keep[p0 + c0 + lane] = 1;
                     }
                     if (lane == 0) {
@@ -602,25 +625,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         TRTX_STAMP(4);
         // ---- short / medium segments (<= kShortSeg rows) ----
         // (1) IoU of every row against the earlier rows of its segment -> suppressor bitmap per row (bit j = row start+j
-        //     overlaps it).  Work unit = (row, 8 earlier rows) = one byte of the bitmap; the units of all segments go
-        //     into one list so the 1024 threads share them evenly whatever the segment lengths are.
-        for (int base = 0; base < M; base += kNmsThreads) {
-            const int i = base + tid;
-            int cnt = 0;
-            if (i < M) {
-                const int rs = s_rowseg[i];
-                if (rs != 0) {
-                    cnt = (i - (rs >> 16) + 7) >> 3;
+        //     overlaps it).  Work unit = (row, group g of 8 earlier rows) = one byte of the bitmap.  The units of all
+        //     segments go into one list so the 1024 threads share them evenly whatever the segment lengths are; inside
+        //     a segment they are ordered group-major, so neighbouring lanes hold neighbouring rows and test them
+        //     against the SAME 8 earlier rows (shared-memory broadcasts instead of 128-byte-stride bank conflicts).
+        for (int i = tid; i < M; i += kNmsThreads) {
+            const int rs = s_rowseg[i];
+            if (rs == 0) continue;
+            const int p0 = rs >> 16, m = rs & 0xffff, li = i - p0;
 #pragma unroll
-                    for (int w = 0; w < kShortSeg / 32; ++w) s_mask[i * (kShortSeg / 32) + w] = 0u;
-                }
-            }
-            int tot;
-            const int ex = warp_excl_scan(cnt, lane, &tot);
-            int wbase = 0;
-            if (lane == 0 && tot > 0) wbase = atomicAdd(&s_nunit, tot);
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            for (int g = 0; g < cnt; ++g) s_unit[wbase + ex + g] = (unsigned short)((i << 4) | g);
+            for (int w = 0; w < kShortSeg / 32; ++w) s_mask[i * (kShortSeg / 32) + w] = 0u;
+            const int ub = s_pos[p0] + li - 1;
+            for (int g = 0; g * 8 < li; ++g)  // group g holds rows 8g+1 .. m-1 of the segment, after groups 0..g-1
+                s_unit[ub + g * (m - 1) - 4 * g * (g - 1) - 8 * g] = (unsigned short)((i << 4) | g);
         }
         __syncthreads();
         TRTX_STAMP(9);
@@ -631,11 +648,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
                 const int e = s_unit[u], i = e >> 4, g = e & 15;
                 const int p0 = s_rowseg[i] >> 16, li = i - p0;
                 const float4 bi = s_box[i];
+                const float ai = s_area[i];
                 unsigned bits = 0u;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int jx = g * 8 + k;
-                    if (jx < li && iou_any(a.box_format, s_box[p0 + jx], bi) > a.nms_thresh) bits |= 1u << k;
+                    if (jx < li && overlaps(iq, s_box[p0 + jx], s_area[p0 + jx], bi, ai)) bits |= 1u << k;
                 }
                 mask_bytes[i * (kShortSeg / 8) + g] = (unsigned char)bits;  // little-endian: byte g of the row's 3 words
             }
@@ -715,7 +733,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         __syncthreads();
         const int k = carry + s_wsum[warp] + __popc(bal & ((1u << lane) - 1u));
         if (emit && k < a.max_det) {
-            const float4 bx = s_box[i];
+            // greedy + cx,cy,w,h rows were turned into corners for the IoU tests: emit the row as it came in
+            const float4 bx = greedy && a.box_format == TRTX_BOX_CXCYWH ? fetch_row(a, b, s_id[i]).box : s_box[i];
             float* row = o + 1 + (size_t)k * R;
             row[0] = bx.x;
             row[1] = bx.y;
@@ -746,7 +765,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
     const size_t S = pre_topk <= 1024 ? 1024 : kMaxSort;
-    return S * (16 + 16 + 8 + 6 * 4 + 4 + 2 + 2 + 1 + 2 * (kShortSeg / 8)) + 64 + sizeof(int) * (size_t)(tiles + 1);
+    return S * (16 + 16 + 8 + 6 * 4 + 4 + 2 + 2 + 1 + 2 * (kShortSeg / 8) + 4) + 64 + sizeof(int) * (size_t)(tiles + 1);
 }
 
 static int nms_validate(const trtx_nms_params* q) {
