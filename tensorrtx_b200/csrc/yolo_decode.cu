@@ -20,23 +20,20 @@ namespace trtx {
 thread_local int g_last_cuda_error = 0;
 
 // tuning knobs (set through trtx_tune_set; defaults chosen from the B200 sweep in profiles/)
-static int g_slices = 4;
-static int g_unroll = 10;
-static int g_use_pipe = 1;
-static int g_prefetch_box = 1;
-__constant__ int g_prefetch_box_rows_dev_dummy;  // (unused; the flag travels as a kernel argument)  // TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
+static int g_slices = 2;
+static int g_unroll = 5;
+static int g_use_pipe = 0;      // 1: TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
+static int g_prefetch_box = 1;  // L2-prefetch the 4 box rows while the class rows stream
 void yolo_pipe_set_consumers(int n);
 void yolo_pipe_set_debug(int v);
 
 // --------------------------------------------------------------------------------------------
-// scan_classes: running (max sigmoid, first argmax) over `nrows` channel rows for VEC adjacent
-// anchors, bit-identical to the reference loop
+// scan_classes: running (max logit, first argmax, max before it) over `nrows` channel rows for VEC
+// adjacent anchors (Best / finish_best in yolo_layout.cuh turn that into the reference's result
 //     for i: p = Logist(x_i); if (p > max) { max = p; cls = i; }          (yololayer.cu:195-201)
-// for every anchor whose final max is >= gate.  Proof sketch: sigmoid is
-// monotone non-decreasing in fp32, so the first class attaining the maximum probability has a
-// logit strictly greater than every earlier logit and (if the max passes the gate) than x_lo;
-// hence it is always taken by the `x > bx` test and wins the strict `p > bp` comparison.
-// Background logits never reach the slow path, so the hot loop is 1 compare per element.
+// bit for bit).  Hot loop: one fmaxf per element, one compare per group of U rows; a group is replayed
+// -- branch-free, 4 instructions per element, no sigmoid -- only when it raises some anchor's running
+// maximum above the gate logit, i.e. around real candidates.
 // --------------------------------------------------------------------------------------------
 template <typename T, int VEC, int U>
 __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t g, int nrows, int cls0, Best<VEC>& s) {
@@ -64,22 +61,24 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
             if ((m.x > s.bx[0]) | (m.y > s.bx[1]) | (m.z > s.bx[2]) | (m.w > s.bx[3])) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const bool any = (v[u].x > s.bx[0]) | (v[u].y > s.bx[1]) | (v[u].z > s.bx[2]) | (v[u].w > s.bx[3]);
-                    if (any) {
-                        const int c = cls0 + r + u;
-                        update_one<VEC>(s, 0, v[u].x, c);
-                        update_one<VEC>(s, 1, v[u].y, c);
-                        update_one<VEC>(s, 2, v[u].z, c);
-                        update_one<VEC>(s, 3, v[u].w, c);
-                    }
+                    const int c = cls0 + r + u;
+                    update_one<VEC>(s, 0, v[u].x, c);
+                    update_one<VEC>(s, 1, v[u].y, c);
+                    update_one<VEC>(s, 2, v[u].z, c);
+                    update_one<VEC>(s, 3, v[u].w, c);
                 }
             }
         } else {
             float v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) v[u] = (r + u < nrows) ? Elem<T>::ld1(p + (size_t)u * g) : -INFINITY;
+            float m = v[0];
 #pragma unroll
-            for (int u = 0; u < U; ++u) update_one<VEC>(s, 0, v[u], cls0 + r + u);
+            for (int u = 1; u < U; ++u) m = fmaxf(m, v[u]);
+            if (m > s.bx[0]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) update_one<VEC>(s, 0, v[u], cls0 + r + u);
+            }
         }
         p += (size_t)U * g;
     }
@@ -91,8 +90,9 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
 template <typename T, int VEC, int SLICES, int U>
 __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_constant__ YoloArgs a) {
     constexpr int TILE = 32 * VEC;
-    __shared__ float s_p[SLICES > 1 ? SLICES - 1 : 1][TILE];
-    __shared__ int s_c[SLICES > 1 ? SLICES - 1 : 1][TILE];
+    __shared__ float s_m[SLICES > 1 ? SLICES - 1 : 1][TILE];   // per class slice: max logit,
+    __shared__ float s_m2[SLICES > 1 ? SLICES - 1 : 1][TILE];  // max logit before its class,
+    __shared__ int s_c[SLICES > 1 ? SLICES - 1 : 1][TILE];     // its class
 
     const int b = blockIdx.x / a.tiles_per_image;
     const int t = blockIdx.x - b * a.tiles_per_image;
@@ -111,61 +111,21 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         s.bx[j] = a.x_lo;
-        s.bp[j] = 0.0f;
+        s.b2[j] = a.x_lo;
         s.bc[j] = 0;
     }
     const int per = (a.nc + SLICES - 1) / SLICES;
     const int c0 = warp * per;
     const int c1 = min(a.nc, c0 + per);
-    if (a.prefetch_box && warp == 0 && active) {
-        // pull the 4 box rows of this tile towards L2 while the class rows stream: the epilogue's dependent
-        // loads then hit L2 instead of paying a second HBM round trip on every tile that has candidates
+    // box rows of this tile.  prefetch_box = 2: warp 0 loads them into registers up front, so the epilogue of a tile
+    // with candidates has no dependent memory round trip left (the kernel's tail is such an epilogue);
+    // 1: only pull them towards L2; 0: load on demand.
+    float d[4][VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * g + a0));
-    }
-    if (active && c1 > c0) scan_classes<T, VEC, U>(base + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
-
-    if constexpr (SLICES > 1) {
-        bool mine = false;
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) mine |= !(s.bp[j] < a.gate);
-        if (warp > 0) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                s_p[warp - 1][lane * VEC + j] = s.bp[j];
-                s_c[warp - 1][lane * VEC + j] = s.bc[j];
-            }
-        }
-        int any = __syncthreads_or(mine ? 1 : 0);
-        if (!any) {
-            if (threadIdx.x == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = 0;
-            return;
-        }
-        if (warp > 0) return;
-        // combine in ascending class-slice order: strict > keeps the FIRST class with the max prob
-#pragma unroll
-        for (int w = 1; w < SLICES; ++w) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                float p2 = s_p[w - 1][lane * VEC + j];
-                if (p2 > s.bp[j]) {
-                    s.bp[j] = p2;
-                    s.bc[j] = s_c[w - 1][lane * VEC + j];
-                }
-            }
-        }
-    }
-
-    // gate (yololayer.cu:203: `if (max_cls_prob < 0.1) return;`) + warp-scan compaction
-    unsigned flags = 0;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j)
-        if (active && (a0 + j < L.g) && !(s.bp[j] < a.gate)) flags |= 1u << j;
-    int total;
-    int off = warp_excl_scan(__popc(flags), lane, &total);
-    if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
-    if (flags) {
-        float d[4][VEC];
+        for (int j = 0; j < VEC; ++j) d[k][j] = 0.0f;
+    auto load_box = [&]() {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if constexpr (VEC == 4) {
@@ -178,6 +138,64 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
                 d[k][0] = Elem<T>::ld1(base + (size_t)k * g + a0);
             }
         }
+    };
+    if (warp == 0 && active) {
+        if (a.prefetch_box == 2) {
+            load_box();
+        } else if (a.prefetch_box == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * g + a0));
+        }
+    }
+    if (active && c1 > c0) scan_classes<T, VEC, U>(base + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
+
+    if constexpr (SLICES > 1) {
+        bool mine = false;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) mine |= s.bx[j] > a.x_lo || !(0.0f < a.gate);  // may pass the gate
+        if (warp > 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                s_m[warp - 1][lane * VEC + j] = s.bx[j];
+                s_m2[warp - 1][lane * VEC + j] = s.b2[j];
+                s_c[warp - 1][lane * VEC + j] = s.bc[j];
+            }
+        }
+        int any = __syncthreads_or(mine ? 1 : 0);
+        if (!any) {
+            if (threadIdx.x == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = 0;
+            return;
+        }
+        if (warp > 0) return;
+        // combine in ascending class-slice order: strict > keeps the FIRST class with the maximum
+#pragma unroll
+        for (int w = 1; w < SLICES; ++w) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                merge_one<VEC>(s, j, s_m[w - 1][lane * VEC + j], s_m2[w - 1][lane * VEC + j], s_c[w - 1][lane * VEC + j]);
+        }
+    }
+
+    // the one sigmoid per anchor that can pass, gate (yololayer.cu:203: `if (max_cls_prob < 0.1) return;`),
+    // warp-scan compaction
+    float bp[VEC];
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        bp[j] = 0.0f;  // the reference's initial max: every logit was -inf / NaN, or below the gate logit
+        if (active && (a0 + j < L.g)) {
+            if (s.bx[j] > a.x_lo) {
+                const T* cls_row0 = base + (size_t)4 * g + a0 + j;
+                bp[j] = finish_best(s.bx[j], s.b2[j], s.bc[j], a.gate, [&](int i) { return Elem<T>::ld1(cls_row0 + (size_t)i * g); });
+            }
+            if (!(bp[j] < a.gate)) flags |= 1u << j;
+        }
+    }
+    int total;
+    int off = warp_excl_scan(__popc(flags), lane, &total);
+    if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
+    if (flags) {
+        if (a.prefetch_box != 2) load_box();
         const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE;
         const float fs = (float)L.stride;
 #pragma unroll
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
                 float y1 = ((float)row + 0.5f - d[1][j]) * fs;
                 float x2 = ((float)col + 0.5f + d[2][j]) * fs;
                 float y2 = ((float)row + 0.5f + d[3][j]) * fs;
-                store_record(a.cand, slot0 + off, x1, y1, x2, y2, s.bp[j], s.bc[j], L.slot_begin + e);
+                store_record(a.cand, slot0 + off, x1, y1, x2, y2, bp[j], s.bc[j], L.slot_begin + e);
                 ++off;
             }
         }
@@ -208,7 +226,8 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
     constexpr int TILE = 32 * VEC;
     constexpr int SLICES = 4;
     __shared__ float s_obj[3][TILE];            // objectness prob (0 if not passing)
-    __shared__ float s_p[SLICES - 1][TILE];     // partial class max of slices 1..3
+    __shared__ float s_m[SLICES - 1][TILE];     // class slices 1..3: max logit, max logit before its class, its class
+    __shared__ float s_m2[SLICES - 1][TILE];
     __shared__ int s_c[SLICES - 1][TILE];
     __shared__ float s_fp[3][TILE];             // final class prob per (k, cell)
     __shared__ int s_fc[3][TILE];
@@ -278,9 +297,9 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
         Best<VEC> s;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            // non-passing anchors never take the slow path; passing ones see every running max
+            // anchors that failed the objectness gate never update; passing ones see every running max
             s.bx[j] = (s_obj[k][lane * VEC + j] >= 0.0f) ? -INFINITY : INFINITY;
-            s.bp[j] = 0.0f;
+            s.b2[j] = s.bx[j];
             s.bc[j] = 0;
         }
         if (active && c1 > c0)
@@ -288,7 +307,8 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
         if (warp > 0) {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                s_p[warp - 1][lane * VEC + j] = s.bp[j];
+                s_m[warp - 1][lane * VEC + j] = s.bx[j];
+                s_m2[warp - 1][lane * VEC + j] = s.b2[j];
                 s_c[warp - 1][lane * VEC + j] = s.bc[j];
             }
         }
@@ -297,17 +317,18 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
 #pragma unroll
             for (int w = 1; w < SLICES; ++w) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    float p2 = s_p[w - 1][lane * VEC + j];
-                    if (p2 > s.bp[j]) {
-                        s.bp[j] = p2;
-                        s.bc[j] = s_c[w - 1][lane * VEC + j];
-                    }
-                }
+                for (int j = 0; j < VEC; ++j)
+                    merge_one<VEC>(s, j, s_m[w - 1][lane * VEC + j], s_m2[w - 1][lane * VEC + j], s_c[w - 1][lane * VEC + j]);
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                s_fp[k][lane * VEC + j] = s.bp[j];
+                // one sigmoid per passing anchor; the v5 class probability has no gate of its own (yololayer.cu:178-186)
+                float P = 0.0f;
+                if (s_obj[k][lane * VEC + j] >= 0.0f && s.bx[j] > -INFINITY) {
+                    const T* cls_row0 = base + ((size_t)k * ilen + 5) * g + a0 + j;
+                    P = finish_best(s.bx[j], s.b2[j], s.bc[j], 0.0f, [&](int i) { return Elem<T>::ld1(cls_row0 + (size_t)i * g); });
+                }
+                s_fp[k][lane * VEC + j] = P;
                 s_fc[k][lane * VEC + j] = s.bc[j];
             }
         }

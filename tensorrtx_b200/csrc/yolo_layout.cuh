@@ -88,23 +88,62 @@ inline YoloLayout yolo_layout(const trtx_yolo_params* p, int batch, int vec) {
 }
 
 // ---- device helpers shared by the scan kernels ----
+// Running state of the reference's class loop
+//     max = 0; cls = 0; for i: p = Logist(x_i); if (p > max) { max = p; cls = i; }        (yololayer.cu:195-201)
+// kept in the LOGIT domain: bx = largest logit so far, bc = the first class holding it, b2 = largest logit seen
+// BEFORE class bc.  Logist is evaluated once per surviving anchor afterwards (finish_best) instead of once per
+// running maximum; DESIGN.md section 4.1 has the equivalence argument.
 template <int VEC>
 struct Best {
     float bx[VEC];
-    float bp[VEC];
+    float b2[VEC];
     int bc[VEC];
 };
 
+// branch-free; `x > bx` is false for NaN, like the reference's `p > max` on a NaN probability
 template <int VEC>
 __device__ __forceinline__ void update_one(Best<VEC>& s, int j, float x, int cls) {
-    if (x > s.bx[j]) {
-        s.bx[j] = x;
-        float p = logist(x);
-        if (p > s.bp[j]) {
-            s.bp[j] = p;
-            s.bc[j] = cls;
+    const bool up = x > s.bx[j];
+    s.b2[j] = up ? s.bx[j] : s.b2[j];
+    s.bc[j] = up ? cls : s.bc[j];
+    s.bx[j] = up ? x : s.bx[j];
+}
+
+// fold the state of a later class slice (m, m2, c) into s: strict `>` keeps the first class holding the maximum,
+// and everything the earlier slices saw lies before class c
+template <int VEC>
+__device__ __forceinline__ void merge_one(Best<VEC>& s, int j, float m, float m2, int c) {
+    if (m > s.bx[j]) {
+        s.b2[j] = fmaxf(s.bx[j], m2);
+        s.bx[j] = m;
+        s.bc[j] = c;
+    }
+}
+
+// (max prob, class) of the reference loop from the logit-domain state.  Logist is monotone non-decreasing in fp32,
+// so max prob = Logist(bx).  The reference's class is the FIRST one whose probability equals that maximum:
+//   * P == 0: no probability ever beat the initial max = 0 -> class 0;
+//   * otherwise class bc, unless an EARLIER class has a smaller logit with the same rounded probability (two logits
+//     a few ulps apart, or both saturated at 1.0f).  The largest earlier logit is b2, so Logist(b2) != P rules that
+//     out; when it does collide the class rows before bc are re-read (`ld(i)`) and the reference loop is replayed.
+// Anchors below the gate return early (the caller drops them, yololayer.cu:203).
+template <typename LoadRow>
+__device__ __forceinline__ float finish_best(float bx, float b2, int& cls, float gate, LoadRow ld) {
+    const float P = logist(bx), P2 = logist(b2);  // independent: the two evaluations overlap
+    if (P < gate) return P;
+    if (P == 0.0f) {
+        cls = 0;
+        return P;
+    }
+    if (P2 == P) {
+        for (int i = 0; i < cls; ++i) {
+            if (logist(ld(i)) == P) {
+                cls = i;
+                break;
+            }
         }
     }
+    return P;
 }
 
 __device__ __forceinline__ void store_record(float4* cand, size_t slot, float b0, float b1, float b2, float b3,

@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(1024, 1)
 
         mbar_wait(&full_bar[s], ph);
         Best<1> st;
-        st.bx[0] = active ? a.x_lo : INFINITY;  // TMA zero-fills columns past the level: never let them reach the sigmoid path
-        st.bp[0] = 0.0f;
+        st.bx[0] = active ? a.x_lo : INFINITY;  // TMA zero-fills columns past the level: those lanes never update
+        st.b2[0] = st.bx[0];
         st.bc[0] = 0;
         if (dbg == 1) {  // profiling aid: copy engine only
             if (lane == 0 && cell0 < L.g) a.tile_count[(size_t)b * a.tiles_per_image + L.tile_begin + (cell0 >> 5)] = 0;
@@ -180,7 +180,11 @@ __global__ void __launch_bounds__(1024, 1)
                 }
             }
             for (; c < a.nc; ++c, p += kTileAnchors) update_one<1>(st, 0, lds1<T>(p), c);
-            const bool keep = active && !(st.bp[0] < a.gate);  // yololayer.cu:203
+            float bp = 0.0f;  // the reference's initial max
+            if (active && st.bx[0] > a.x_lo)
+                bp = finish_best(st.bx[0], st.b2[0], st.bc[0], a.gate,
+                                 [&](int i) { return lds1<T>(tile + (size_t)(4 + i) * kTileAnchors); });
+            const bool keep = active && !(bp < a.gate);  // yololayer.cu:203
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + L.tile_begin + (cell0 >> 5)] = __popc(bal);
             if (keep) {
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(1024, 1)
                 const float x2 = ((float)col + 0.5f + d2) * fs;
                 const float y2 = ((float)row + 0.5f + d3) * fs;
                 const size_t slot = (size_t)b * a.slots_per_image + L.slot_begin + cell0 + __popc(bal & ((1u << lane) - 1u));
-                store_record(a.cand, slot, x1, y1, x2, y2, st.bp[0], st.bc[0], L.slot_begin + e);
+                store_record(a.cand, slot, x1, y1, x2, y2, bp, st.bc[0], L.slot_begin + e);
             }
         }
         __syncwarp();

@@ -65,6 +65,52 @@ def test_yolov8_plugin_vs_reference_kernel(dev, seed, B):
         assert np.array_equal(r, g)  # same CUDA expf, same operation order: bit-exact
 
 
+def test_yolov8_near_ulp_sigmoid_collisions_vs_reference_kernel(dev):
+    """Logits a few ulps apart: whether two of them round to the same probability (-> the EARLIER class wins the
+    reference's strict `p > max`) depends on expf itself, so this is checked against the reference kernel (same CUDA
+    expf), for every scan variant (class slices merge their running state; the TMA pipeline replays from smem)."""
+    lib = _load("libref_yolov8.so")
+    ours = L.load()
+    heads = synth.yolov8_heads(1, seed=430, n_obj=0)
+    h = heads[0]
+    n = 0
+    for x0 in (0.3, 1.5, 2.75, 5.0, 9.0, 14.0):
+        x = np.float32(x0)
+        for k in range(1, 25):
+            y = x
+            for _ in range(k):
+                y = np.nextafter(y, np.float32(0))
+            cell = 40 * n + k
+            h[0, 4 + 60 - k, cell] = y      # earlier class, k ulps below the maximum
+            h[0, 4 + 60, cell] = x
+            h[0, 4 + 70, cell] = y          # later class: never wins
+        n += 1
+    hd = [torch.from_numpy(a).to(dev) for a in heads]
+    ref = torch.zeros((1, 1 + 1000 * 90), dtype=torch.float32, device=dev)
+    strides = (C.c_int * 3)(8, 16, 32)
+    assert lib.ref_v8_plugin_enqueue(80, 17, C.c_float(0.0), 640, 640, 1000, 0, 0, 0, strides, 3, 1, _ptrs(hd),
+                                     C.c_void_p(ref.data_ptr()), None) == 0
+    ref = ref.cpu().numpy()
+    nref = int(ref[0, 0])
+    r = _canon(ref[0, 1:1 + nref * 90].reshape(nref, 90)[:, :6])
+    assert nref >= 6 * 24
+    assert (r[:, 5] == 60).any() and (r[:, 5] != 60).any()     # both outcomes occur
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
+    try:
+        for pipe, slices, unroll in ((1, 2, 5), (0, 2, 5), (0, 4, 10), (0, 1, 8), (0, 8, 5)):
+            ours.trtx_tune_set(2, pipe)
+            ours.trtx_tune_set(0, slices)
+            ours.trtx_tune_set(1, unroll)
+            got = _ours_decode(plug, hd, 1, dev)
+            assert got[0, 0] == nref
+            g = _canon(got[0, 1:1 + nref * 90].reshape(nref, 90)[:, :6])
+            assert np.array_equal(r, g), (pipe, slices, unroll)
+    finally:
+        ours.trtx_tune_set(2, 0)
+        ours.trtx_tune_set(0, 2)
+        ours.trtx_tune_set(1, 5)
+
+
 @pytest.mark.parametrize("mode", ["seg", "pose", "obb"])
 def test_yolov8_plugin_extras_vs_reference_kernel(dev, mode):
     lib = _load("libref_yolov8.so")

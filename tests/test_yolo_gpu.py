@@ -171,11 +171,21 @@ def test_first_argmax_on_sigmoid_collisions(oracle, dev):
     h[0, 4 + 20, 200] = 6.0000  # exact tie -> first class wins
     ref, _ = oracle.yolov8_decode(heads)
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
-    got = _decode_gpu(plug, _to_dev(heads, dev), 1, dev)
-    assert got[0, 0] == ref[0, 0] == 2
-    g = got[0, 1:181].reshape(2, 90)
-    assert g[0, 5] == 3 and g[1, 5] == 20
-    _check_rows(got, ref, 1, 90, 6, 1000)
+    lib = L.load()
+    try:
+        for pipe, slices, unroll in ((1, 2, 5), (0, 2, 5), (0, 4, 10), (0, 1, 8)):
+            lib.trtx_tune_set(2, pipe)
+            lib.trtx_tune_set(0, slices)
+            lib.trtx_tune_set(1, unroll)
+            got = _decode_gpu(plug, _to_dev(heads, dev), 1, dev)
+            assert got[0, 0] == ref[0, 0] == 2
+            g = got[0, 1:181].reshape(2, 90)
+            assert g[0, 5] == 3 and g[1, 5] == 20
+            _check_rows(got, ref, 1, 90, 6, 1000)
+    finally:
+        lib.trtx_tune_set(2, 0)
+        lib.trtx_tune_set(0, 2)
+        lib.trtx_tune_set(1, 5)
 
 
 # ------------------------------------------------------------------ NMS ------------------------

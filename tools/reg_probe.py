@@ -21,9 +21,9 @@ for name, nobj in (("dense", 64), ("typical(8 obj)", 8), ("background", 0)):
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
     lib.trtx_tune_set(2, 0)
-    for pf in (0, 1):
+    for pf in (1, 2):
         lib.trtx_tune_set(5, pf)
-        for sl, u in ((4, 5), (4, 4), (2, 4), (2, 5), (2, 8), (2, 10)):
+        for sl, u in ((4, 5), (2, 4), (2, 5), (2, 8), (1, 8), (1, 16)):
             lib.trtx_tune_set(0, sl); lib.trtx_tune_set(1, u)
             print(json.dumps({"data": name, "prefetch": pf, "slices": sl, "unroll": u, "us": round(timeit(fused, sets), 2)}), flush=True)
     lib.trtx_tune_set(2, 1); lib.trtx_tune_set(3, 15)

@@ -22,7 +22,7 @@ res = []
 for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32), in_dtype=dt)
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-    for slices, unroll in [(-1, 15), (2, 5), (4, 5), (2, 8)]:
+    for slices, unroll in [(-1, 15), (1, 8), (1, 16), (2, 5), (2, 10), (2, 20), (4, 5), (4, 10), (4, 20), (8, 5)]:
         if slices < 0:   # TMA pipeline kernel, `unroll` = cap on stages (= consumer warps)
             lib.trtx_tune_set(2, 1)
             lib.trtx_tune_set(3, unroll)
