@@ -3,9 +3,9 @@
 // (identical bodies in yolov5/7/9/10/11/12/13/26), which launch once per image and synchronise the
 // stream after every image (:119-127).  Here: ONE launch for the whole batch, per-image descriptors
 // and affine matrices in the kernel parameter block (no H2D copy of metadata); a warp covers 32
-// adjacent destination columns and every thread produces 4 rows of its column.  Measured and rejected
-// (profiles/r01j_sweep.log): 4 adjacent pixels per lane (L1 sector-bound), staging the source band in
-// shared memory (2x slower).
+// adjacent destination columns and every thread produces a strip of rows of its column.  Measured and
+// rejected (profiles/): 4 adjacent pixels per lane (L1 sector-bound), staging the source band in shared
+// memory (2x slower).
 //
 // Roofline: HBM-bound; algorithmic bytes per image = src_w*src_h*3 (u8 read once) +
 // 3*dst_w*dst_h*sizeof(out) (6 144 000 B for 640x640 -> 640x640 fp32).
@@ -13,6 +13,8 @@
 // Arithmetic follows the reference kernel statement by statement (including its `+0.5f` source
 // offset without a matching `-0.5f`, preprocess.cu:22-23) and, like the reference's own nvcc build,
 // leaves the bilinear sums to the default FMA contraction (<= 1 ulp from the uncontracted oracle).
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace trtx {
@@ -38,65 +40,110 @@ __device__ __forceinline__ float div255(float x) {
     return __fmaf_rn(__fmaf_rn(-255.0f, q0, x), r, q0);
 }
 
-// int -> float without the XU (conversion) pipe: for 0 <= i < 2^23, (2^23 + i) is exactly representable with the
-// integer sitting in the mantissa, so OR-ing i into the bits of 2^23 and subtracting 2^23 gives float(i) exactly.
-// ncu showed the first version of this kernel bound by the quarter-rate XU pipe (12 u8->f32 conversions per
-// pixel, sm__inst_executed_pipe_xu at its peak); these run on the full-rate ALU/FMA pipes instead.
-__device__ __forceinline__ float u23_to_float(uint32_t i) { return __uint_as_float(0x4B000000u | i) - 8388608.0f; }
-__device__ __forceinline__ float ldg_u8f(const uint8_t* p) { return u23_to_float((uint32_t)__ldg(p)); }
+// One thread = ONE destination column x kRowsPerThread destination rows; the 32 lanes of a warp are 32 adjacent
+// columns, so a warp-level byte load spans 32 px * 3 B = 96 B = 3-4 sectors and the planar stores are 128 contiguous
+// bytes per warp.  ncu (profiles/r01k_letterbox_ncu.txt) shows the kernel bound by INSTRUCTION ISSUE (81 % issue
+// active, 136 SASS instructions per pixel before the fast path below), not by HBM, and a rolled, row-serial variant
+// with fewer instructions was slower still (too few loads in flight): so everything is straight-line code that
+// issues all of a strip's loads before the first use.
+//   * the letterbox matrix has no rotation (m[1] = m[3] = -0.0f, preprocess.cu:99-104), so everything that depends on
+//     the column only (src_x, x taps, horizontal weights, byte offsets, validity) is computed once per thread;
+//   * the bilinear sum is written as the reference writes it and left to nvcc's default FMA contraction, exactly
+//     like the reference's own build: the output is BIT-IDENTICAL to the reference kernel's
+//     (tests/test_vs_reference_gpu.py::test_preprocess_vs_reference_kernel).
+constexpr int kRowsPerThread = 4;
 
-// One thread = ONE destination column x FOUR destination rows; the 32 lanes of a warp are 32 adjacent columns, so a
-// warp-level byte load spans 32 px * 3 B = 96 B = 3-4 sectors (with 4 adjacent pixels per lane it was 11.8 sectors per
-// request and the kernel sat on the L1 sector throughput: 59.5 M sectors for 39 MB of pixels), and the planar stores are
-// 128 contiguous bytes per warp.  The letterbox matrix has no rotation (m[1] = m[3] = -0.0f, preprocess.cu:99-104), so
-// everything that depends on the column only (src_x, x taps, horizontal weights, byte offsets, validity) is computed once
-// for the 4 rows; `m1*dy` / `m3*dx` only contribute signed zeros.
-//
-// Few instructions per pixel: source coordinates are CLAMPED into the image and the 12 bytes are always loaded (one
-// address per tap, channels through immediate offsets, no divergent border path); out-of-image taps are then replaced
-// by the border value with selects, which is what the reference's pointer redirection to `const_value` does
-// (preprocess.cu:38-57).  The bilinear sum is written as the reference writes it and left to nvcc's default FMA
-// contraction, exactly like the reference's own build: the output is BIT-IDENTICAL to the reference kernel's
-// (tests/test_vs_reference_gpu.py::test_preprocess_vs_reference_kernel).
 template <typename OutT>
 __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
                                                         int first_image) {
+    constexpr int R = kRowsPerThread;
     const int b = blockIdx.z;
     const PreImage& im = a.img[b];
     const int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int dy0 = (blockIdx.y * blockDim.y + threadIdx.y) * 4;
+    const int dy0 = (blockIdx.y * blockDim.y + threadIdx.y) * R;
     if (dx >= a.dw || dy0 >= a.dh) return;
     const size_t area = (size_t)a.dw * a.dh;
     OutT* base = dst + (size_t)(first_image + b) * 3 * area + (size_t)dy0 * a.dw + dx;
     const float cv = 128.0f;  // const_value_st (:115)
     const uint8_t* __restrict__ img = im.src;
+    const int sw = im.sw, sh = im.sh;
 
     // preprocess.cu:22 (src_x), evaluated with the thread's first dy: m[1]*dy is +-0 for every dy
     const float src_x = im.m[0] * (float)dx + im.m[1] * (float)dy0 + im.m[2] + 0.5f;
-    const bool x_out = src_x <= -1 || src_x >= im.sw;
+    const bool x_out = src_x <= -1 || src_x >= sw;
     const int x_low = (int)floorf(src_x);
     const int x_high = x_low + 1;
     const float lx = src_x - (float)x_low, hx = 1 - lx;
-    const bool xl = x_low >= 0, xh = x_high < im.sw;
-    const uint32_t o1 = (uint32_t)min(max(x_low, 0), im.sw - 1) * 3u, o2 = (uint32_t)min(max(x_high, 0), im.sw - 1) * 3u;
+    const bool xl = x_low >= 0, xh = x_high < sw;
     const float xm = im.m[3] * (float)dx;
 
+    // bgr -> rgb, /255 (:64-74); planar stores, 128 B per warp and plane
+    auto emit = [&](int r, float c0, float c1, float c2) {
+        OutT* o = base + (size_t)r * a.dw;
+        if constexpr (sizeof(OutT) == 4) {
+            o[0] = div255(c2);
+            o[area] = div255(c1);
+            o[2 * area] = div255(c0);
+        } else {
+            o[0] = __float2half_rn(div255(c2));
+            o[area] = __float2half_rn(div255(c1));
+            o[2 * area] = __float2half_rn(div255(c0));
+        }
+    };
+
+    float src_y[R];
+    int y_low[R];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int dy = dy0 + r;
-        if (dy >= a.dh) break;
-        const float src_y = xm + im.m[4] * (float)dy + im.m[5] + 0.5f;  // :23
-        float c0 = cv, c1 = cv, c2 = cv;
-        if (!(x_out || src_y <= -1 || src_y >= im.sh)) {
-            const int y_low = (int)floorf(src_y);
-            const int y_high = y_low + 1;
-            const float ly = src_y - (float)y_low, hy = 1 - ly;
+    for (int r = 0; r < R; ++r) {
+        src_y[r] = xm + im.m[4] * (float)(dy0 + r) + im.m[5] + 0.5f;  // :23
+        y_low[r] = (int)floorf(src_y[r]);
+    }
+    // Fast path (warp-uniform but for the image's left/right edge): a full strip whose rows step through CONSECUTIVE
+    // source rows, all taps inside the image -- any letterbox that does not shrink the image, e.g. the 640x640 ->
+    // 640x640 benchmark.  The R+1 source rows are loaded once (one address per row: the right tap is the next pixel)
+    // and shared by neighbouring destination rows: (R+1)*6 loads and conversions instead of R*12, no clamps, no selects.
+    bool fast = dy0 + R <= a.dh && xl && xh && y_low[0] >= 0 && y_low[0] + R < sh;
+#pragma unroll
+    for (int r = 1; r < R; ++r) fast = fast && y_low[r] == y_low[0] + r;
+    if (fast) {
+        const uint8_t* p = img + (size_t)y_low[0] * (size_t)im.pitch + (uint32_t)x_low * 3u;
+        float t[R + 1][6];
+#pragma unroll
+        for (int s = 0; s <= R; ++s) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) t[s][k] = (float)(uint32_t)__ldg(p + k);
+            p += im.pitch;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float ly = src_y[r] - (float)y_low[r], hy = 1 - ly;
             const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-            const bool r0ok = y_low >= 0, r1ok = y_high < im.sh;
-            const uint32_t row0 = (uint32_t)max(y_low, 0) * (uint32_t)im.pitch;               // images < 4 GiB
-            const uint32_t row1 = (uint32_t)min(y_high, im.sh - 1) * (uint32_t)im.pitch;
+            // :59-61 (left-to-right; nvcc contracts to mul + 3 fma, as in the reference build)
+            emit(r, w1 * t[r][0] + w2 * t[r][3] + w3 * t[r + 1][0] + w4 * t[r + 1][3],
+                 w1 * t[r][1] + w2 * t[r][4] + w3 * t[r + 1][1] + w4 * t[r + 1][4],
+                 w1 * t[r][2] + w2 * t[r][5] + w3 * t[r + 1][2] + w4 * t[r + 1][5]);
+        }
+        return;
+    }
+
+    // General path (borders, shrinking letterboxes): source coordinates are CLAMPED into the image and the 12 bytes
+    // always loaded (one address per tap, channels through immediate offsets, no divergent border path); out-of-image
+    // taps are then replaced by the border value with selects, which is what the reference's pointer redirection to
+    // `const_value` does (preprocess.cu:38-57).
+    const uint32_t o1 = (uint32_t)min(max(x_low, 0), sw - 1) * 3u, o2 = (uint32_t)min(max(x_high, 0), sw - 1) * 3u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (dy0 + r >= a.dh) break;
+        float c0 = cv, c1 = cv, c2 = cv;
+        if (!(x_out || src_y[r] <= -1 || src_y[r] >= sh)) {
+            const int y_high = y_low[r] + 1;
+            const float ly = src_y[r] - (float)y_low[r], hy = 1 - ly;
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const bool r0ok = y_low[r] >= 0, r1ok = y_high < sh;
+            const uint32_t row0 = (uint32_t)max(y_low[r], 0) * (uint32_t)im.pitch;  // images < 4 GiB
+            const uint32_t row1 = (uint32_t)min(y_high, sh - 1) * (uint32_t)im.pitch;
             const bool k1 = r0ok && xl, k2 = r0ok && xh, k3 = r1ok && xl, k4 = r1ok && xh;
-            const uint8_t* p1 = img + (row0 + o1);  // one address per tap, channels through immediate offsets
+            const uint8_t* p1 = img + (row0 + o1);
             const uint8_t* p2 = img + (row0 + o2);
             const uint8_t* p3 = img + (row1 + o1);
             const uint8_t* p4 = img + (row1 + o2);
@@ -112,22 +159,11 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ 
                 v3[k] = k3 ? t3 : cv;
                 v4[k] = k4 ? t4 : cv;
             }
-            // :59-61 (left-to-right; nvcc contracts to mul + 3 fma, as in the reference build)
             c0 = w1 * v1[0] + w2 * v2[0] + w3 * v3[0] + w4 * v4[0];
             c1 = w1 * v1[1] + w2 * v2[1] + w3 * v3[1] + w4 * v4[1];
             c2 = w1 * v1[2] + w2 * v2[2] + w3 * v3[2] + w4 * v4[2];
         }
-        // bgr -> rgb, /255 (:64-74); planar stores, 128 B per warp and plane
-        OutT* o = base + (size_t)r * a.dw;
-        if constexpr (sizeof(OutT) == 4) {
-            o[0] = div255(c2);
-            o[area] = div255(c1);
-            o[2 * area] = div255(c0);
-        } else {
-            o[0] = __float2half_rn(div255(c2));
-            o[area] = __float2half_rn(div255(c1));
-            o[2 * area] = __float2half_rn(div255(c0));
-        }
+        emit(r, c0, c1, c2);
     }
 }
 
@@ -188,8 +224,8 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
             a.img[i].pitch = d.pitch;
             trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, a.img[i].m);
         }
-        dim3 block(128, 2, 1);  // 128 columns x (2 x 4) rows per block
-        dim3 grid((dst_w + 127) / 128, (dst_h + 7) / 8, n);
+        dim3 block(128, 2, 1);  // 128 columns x (2 x kRowsPerThread) rows per block
+        dim3 grid((dst_w + 127) / 128, (dst_h + 2 * kRowsPerThread - 1) / (2 * kRowsPerThread), n);
         if (out_dtype == TRTX_F32)
             letterbox_kernel<float><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
         else

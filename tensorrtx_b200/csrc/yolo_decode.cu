@@ -198,11 +198,18 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
         if (a.prefetch_box != 2) load_box();
         const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE;
         const float fs = (float)L.stride;
+        // this epilogue is the kernel's tail (a lone warp, every instruction at full latency): one division per
+        // lane, the other cells of the quad step along the row
+        const int row0 = a0 / L.gw, col0 = a0 - row0 * L.gw;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             if (flags & (1u << j)) {
                 const int e = a0 + j;
-                const int row = e / L.gw, col = e - row * L.gw;
+                int row = row0, col = col0 + j;
+                while (col >= L.gw) {  // at most once unless the grid is narrower than the quad
+                    col -= L.gw;
+                    ++row;
+                }
                 // yololayer.cu:217-220
                 float x1 = ((float)col + 0.5f - d[0][j]) * fs;
                 float y1 = ((float)row + 0.5f - d[1][j]) * fs;

@@ -19,7 +19,8 @@ for f in glob.glob(tmp + "/*.cubin"):
         if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
         if re.match(r'\s+/\*[0-9a-f]{4,}\*/', ln): s.append(cur)
     if s: seq = s; break
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kre}"], capture_output=True, text=True).stdout
+extra = os.environ.get("NCU_EXTRA", "").split()  # e.g. NCU_EXTRA="--launch-skip 4 --launch-count 1" picks one launch
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kre}"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 for i, r in enumerate(rows):
     if '# Samples' in r: hdr = r; start = i + 1; break
