@@ -38,6 +38,9 @@ STRIDES = (8, 16, 32)
 MAX_OUT = 1000
 CONF, IOU = 0.5, 0.45
 ALGO_BYTES_PER_IMAGE = (4 + NC) * sum((NET // s) ** 2 for s in STRIDES) * 4  # 2 822 400 B, SURVEY 8d
+# dram__bytes_read.sum + dram__bytes_write.sum of one yolo_v8_scan_kernel launch at b32 on the dense synthetic heads,
+# from the `ncu --set full` capture summarised in profiles/r01k_scan_ncu.csv (90.30 MB read + 2.5 MB written)
+NCU_SCAN_DRAM_BYTES_B32 = 92_800_000
 METRIC = "end_to_end_fps_yolov8n_640_b32 (pre-process + fused decode + NMS); decode+NMS us/frame alongside"
 WORKLOAD = "YOLOv8n 640x640 b32/GPU: letterbox preprocess + YoloLayer decode + NMS, synthetic (SURVEY 8d), fp32 heads"
 
@@ -380,7 +383,8 @@ def main():
         "decode_nms_us_per_frame": ms_decnms * 1e3 / BATCH,
         "decode_nms_ms_per_batch": ms_decnms,
         "roofline": {"bound": "hbm", "kernel": "yolo_v8_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     "traffic": NCU_SCAN_DRAM_BYTES_B32 if BATCH == 32 and head_dtype == L.F32 else None,
                      "algorithmic_bytes_per_launch": algo, "kernel_us": scan_ms_b2b * 1e3,
                      "kernel_us_event_pair_per_launch": scan_ms_avg * 1e3,
                      "achieved_event_pair_per_launch": algo / (scan_ms_avg * 1e-3) / 1e9,

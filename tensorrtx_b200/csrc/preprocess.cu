@@ -51,12 +51,12 @@ __device__ __forceinline__ float div255(float x) {
 //   * the bilinear sum is written as the reference writes it and left to nvcc's default FMA contraction, exactly
 //     like the reference's own build: the output is BIT-IDENTICAL to the reference kernel's
 //     (tests/test_vs_reference_gpu.py::test_preprocess_vs_reference_kernel).
-constexpr int kRowsPerThread = 4;
+static int g_rows_per_thread = 4;  // tuning knob 6 (4 or 8)
+void preprocess_set_rows(int r) { g_rows_per_thread = r == 8 ? 8 : 4; }
 
-template <typename OutT>
+template <typename OutT, int R>
 __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
                                                         int first_image) {
-    constexpr int R = kRowsPerThread;
     const int b = blockIdx.z;
     const PreImage& im = a.img[b];
     const int dx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,12 +224,20 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
             a.img[i].pitch = d.pitch;
             trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, a.img[i].m);
         }
-        dim3 block(128, 2, 1);  // 128 columns x (2 x kRowsPerThread) rows per block
-        dim3 grid((dst_w + 127) / 128, (dst_h + 2 * kRowsPerThread - 1) / (2 * kRowsPerThread), n);
-        if (out_dtype == TRTX_F32)
-            letterbox_kernel<float><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
-        else
-            letterbox_kernel<__half><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
+        const int R = g_rows_per_thread;
+        dim3 block(128, 2, 1);  // 128 columns x (2 x R) rows per block
+        dim3 grid((dst_w + 127) / 128, (dst_h + 2 * R - 1) / (2 * R), n);
+        if (out_dtype == TRTX_F32) {
+            if (R == 8)
+                letterbox_kernel<float, 8><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
+            else
+                letterbox_kernel<float, 4><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
+        } else {
+            if (R == 8)
+                letterbox_kernel<__half, 8><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
+            else
+                letterbox_kernel<__half, 4><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
+        }
         int rc = check_launch();
         if (rc) return rc;
     }

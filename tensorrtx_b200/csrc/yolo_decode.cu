@@ -26,6 +26,7 @@ static int g_use_pipe = 0;      // 1: TMA-pipelined persistent scan (yolo_scan_p
 static int g_prefetch_box = 1;  // L2-prefetch the 4 box rows while the class rows stream
 void yolo_pipe_set_consumers(int n);
 void yolo_pipe_set_debug(int v);
+void preprocess_set_rows(int r);
 
 // --------------------------------------------------------------------------------------------
 // scan_classes: running (max logit, first argmax, max before it) over `nrows` channel rows for VEC
@@ -683,6 +684,7 @@ TRTX_API int trtx_tune_set(int key, int value) {
     else if (key == 3) yolo_pipe_set_consumers(value);
     else if (key == 4) yolo_pipe_set_debug(value);
     else if (key == 5) g_prefetch_box = value;
+    else if (key == 6) preprocess_set_rows(value);
     else return TRTX_ERR_INVALID;
     return TRTX_OK;
 }

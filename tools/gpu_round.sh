@@ -9,6 +9,7 @@ nproc >> $OUT/${TAG}_gpu.txt
 echo "== smoke" ; timeout 180 python __graft_entry__.py --smoke 2>&1 | tail -5 | tee $OUT/${TAG}_smoke.log
 echo "== pytest -m gpu" ; timeout 600 python -m pytest tests -q -m gpu --timeout 120 2>&1 | tail -25 | tee $OUT/${TAG}_pytest_gpu.log
 echo "== bench" ; timeout 600 python bench.py --steps 300 --warmup 20 2>$OUT/${TAG}_bench.err | tee $OUT/${TAG}_bench.json
+echo "== bench --impl reference" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>>$OUT/${TAG}_bench.err | tee $OUT/${TAG}_bench_reference.json
 tail -5 $OUT/${TAG}_bench.err
 echo "== sweep" ; timeout 600 python tools/sweep_scan.py 2>&1 | tee $OUT/${TAG}_sweep.log
 echo "== ncu launches"
