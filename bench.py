@@ -221,7 +221,7 @@ def main():
 
     from tensorrtx_b200 import _lib as L
     from tensorrtx_b200 import synth
-    from tensorrtx_b200.pipeline import DetectionPipeline, gather
+    from tensorrtx_b200.pipeline import DetectionPipeline, GatherRing
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
@@ -264,26 +264,71 @@ def main():
     del frame_sets_dev
 
     with torch.cuda.stream(stream):
+        # N > 1: the fixed-size all-gather of step i-1 rides a side stream WHILE step i computes, as a parallel branch
+        # of step i's CUDA graph (tensorrtx_b200.pipeline.GatherRing): every step still issues exactly one collective,
+        # and the last step's is flushed before the closing event.
+        ring = GatherRing(world, BATCH, pipe.fused.out.shape[1], dev, slots=R)
+
+        def make_step(j):
+            p, h, prev = pipes_dev[j], head_sets[j], pipes_dev[(j - 1) % R]
+
+            def f():
+                if world > 1:
+                    ring.launch(prev.fused.out, (j - 1) % R)  # fork: detections of the previous step
+                p.run_device(h)
+                ring.join()                                    # join the side stream (ends the graph's second branch)
+            return f
+
+        if world > 1:  # NCCL communicator and buffers must exist before anything is captured
+            ring.launch(pipes_dev[0].fused.out, 0)
+            ring.join()
+            torch.cuda.synchronize(dev)
+        gather_mode = "none" if world == 1 else "graph-branch"
+        needs_flush = world > 1  # make_step() gathers the PREVIOUS step's detections
         if args.no_graph:
-            dev_steps = [(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
+            dev_steps = [make_step(j) for j in range(R)]
+            gather_mode = "none" if world == 1 else "side-stream"
         else:
-            dg = [p.capture(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
-            dev_steps = [g.replay for g in dg]
+            try:
+                dg = [pipe.capture(make_step(j), "thread_local" if world > 1 else "global") for j in range(R)]
+                dev_steps = [g.replay for g in dg]
+            except Exception as e:  # NCCL refused to be captured: graphs for the kernels, eager collective on the side stream
+                if world == 1:
+                    raise
+                print(f"[bench] capturing the all-gather failed ({type(e).__name__}: {e}); falling back to an eager gather",
+                      file=sys.stderr)
+                torch.cuda.synchronize(dev)
+                gather_mode = "side-stream, eager"
+                needs_flush = False
+                dgc = [p.capture(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
+
+                def make_eager(j):
+                    def f():
+                        ring.reuse(j)  # the collective that last read this slot must be done before it is overwritten
+                        dgc[j].replay()
+                        ring.launch(pipes_dev[j].fused.out, j)
+                    return f
+                dev_steps = [make_eager(j) for j in range(R)]
 
         def step_dev(i):
             dev_steps[i % R]()
-            if world > 1:
-                return gather(pipes_dev[i % R].fused.out, world)
+
+        def flush_dev(i_last):
+            if needs_flush:
+                ring.launch(pipes_dev[i_last % R].fused.out, i_last % R)
+                ring.join()
 
         def step_e2e(i):
             # public API call with HOST frames: H2D (copy stream, double-buffered) + preprocess + decode + NMS + D2H
+            ring.join()  # one pipeline, one output buffer: the previous step's collective must have read it
             pipe.submit(frame_sets_host[i % R], head_sets[i % R])
             if world > 1:
-                return gather(pipe.fused.out, world)
+                ring.launch(pipe.fused.out, i % R)
 
-        def timed(step, K, W):
+        def timed(step, K, W, flush=None):
             for i in range(W):
                 step(i)
+            ring.join()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize(dev)
@@ -292,6 +337,9 @@ def main():
             e0.record(stream)
             for i in range(K):
                 step(W + i)
+            if flush is not None:
+                flush(W + K - 1)  # the last step's collective
+            ring.join()  # every collective of the timed steps completes inside the timed region
             e1.record(stream)
             torch.cuda.synchronize(dev)
             t1 = time.time()
@@ -309,7 +357,7 @@ def main():
             sampler.start()
             time.sleep(0.25)
         K, W = args.steps, args.warmup
-        ms_dev, win_dev = timed(step_dev, K, W)
+        ms_dev, win_dev = timed(step_dev, K, W, flush_dev)
         ms_e2e, win_e2e = timed(step_e2e, K, W)
 
         # ---- decode+NMS only (the "decode+NMS us/frame" half of the metric) and the scan kernel alone,
@@ -346,9 +394,25 @@ def main():
         if rank == 0:
             sampler.stop()
 
+    def leave():
+        """N > 1: the step graphs hold captured NCCL kernels, and destroying the communicator under them can block;
+        drop the graphs, meet the other ranks once more, flush and leave without the interpreter's teardown."""
+        if world == 1:
+            return
+        sys.stdout.flush()
+        t = threading.Timer(60.0, lambda: os._exit(0))  # never outlive the run because a peer is gone
+        t.daemon = True
+        t.start()
+        torch.cuda.synchronize(dev)
+        dev_steps.clear()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave()
         return
 
     peaks, peak_src = None, "fallback"
@@ -368,7 +432,7 @@ def main():
         "dtype": "f32" if head_dtype == L.F32 else "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "net": [NET, NET],
                    "num_classes": NC, "max_out": MAX_OUT, "conf_thresh": CONF, "nms_thresh": IOU,
-                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [32,1+1000*7] fp32 per step)" if world > 1 else "single GPU",
+                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [32,1+1000*7] fp32 per step, overlapped with the next step: {gather_mode})" if world > 1 else "single GPU",
                    "l2": f"inputs rotate over {R} distinct sets ({R * head_bytes / 1e6:.0f} MB of head tensors + "
                          f"{R * BATCH * NET * NET * 3 / 1e6:.0f} MB of frames > 126 MB L2)",
                    "cuda_graphs": not args.no_graph,
@@ -402,9 +466,8 @@ def main():
         out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": f"{total} frames (the b32 set cycled), decode+nms oracle, {cores} threads",
                                "single_thread_fps": c1fps, "us_per_frame_single_thread": 1e6 / c1fps}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    leave()
 
 
 if __name__ == "__main__":

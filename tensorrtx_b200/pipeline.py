@@ -95,12 +95,14 @@ class DetectionPipeline:
 
     # ---- CUDA graphs: the step is launch-bound (4 kernels of 10-30 us), so replaying a captured graph
     # removes the per-launch host cost (guide: "capture launch-bound inner loops in CUDA graphs") ----
-    def capture(self, fn: Callable[[], object]) -> "torch.cuda.CUDAGraph":
-        """Capture `fn` (which must only enqueue work on the current stream) into a CUDA graph."""
+    def capture(self, fn: Callable[[], object], capture_error_mode: str = "global") -> "torch.cuda.CUDAGraph":
+        """Capture `fn` (which must only enqueue work on the current stream, or on streams forked from and joined
+        back into it) into a CUDA graph.  Use capture_error_mode="thread_local" when other threads of the process
+        (e.g. the NCCL watchdog) may touch CUDA during the capture."""
         fn()  # warm-up outside capture (lazy module loads, cudaFuncSetAttribute)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode=capture_error_mode):
             fn()
         return g
 
@@ -114,3 +116,49 @@ def gather(local: torch.Tensor, world_size: int) -> torch.Tensor:
     out = torch.empty((world_size * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous())
     return out
+
+
+class GatherRing:
+    """The same all-gather, pipelined: step i's compact detections travel on a side stream while step i+1 computes.
+
+    `slots` preallocated destination buffers ([world*B_local, 1+K*7]); `launch(local, slot)` orders the collective
+    after everything queued so far on the current stream and returns immediately; `reuse(slot)` makes the current stream
+    wait until that slot's previous collective has read its source (call it before overwriting the source buffer);
+    `join()` makes the current stream wait for all collectives (call before the closing timing event / before reading).
+    On a CPU process group (gloo, tests) there are no streams and every call is synchronous."""
+
+    def __init__(self, world_size: int, rows: int, cols: int, device, slots: int = 4, dtype=torch.float32):
+        self.world = world_size
+        self.cuda = torch.device(device).type == "cuda"
+        self.bufs = [torch.empty((world_size * rows, cols), dtype=dtype, device=device) for _ in range(slots)]
+        if self.cuda:
+            self.comm = torch.cuda.Stream(device=device)
+            self.done = [torch.cuda.Event() for _ in range(slots)]
+            self.ready = [torch.cuda.Event() for _ in range(slots)]
+            self.used = [False] * slots
+
+    def launch(self, local: torch.Tensor, slot: int) -> torch.Tensor:
+        import torch.distributed as dist
+
+        out = self.bufs[slot]
+        if self.world == 1:
+            return local
+        if not self.cuda:
+            dist.all_gather_into_tensor(out, local.contiguous())
+            return out
+        cur = torch.cuda.current_stream(local.device)
+        self.ready[slot].record(cur)
+        self.comm.wait_event(self.ready[slot])
+        with torch.cuda.stream(self.comm):
+            dist.all_gather_into_tensor(out, local)
+            self.done[slot].record(self.comm)
+        self.used[slot] = True
+        return out
+
+    def reuse(self, slot: int) -> None:
+        if self.cuda and self.world > 1 and self.used[slot]:
+            torch.cuda.current_stream(self.bufs[slot].device).wait_event(self.done[slot])
+
+    def join(self) -> None:
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.bufs[0].device).wait_stream(self.comm)

@@ -148,6 +148,16 @@ assert out.shape == (world * B, 1 + K * 7)
 for r in range(world):
     assert torch.equal(out[r * B:(r + 1) * B], torch.full((B, 1 + K * 7), float(r)) + torch.arange(B)[:, None])
 # batch sharding: rank r owns images [B*r, B*(r+1)) of the global batch
+# the pipelined form used by bench.py (side stream on CUDA, synchronous on a CPU group): several steps, rotating slots
+from tensorrtx_b200.pipeline import GatherRing
+ring = GatherRing(world, B, 1 + K * 7, "cpu", slots=2)
+for step in range(5):
+    ring.reuse(step % 2)
+    src = local + 100.0 * step
+    got = ring.launch(src, step % 2)
+    ring.join()
+    for r in range(world):
+        assert torch.equal(got[r * B:(r + 1) * B], torch.full((B, 1 + K * 7), float(r)) + torch.arange(B)[:, None] + 100.0 * step)
 dist.barrier(); dist.destroy_process_group(); print("ok", rank)
 """
 
