@@ -107,6 +107,10 @@ enum {
     TRTX_BOX_LTRB = 0,   /* yolov8 Detection: x1,y1,x2,y2; IoU of postprocess.cpp:71-85 */
     TRTX_BOX_CXCYWH = 1, /* yolov5 Detection: cx,cy,w,h;   IoU of yolov5 postprocess.cpp:30-43 */
     TRTX_BOX_RETINA = 2, /* retinaface: x1,y1,x2,y2, +1e-6f in the denominator, single class (common.hpp:91-104) */
+    TRTX_BOX_OBB = 3,    /* yolov8-obb Detection: cx,cy,w,h + angle = the FIRST extra float (extra_floats >= 1,
+                            extra_offset = 89 for plugin rows); greedy = nms_obb / probiou `>=`
+                            (postprocess.cpp:303-385), one-shot = nms_kernel_obb / box_probiou `>`
+                            (postprocess.cu:113-166).  Plugin-row source only (not the fused tile source). */
 };
 enum {
     TRTX_NMS_GREEDY = 0,  /* CPU nms() semantics (the contract, SURVEY.md section 7 "Hard parts") */

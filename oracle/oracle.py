@@ -88,7 +88,7 @@ def retina_decode(heads, in_h=640, in_w=640, gate=0.02):
 
 
 def nms(variant, plugin_out_img, max_rows, det_floats, conf_thresh, nms_thresh):
-    """One image. variant 0 v8 / 1 v5 / 2 retinaface. -> (res [n, det_floats], src_row [n])."""
+    """One image. variant 0 v8 / 1 v5 / 2 retinaface / 3 v8-obb (nms_obb, probiou). -> (res [n, det_floats], src_row [n])."""
     lib = load()
     lib.oracle_nms.restype = C.c_int
     p = np.ascontiguousarray(plugin_out_img, np.float32)
@@ -105,6 +105,16 @@ def cuda_decode_nms(plugin_out_img, max_rows, det_floats, conf_thresh, nms_thres
     out = np.zeros(1 + max_objects * 7, np.float32)
     lib.oracle_cuda_decode_nms(p.ctypes.data_as(C.c_void_p), max_rows, det_floats, C.c_float(conf_thresh),
                                C.c_float(nms_thresh), max_objects, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def cuda_decode_nms_obb(plugin_out_img, max_rows, det_floats, conf_thresh, nms_thresh, max_objects):
+    """decode_kernel_obb + nms_kernel_obb (one-shot, ProbIoU); rows of 8 floats (cx,cy,w,h,conf,cls,keep,angle)."""
+    lib = load()
+    p = np.ascontiguousarray(plugin_out_img, np.float32)
+    out = np.zeros(1 + max_objects * 8, np.float32)
+    lib.oracle_cuda_decode_nms_obb(p.ctypes.data_as(C.c_void_p), max_rows, det_floats, C.c_float(conf_thresh),
+                                   C.c_float(nms_thresh), max_objects, out.ctypes.data_as(C.c_void_p))
     return out
 
 

@@ -15,6 +15,13 @@ __attribute__((visibility("default"))) int ref_v8_nms(float* output_host, float 
     for (size_t i = 0; i < res.size(); ++i) memcpy(res_out + i * (sizeof(Detection) / 4), &res[i], sizeof(Detection));
     return (int)res.size();
 }
+// nms_obb (postprocess.cpp:357-385): greedy, probiou >= thresh
+__attribute__((visibility("default"))) int ref_v8_nms_obb(float* output_host, float conf_thresh, float nms_thresh, float* res_out) {
+    std::vector<Detection> res;
+    nms_obb(res, output_host, conf_thresh, nms_thresh);
+    for (size_t i = 0; i < res.size(); ++i) memcpy(res_out + i * (sizeof(Detection) / 4), &res[i], sizeof(Detection));
+    return (int)res.size();
+}
 __attribute__((visibility("default"))) int ref_v8_batch_nms(float* output_host, int batch, int output_size, float conf_thresh,
                                                             float nms_thresh, float* res_out, int* counts, int max_rows) {
     std::vector<std::vector<Detection>> rb;

@@ -325,6 +325,38 @@ static float iou_retina(const float* l, const float* r) { /* retinaface/common.h
     return inter / ((l[2] - l[0]) * (l[3] - l[1]) + (r[2] - r[0]) * (r[3] - r[1]) - inter + 0.000001f);
 }
 
+/* yolov8-obb: convariance_matrix / probiou, yolov8/src/postprocess.cpp:303-355, with the C++ promotions spelled out:
+ * `w * w / 12.0` divides in double; std::pow(float, int) is double; std::cos/sin/exp/sqrt(float) are the float
+ * overloads; std::log and the last std::sqrt see double arguments.  d = Detection row, angle = d[89] (types.h:4-12). */
+static void cov_host(const float* d, int angle_idx, float* a, float* b, float* c) {
+    float w = d[2], h = d[3];
+    float A = (float)((double)(w * w) / 12.0), B = (float)((double)(h * h) / 12.0);
+    float r = d[angle_idx];
+    float cos_r = cosf(r), sin_r = sinf(r);
+    float cos_r2 = cos_r * cos_r, sin_r2 = sin_r * sin_r;
+    *a = A * cos_r2 + B * sin_r2;
+    *b = A * sin_r2 + B * cos_r2;
+    *c = (A - B) * cos_r * sin_r;
+}
+static float probiou_host(const float* r1, const float* r2, int angle_idx) {
+    const float eps = 1e-7;
+    float a1, b1, c1, a2, b2, c2;
+    cov_host(r1, angle_idx, &a1, &b1, &c1);
+    cov_host(r2, angle_idx, &a2, &b2, &c2);
+    float x1 = r1[0], y1 = r1[1], x2 = r2[0], y2 = r2[1];
+    double py = pow((double)(y1 - y2), 2), px = pow((double)(x1 - x2), 2), pc = pow((double)(c1 + c2), 2);
+    float t1 = (float)(((double)(a1 + a2) * py + (double)(b1 + b2) * px) / ((double)((a1 + a2) * (b1 + b2)) - pc + (double)eps));
+    float t2 = (float)((double)((c1 + c2) * (x2 - x1) * (y1 - y2)) / ((double)((a1 + a2) * (b1 + b2)) - pc + (double)eps));
+    float m1 = a1 * b1 - c1 * c1, m2 = a2 * b2 - c2 * c2;
+    float den3 = 4 * sqrtf(m1 > 0.0f ? m1 : 0.0f) * sqrtf(m2 > 0.0f ? m2 : 0.0f) + eps; /* std::max(x, 0.0f) */
+    float t3 = (float)log(((double)((a1 + a2) * (b1 + b2)) - pc) / (double)den3 + (double)eps);
+    float bd = 0.25f * t1 + 0.5f * t2 + 0.5f * t3;
+    bd = bd < 100.0f ? bd : 100.0f; /* std::min(bd, 100.0f) */
+    bd = bd > eps ? bd : eps;       /* std::max(.., eps) */
+    float hd = (float)sqrt(1.0 - (double)expf(-bd) + (double)eps);
+    return 1 - hd;
+}
+
 typedef struct {
     float cls, conf, x0;
     int src;
@@ -335,7 +367,7 @@ static int nms_cmp(const void* pa, const void* pb) {
     const nms_key* b = (const nms_key*)pb;
     if (a->cls != b->cls) return a->cls < b->cls ? -1 : 1;    /* std::map key order */
     if (a->conf != b->conf) return a->conf > b->conf ? -1 : 1; /* cmp: conf desc */
-    if (g_variant == 0 && a->x0 != b->x0) return a->x0 < b->x0 ? -1 : 1; /* v8 :87-92 */
+    if ((g_variant == 0 || g_variant == 3) && a->x0 != b->x0) return a->x0 < b->x0 ? -1 : 1; /* v8 :87-92 */
     return a->src < b->src ? -1 : (a->src > b->src ? 1 : 0);
 }
 
@@ -376,6 +408,10 @@ ORACLE_API int oracle_nms(int variant, const float* plugin_out, int max_rows, in
         for (int q = m + 1; q < n && keys[q].cls == keys[m].cls; ++q) {
             if (erased[q]) continue;
             const float* other = plugin_out + 1 + (size_t)keys[q].src * det_floats;
+            if (variant == 3) { /* nms_obb :357-385: probiou `>=` */
+                if (probiou_host(item, other, det_floats - 1) >= nms_thresh) erased[q] = 1;
+                continue;
+            }
             float v = variant == 0 ? iou_ltrb(item, other) : (variant == 1 ? iou_cxcywh(item, other) : iou_retina(item, other));
             if (v > nms_thresh) erased[q] = 1; /* dets.erase(...) */
         }
@@ -444,6 +480,75 @@ ORACLE_API void oracle_cuda_decode_nms(const float* predict, int max_rows, int d
     }
     for (int p = 0; p < n; ++p)
         if (drop[p]) parray[1 + p * 7 + 6] = 0;
+    free(drop);
+}
+
+/* The oriented-box flavour of the same post-process: decode_kernel_obb + nms_kernel_obb, yolov8/src/postprocess.cu:7-40,
+ * 113-166.  parray rows are 8 floats (cx,cy,w,h,conf,cls,keep,angle), angle = Detection float 89; box_probiou is all
+ * float (powf/logf/expf/sqrtf/cosf/sinf); `>` threshold. */
+static void cov_dev(float w, float h, float r, float* a, float* b, float* c) {
+    float a_val = w * w / 12.0f, b_val = h * h / 12.0f;
+    float cos_r = cosf(r), sin_r = sinf(r);
+    *a = a_val * cos_r * cos_r + b_val * sin_r * sin_r;
+    *b = a_val * sin_r * sin_r + b_val * cos_r * cos_r;
+    *c = (a_val - b_val) * sin_r * cos_r;
+}
+static float box_probiou_gpu(const float* p, const float* q) {
+    const float eps = 1e-7;
+    float a1, b1, c1, a2, b2, c2;
+    cov_dev(p[2], p[3], p[7], &a1, &b1, &c1);
+    cov_dev(q[2], q[3], q[7], &a2, &b2, &c2);
+    float cx1 = p[0], cy1 = p[1], cx2 = q[0], cy2 = q[1];
+    float t1 = ((a1 + a2) * powf(cy1 - cy2, 2) + (b1 + b2) * powf(cx1 - cx2, 2)) / ((a1 + a2) * (b1 + b2) - powf(c1 + c2, 2) + eps);
+    float t2 = ((c1 + c2) * (cx2 - cx1) * (cy1 - cy2)) / ((a1 + a2) * (b1 + b2) - powf(c1 + c2, 2) + eps);
+    float t3 = logf(((a1 + a2) * (b1 + b2) - powf(c1 + c2, 2)) /
+                            (4 * sqrtf(fmaxf(a1 * b1 - c1 * c1, 0.0f)) * sqrtf(fmaxf(a2 * b2 - c2 * c2, 0.0f)) + eps) +
+                    eps);
+    float bd = 0.25f * t1 + 0.5f * t2 + 0.5f * t3;
+    bd = fmaxf(fminf(bd, 100.0f), eps);
+    float hd = sqrtf(1.0f - expf(-bd) + eps);
+    return 1 - hd;
+}
+ORACLE_API void oracle_cuda_decode_nms_obb(const float* predict, int max_rows, int det_floats, float conf_thresh,
+                                           float nms_thresh, int max_objects, float* parray) {
+    memset(parray, 0, sizeof(float) * (size_t)(1 + max_objects * 8));
+    int count = (int)predict[0];
+    if (count > max_rows) count = max_rows;
+    int index = 0;
+    for (int pos = 0; pos < count; ++pos) { /* decode_kernel_obb :7-40 */
+        const float* pitem = predict + 1 + (size_t)pos * det_floats;
+        int my = index++;
+        if (my >= max_objects) continue;
+        if (pitem[4] < conf_thresh) continue;
+        float* po = parray + 1 + my * 8;
+        po[0] = pitem[0];
+        po[1] = pitem[1];
+        po[2] = pitem[2];
+        po[3] = pitem[3];
+        po[4] = pitem[4];
+        po[5] = pitem[5];
+        po[6] = 1;
+        po[7] = pitem[det_floats - 1]; /* pitem[89] */
+    }
+    parray[0] = (float)index;
+    int n = index < max_objects ? index : max_objects;
+    char* drop = (char*)calloc((size_t)(n > 0 ? n : 1), 1);
+    for (int p = 0; p < n; ++p) { /* nms_kernel_obb :147-166 */
+        const float* pc = parray + 1 + p * 8;
+        for (int i = 0; i < n; ++i) {
+            const float* pi = parray + 1 + i * 8;
+            if (i == p || pc[5] != pi[5]) continue;
+            if (pi[4] >= pc[4]) {
+                if (pi[4] == pc[4] && i < p) continue;
+                if (box_probiou_gpu(pc, pi) > nms_thresh) {
+                    drop[p] = 1;
+                    break;
+                }
+            }
+        }
+    }
+    for (int p = 0; p < n; ++p)
+        if (drop[p]) parray[1 + p * 8 + 6] = 0;
     free(drop);
 }
 

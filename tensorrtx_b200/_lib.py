@@ -13,7 +13,7 @@ MAX_LEVELS = 8
 OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = range(5)
 YOLO_V8, YOLO_V5 = 0, 1
 F32, F16 = 0, 1
-BOX_LTRB, BOX_CXCYWH, BOX_RETINA = 0, 1, 2
+BOX_LTRB, BOX_CXCYWH, BOX_RETINA, BOX_OBB = 0, 1, 2, 3
 NMS_GREEDY, NMS_ONESHOT = 0, 1
 
 _ERR = {1: "TRTX_ERR_INVALID", 2: "TRTX_ERR_WORKSPACE", 3: "TRTX_ERR_CUDA", 4: "TRTX_ERR_UNSUPPORTED"}

@@ -79,6 +79,61 @@ __device__ __forceinline__ float iou_oneshot(const float4 a, const float4 b) {
     float b_area = __fmul_rn(fmaxf(0.0f, __fsub_rn(b.z, b.x)), fmaxf(0.0f, __fsub_rn(b.w, b.y)));
     return __fdiv_rn(c_area, __fsub_rn(__fadd_rn(a_area, b_area), c_area));
 }
+// ---- oriented boxes (yolov8-obb): Gaussian covariance per row + ProbIoU per pair ------------------------------
+// Host flavour = convariance_matrix / probiou of yolov8/src/postprocess.cpp:303-355 with its C++ promotions
+// (`w*w/12.0` and every std::pow(x, 2) are double, std::cos/sin/exp(float) are float, std::log/sqrt of the mixed
+// expressions are double); device flavour = postprocess.cu:113-145, all float, left to nvcc's FMA contraction like
+// the reference build.  A row is kept as (cx, cy, a, b) + c.
+__device__ __forceinline__ void obb_cov_host(float w, float h, float r, float& a, float& b, float& c) {
+    const float A = (float)((double)__fmul_rn(w, w) / 12.0), B = (float)((double)__fmul_rn(h, h) / 12.0);
+    const float cr = cosf(r), sr = sinf(r);
+    const float cr2 = __fmul_rn(cr, cr), sr2 = __fmul_rn(sr, sr);
+    a = __fadd_rn(__fmul_rn(A, cr2), __fmul_rn(B, sr2));
+    b = __fadd_rn(__fmul_rn(A, sr2), __fmul_rn(B, cr2));
+    c = __fmul_rn(__fmul_rn(__fsub_rn(A, B), cr), sr);
+}
+__device__ __forceinline__ float obb_probiou_host(const float4 p1, float c1, const float4 p2, float c2) {
+    const float eps = 1e-7;
+    const float x1 = p1.x, y1 = p1.y, a1 = p1.z, b1 = p1.w, x2 = p2.x, y2 = p2.y, a2 = p2.z, b2 = p2.w;
+    const float sa = __fadd_rn(a1, a2), sb = __fadd_rn(b1, b2), sc = __fadd_rn(c1, c2);
+    const double dy = (double)__fsub_rn(y1, y2), dx = (double)__fsub_rn(x1, x2), dc = (double)sc;
+    const double py = __dmul_rn(dy, dy), px = __dmul_rn(dx, dx), pc = __dmul_rn(dc, dc);  // std::pow(float, 2): exact in double
+    const double den = __dadd_rn(__dsub_rn((double)__fmul_rn(sa, sb), pc), (double)eps);
+    const float t1 = (float)__ddiv_rn(__dadd_rn(__dmul_rn((double)sa, py), __dmul_rn((double)sb, px)), den);
+    const float t2 = (float)__ddiv_rn((double)__fmul_rn(__fmul_rn(sc, __fsub_rn(x2, x1)), __fsub_rn(y1, y2)), den);
+    const float s1 = sqrtf(fmaxf(__fsub_rn(__fmul_rn(a1, b1), __fmul_rn(c1, c1)), 0.0f));
+    const float s2 = sqrtf(fmaxf(__fsub_rn(__fmul_rn(a2, b2), __fmul_rn(c2, c2)), 0.0f));
+    const float d3 = __fadd_rn(__fmul_rn(__fmul_rn(4.0f, s1), s2), eps);
+    const float t3 = (float)log(__dadd_rn(__ddiv_rn(__dsub_rn((double)__fmul_rn(sa, sb), pc), (double)d3), (double)eps));
+    float bd = __fadd_rn(__fadd_rn(__fmul_rn(0.25f, t1), __fmul_rn(0.5f, t2)), __fmul_rn(0.5f, t3));
+    bd = fmaxf(fminf(bd, 100.0f), eps);
+    const float hd = (float)sqrt(__dadd_rn(__dsub_rn(1.0, (double)expf(-bd)), (double)eps));
+    return __fsub_rn(1.0f, hd);
+}
+__device__ __forceinline__ void obb_cov_dev(float w, float h, float r, float& a, float& b, float& c) {  // :113-122
+    float a_val = w * w / 12.0f;
+    float b_val = h * h / 12.0f;
+    float cos_r = cosf(r);
+    float sin_r = sinf(r);
+    a = a_val * cos_r * cos_r + b_val * sin_r * sin_r;
+    b = a_val * sin_r * sin_r + b_val * cos_r * cos_r;
+    c = (a_val - b_val) * sin_r * cos_r;
+}
+__device__ __forceinline__ float obb_probiou_dev(const float4 p1, float c1, const float4 p2, float c2) {  // :124-145
+    const float eps = 1e-7;
+    const float cx1 = p1.x, cy1 = p1.y, a1 = p1.z, b1 = p1.w, cx2 = p2.x, cy2 = p2.y, a2 = p2.z, b2 = p2.w;
+    float t1 = ((a1 + a2) * powf(cy1 - cy2, 2) + (b1 + b2) * powf(cx1 - cx2, 2)) /
+               ((a1 + a2) * (b1 + b2) - powf(c1 + c2, 2) + eps);
+    float t2 = ((c1 + c2) * (cx2 - cx1) * (cy1 - cy2)) / ((a1 + a2) * (b1 + b2) - powf(c1 + c2, 2) + eps);
+    float t3 = logf(((a1 + a2) * (b1 + b2) - powf(c1 + c2, 2)) /
+                            (4 * sqrtf(fmaxf(a1 * b1 - c1 * c1, 0.0f)) * sqrtf(fmaxf(a2 * b2 - c2 * c2, 0.0f)) + eps) +
+                    eps);
+    float bd = 0.25f * t1 + 0.5f * t2 + 0.5f * t3;
+    bd = fmaxf(fminf(bd, 100.0f), eps);
+    float hd = sqrtf(1.0f - expf(-bd) + eps);
+    return 1 - hd;
+}
+
 // ---- greedy NMS inner loop: boxes pre-converted to corners, areas precomputed ---------------------------------
 // The three host IoUs above differ only in how corners and areas are formed and in retinaface's +1e-6; with those
 // hoisted out (phase D) one test serves all.  Every operation is the reference's, in the reference's order.
@@ -94,6 +149,7 @@ __device__ __forceinline__ float box_area(int fmt, const float4 b) {  // b = the
 }
 struct IouTest {
     float thr;
+    bool obb;       // rows are (cx, cy, a, b) + c: ProbIoU `>= thr` (nms_obb, postprocess.cpp:378)
     bool retina;    // denominator + 0.000001f
     bool zero_hit;  // `0.0f > thr` (disjoint boxes)
     bool fast_ok;   // the division-free test below is proven for |thr| <= 4
@@ -103,6 +159,7 @@ struct IouTest {
 // least ~1e-5 away from thr -- hundreds of ulps for |thr| <= 4.  Anything closer, or a non-positive / non-finite
 // denominator, takes the IEEE division the reference takes.
 __device__ __forceinline__ bool overlaps(const IouTest& q, const float4 l, float la, const float4 r, float ra) {
+    if (q.obb) return obb_probiou_host(l, la, r, ra) >= q.thr;
     const float ib0 = l.x < r.x ? r.x : l.x;
     const float ib1 = r.z < l.z ? r.z : l.z;
     const float ib2 = l.y < r.y ? r.y : l.y;
@@ -508,13 +565,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     const bool greedy = a.mode == TRTX_NMS_GREEDY;
     IouTest iq;
     iq.thr = a.nms_thresh;
+    iq.obb = a.box_format == TRTX_BOX_OBB;
     iq.retina = a.box_format == TRTX_BOX_RETINA;
     iq.zero_hit = 0.0f > a.nms_thresh;
     iq.fast_ok = fabsf(a.nms_thresh) <= 4.0f;
     for (int i = tid; i < M; i += kNmsThreads) {
         const int pos = (int)(k64[i] & 0xffffull);
         const float4 bx = u_box[pos];
-        if (greedy) {  // the host IoUs work on corners and areas: form both once per row instead of once per pair
+        if (a.box_format == TRTX_BOX_OBB) {  // covariance of the row's Gaussian, once per row; the angle is the first extra float
+            const float ang = a.rows[(size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 + (size_t)u_id[pos] * a.det_floats +
+                                     a.extra_offset];
+            float ca, cb, cc;
+            if (greedy)
+                obb_cov_host(bx.z, bx.w, ang, ca, cb, cc);
+            else
+                obb_cov_dev(bx.z, bx.w, ang, ca, cb, cc);
+            s_box[i] = make_float4(bx.x, bx.y, ca, cb);
+            s_area[i] = cc;
+        } else if (greedy) {  // the host IoUs work on corners and areas: form both once per row instead of once per pair
             s_box[i] = to_corners(a.box_format, bx);
             s_area[i] = box_area(a.box_format, bx);
         } else {
@@ -704,7 +772,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             const float4 bi = s_box[i];
             bool keep = true;
             for (int jx = i - 1; jx >= 0 && s_cls[jx] == ci; --jx) {
-                if (iou_oneshot(bi, s_box[jx]) > a.nms_thresh) {
+                if (iq.obb ? obb_probiou_dev(bi, s_area[i], s_box[jx], s_area[jx]) > a.nms_thresh
+                           : iou_oneshot(bi, s_box[jx]) > a.nms_thresh) {
                     keep = false;
                     break;
                 }
@@ -733,8 +802,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         __syncthreads();
         const int k = carry + s_wsum[warp] + __popc(bal & ((1u << lane) - 1u));
         if (emit && k < a.max_det) {
-            // greedy + cx,cy,w,h rows were turned into corners for the IoU tests: emit the row as it came in
-            const float4 bx = greedy && a.box_format == TRTX_BOX_CXCYWH ? fetch_row(a, b, s_id[i]).box : s_box[i];
+            // rows that were turned into corners / covariances for the overlap tests are emitted as they came in
+            const float4 bx = a.box_format == TRTX_BOX_OBB || (greedy && a.box_format == TRTX_BOX_CXCYWH)
+                                  ? fetch_row(a, b, s_id[i]).box
+                                  : s_box[i];
             float* row = o + 1 + (size_t)k * R;
             row[0] = bx.x;
             row[1] = bx.y;
@@ -770,7 +841,8 @@ static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
 
 static int nms_validate(const trtx_nms_params* q) {
     if (!q) return TRTX_ERR_INVALID;
-    if (q->box_format < 0 || q->box_format > 2) return TRTX_ERR_INVALID;
+    if (q->box_format < 0 || q->box_format > TRTX_BOX_OBB) return TRTX_ERR_INVALID;
+    if (q->box_format == TRTX_BOX_OBB && q->extra_floats < 1) return TRTX_ERR_INVALID;  // the angle travels as the first extra
     if (q->mode != TRTX_NMS_GREEDY && q->mode != TRTX_NMS_ONESHOT) return TRTX_ERR_INVALID;
     if (q->max_det <= 0 || q->extra_floats < 0 || q->extra_offset < 0) return TRTX_ERR_INVALID;
     return TRTX_OK;
@@ -842,6 +914,7 @@ TRTX_API int trtx_nms_enqueue(const trtx_nms_params* p, int batch, const float* 
 static int yolo_nms_tiles(const trtx_yolo_params* p, const trtx_nms_params* q, int batch, const YoloArgs& ya,
                           const YoloLayout& L, float* compact_out_dev, int32_t* keep_index_dev, void* workspace_dev,
                           cudaStream_t st) {
+    if (q->box_format == TRTX_BOX_OBB) return TRTX_ERR_UNSUPPORTED;  // the tile records carry no angle: use the plugin-row source
     NmsArgs a{};
     a.from_tiles = 1;
     a.tiles_per_image = L.tiles_per_image;

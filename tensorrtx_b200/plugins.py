@@ -317,7 +317,7 @@ def nms_params(box_format=L.BOX_LTRB, mode=L.NMS_GREEDY, conf_thresh=0.5, nms_th
     q.conf_thresh, q.nms_thresh = conf_thresh, nms_thresh
     q.max_det = max_det
     q.class_aware = int(class_aware)
-    q.tie_break_x0 = int(box_format == L.BOX_LTRB if tie_break_x0 is None else tie_break_x0)
+    q.tie_break_x0 = int(box_format in (L.BOX_LTRB, L.BOX_OBB) if tie_break_x0 is None else tie_break_x0)  # v8 cmp, postprocess.cpp:87-92
     q.extra_floats, q.extra_offset = extra_floats, extra_offset
     return q
 
@@ -341,6 +341,15 @@ def batch_nms(output: torch.Tensor, batch_size: int, output_size: int, conf_thre
                                  _ptr(idx) if idx is not None else None, _ptr(ws), ws_bytes, _stream(stream)),
             "trtx_nms_enqueue")
     return (out, idx) if return_index else out
+
+
+def batch_nms_obb(output: torch.Tensor, batch_size: int, output_size: int, conf_thresh: float, nms_thresh: float = 0.5,
+                  max_det: int | None = None, mode: int = L.NMS_GREEDY, return_index: bool = False, stream=None):
+    """GPU drop-in for batch_nms_obb() (yolov8/src/postprocess.cpp:387-393; mode=NMS_ONESHOT: cuda_decode_obb +
+    cuda_nms_obb, postprocess.cu:7-40,147-193): oriented boxes, ProbIoU.  Returns [batch, 1 + max_det*8] rows
+    (cx, cy, w, h, conf, cls, keep, angle) -- the 8-float element decode_kernel_obb writes."""
+    return batch_nms(output, batch_size, output_size, conf_thresh, nms_thresh, box_format=L.BOX_OBB, det_floats=90,
+                     max_det=max_det, mode=mode, extra_floats=1, extra_offset=89, return_index=return_index, stream=stream)
 
 
 class FusedYoloDecodeNms:

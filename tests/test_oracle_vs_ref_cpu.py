@@ -40,6 +40,25 @@ def test_v8_nms_equals_reference(oracle, seed):
         assert np.array_equal(mine, ref)  # same rows, same order (class asc, conf desc), bit for bit
 
 
+def _obb_plugin_rows(oracle, seed, B=2):
+    heads = synth.yolov8_heads(B, seed=seed, nc=15, extra=1, n_obj=40)
+    out, _ = oracle.yolov8_decode(heads, nc=15, is_obb=True)
+    return out
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_v8_nms_obb_equals_reference(oracle, seed):
+    """nms_obb + probiou (mixed float/double C++ promotions): identical rows in identical order."""
+    lib = _load("libref_yolov8_host.so")
+    out = _obb_plugin_rows(oracle, 130 + seed)
+    for b in range(out.shape[0]):
+        for thr in (0.5, 0.2):
+            mine, _ = oracle.nms(3, out[b], 1000, 90, 0.3, thr)
+            ref = _ref_nms(lib.ref_v8_nms_obb, out[b], 90, 0.3, thr)
+            assert len(ref) > 10 and len(ref) < int(out[b, 0])
+            assert np.array_equal(mine, ref)
+
+
 def test_v8_nms_ties_broken_by_bbox0_like_reference(oracle):
     lib = _load("libref_yolov8_host.so")
     rng = np.random.default_rng(1)

@@ -268,6 +268,52 @@ def test_nms_oneshot_mode(oracle, dev):
     assert kept_gpu == kept_ref
 
 
+def _obb_rows(oracle, seed, B):
+    heads = synth.yolov8_heads(B, seed=seed, nc=15, extra=1, n_obj=40)
+    out, _ = oracle.yolov8_decode(heads, nc=15, is_obb=True)
+    return out
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.2])
+def test_batch_nms_obb_matches_reference_nms_obb(oracle, dev, thr):
+    """Oriented boxes, greedy: nms_obb + probiou (yolov8/src/postprocess.cpp:303-385); the oracle is pinned bit for bit
+    to the reference's own host code (tests/test_oracle_vs_ref_cpu.py::test_v8_nms_obb_equals_reference)."""
+    B = 3
+    ref = _obb_rows(oracle, 140, B)
+    comp, idx = P.batch_nms_obb(torch.from_numpy(ref).to(dev), B, ref.shape[1], 0.3, thr, return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        res, src = oracle.nms(3, ref[b], 1000, 90, 0.3, thr)
+        n = int(comp[b, 0])
+        assert n == len(res) and 10 < n < int(ref[b, 0])
+        assert np.array_equal(idx[b, :n], src)            # identical kept rows, identical (class, conf) order
+        rows = comp[b, 1:1 + n * 8].reshape(n, 8)
+        assert np.array_equal(rows[:, :6], res[:, :6])    # cx, cy, w, h, conf, cls: copies
+        assert np.array_equal(rows[:, 7], res[:, 89])     # the angle rides along as the 8th float
+        assert np.all(rows[:, 6] == 1) and np.all(comp[b, 1 + n * 8:] == 0)
+
+
+def test_nms_obb_oneshot_mode(oracle, dev):
+    """decode_kernel_obb + nms_kernel_obb semantics (postprocess.cu:7-40, 113-166) with 8-float elements.  (The
+    reference strides its 8-float rows by bbox_element = 7, so its own GPU path lets neighbouring rows overwrite each
+    other -- DESIGN.md section 2; the oracle restates the intended layout.)"""
+    ref = _obb_rows(oracle, 141, 1)
+    comp, idx = P.batch_nms_obb(torch.from_numpy(ref).to(dev), 1, ref.shape[1], 0.3, 0.3, mode=L.NMS_ONESHOT,
+                                return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    exp = oracle.cuda_decode_nms_obb(ref[0], 1000, 90, 0.3, 0.3, 1000)
+    n = int(comp[0, 0])
+    rows = comp[0, 1:1 + n * 8].reshape(n, 8)
+    exp_rows = exp[1:].reshape(1000, 8)
+    exp_valid = {i for i in range(int(exp[0])) if exp_rows[i, 4] > 0}
+    assert set(idx[0, :n].tolist()) == exp_valid and len(exp_valid) > 50
+    kept_gpu = {int(idx[0, i]) for i in range(n) if rows[i, 6] == 1}
+    kept_ref = {i for i in exp_valid if exp_rows[i, 6] == 1}
+    assert kept_gpu == kept_ref and 5 < len(kept_ref) < len(exp_valid)
+    for i in range(n):
+        assert np.array_equal(rows[i, [0, 1, 2, 3, 4, 5, 7]], exp_rows[idx[0, i], [0, 1, 2, 3, 4, 5, 7]])
+
+
 def test_nms_topk_select_when_overflowing(oracle, dev):
     # fused path with > max_out candidates above conf_thresh: the top max_out by conf enter NMS
     B = 1
