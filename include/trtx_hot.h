@@ -226,6 +226,30 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
 /* The reference's d2s matrix (preprocess.cu:98-110): scale, centre, cv::invertAffineTransform. */
 TRTX_API void trtx_letterbox_matrix(int src_w, int src_h, int dst_w, int dst_h, float d2s[6]);
 
+/* =====================================================================================
+ * 6. Instance masks of the segmentation models
+ *    replaces the HOST function process_mask(), yolov8/yolov8_seg.cpp:17-60 and
+ *    yolov5/src/postprocess.cpp:94-125: sigmoid(coeffs . prototypes) inside the detection's
+ *    down-scaled rectangle, then cv::resize (bilinear) to the network input size.
+ * ===================================================================================== */
+typedef struct trtx_mask_params {
+    int32_t variant;      /* TRTX_YOLO_V8: rect from (x, y, w, h) with int() truncation and clamping (yolov8_seg.cpp:17-34);
+                             TRTX_YOLO_V5: rect from (cx, cy, w, h) with round() (yolov5 postprocess.cpp:94-104) */
+    int32_t net_w, net_h; /* kInputW, kInputH: size of the masks written */
+    int32_t mask_w, mask_h; /* prototype resolution; must be net/4 like the reference */
+    int32_t num_coeffs;   /* 32 */
+    int32_t row_floats;   /* floats per detection row of `dets_dev` */
+    int32_t coeff_offset; /* first mask coefficient inside a row (box = floats 0..3) */
+    int32_t max_masks;    /* masks written per image: the first min(count, max_masks) rows */
+} trtx_mask_params;
+
+/* proto_dev: [batch, num_coeffs, mask_h, mask_w] fp32 (the engine's "proto" output);
+ * dets_dev : [batch, 1 + max_rows*row_floats] fp32 = count, rows (e.g. the compact NMS output with
+ *            extra_floats = 32, extra_offset = 6: row_floats = 39, coeff_offset = 7);
+ * masks_dev: [batch, max_masks, net_h, net_w] fp32; slots >= count are left untouched.  One launch. */
+TRTX_API int trtx_process_mask_enqueue(const trtx_mask_params* p, int batch, const float* proto_dev, const float* dets_dev,
+                                       int max_rows, float* masks_dev, trtx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

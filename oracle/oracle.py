@@ -118,6 +118,26 @@ def cuda_decode_nms_obb(plugin_out_img, max_rows, det_floats, conf_thresh, nms_t
     return out
 
 
+def resize_bilinear(src, dh, dw):
+    lib = load()
+    s = np.ascontiguousarray(src, np.float32)
+    dst = np.zeros((dh, dw), np.float32)
+    lib.oracle_resize_bilinear(s.ctypes.data_as(C.c_void_p), s.shape[0], s.shape[1], dst.ctypes.data_as(C.c_void_p), dh, dw)
+    return dst
+
+
+def process_mask(variant, proto, bbox, coeffs, net_w=640, net_h=640):
+    """variant 0 yolov8 / 1 yolov5; proto [nm, mh, mw]; -> mask [net_h, net_w] (process_mask of the seg drivers)."""
+    lib = load()
+    pr = np.ascontiguousarray(proto, np.float32)
+    bb = np.ascontiguousarray(bbox, np.float32)
+    cf = np.ascontiguousarray(coeffs, np.float32)
+    out = np.zeros((net_h, net_w), np.float32)
+    lib.oracle_process_mask(int(variant), pr.ctypes.data_as(C.c_void_p), pr.shape[0], pr.shape[1], pr.shape[2], net_w, net_h,
+                            bb.ctypes.data_as(C.c_void_p), cf.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def letterbox_matrix(sw, sh, dw, dh):
     lib = load()
     m = np.zeros(6, np.float32)

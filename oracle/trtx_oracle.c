@@ -849,3 +849,95 @@ ORACLE_API int oracle_yolov8_decode_nms_image(const float* const* inputs /* per 
                          det_floats, gate, scratch_out, NULL);
     return oracle_nms(0, scratch_out, max_out, det_floats, conf_thresh, nms_thresh, res, NULL);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * process_mask: yolov8/yolov8_seg.cpp:17-60 (variant 0) and yolov5/src/postprocess.cpp:94-125 (variant 1), one
+ * detection.  proto [nm, mh, mw]; bbox/coeffs = Detection.bbox / Detection.mask; out [net_h, net_w].
+ * cv::resize(CV_32FC1, INTER_LINEAR) restated from OpenCV's resize.cpp (fx = (dx+0.5)*scale-0.5, floor, clamp with
+ * zero fraction, horizontal pass then vertical pass in float); checked against cv2 4.13 in tests/test_oracle_cpu.py.
+ * The x/y loops are clamped to the mask (the reference would index out of bounds for a yolov5 box leaving the image).
+ * ------------------------------------------------------------------------------------------ */
+static void resize_tap(int d, double scale, int src, int* s0, float* f) {
+    float fx = (float)(((double)d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    if (sx < 0) {
+        fx = 0.0f;
+        sx = 0;
+    }
+    if (sx >= src - 1) {
+        fx = 0.0f;
+        sx = src - 1;
+    }
+    *s0 = sx;
+    *f = fx;
+}
+ORACLE_API void oracle_resize_bilinear(const float* src, int sh, int sw, float* dst, int dh, int dw) {
+    double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+    for (int y = 0; y < dh; ++y) {
+        int sy;
+        float fy;
+        resize_tap(y, scale_y, sh, &sy, &fy);
+        int sy1 = sy + 1 < sh ? sy + 1 : sh - 1;
+        float b0 = 1.0f - fy, b1 = fy;
+        for (int x = 0; x < dw; ++x) {
+            int sx;
+            float fx;
+            resize_tap(x, scale_x, sw, &sx, &fx);
+            int sx1 = sx + 1 < sw ? sx + 1 : sw - 1;
+            float a0 = 1.0f - fx, a1 = fx;
+            float h0 = src[(size_t)sy * sw + sx] * a0 + src[(size_t)sy * sw + sx1] * a1;
+            float h1 = src[(size_t)sy1 * sw + sx] * a0 + src[(size_t)sy1 * sw + sx1] * a1;
+            dst[(size_t)y * dw + x] = h0 * b0 + h1 * b1;
+        }
+    }
+}
+ORACLE_API void oracle_process_mask(int variant, const float* proto, int nm, int mh, int mw, int net_w, int net_h,
+                                    const float* bbox, const float* coeffs, float* out) {
+    float* m = (float*)calloc((size_t)mh * mw, sizeof(float)); /* cv::Mat::zeros */
+    float left, top, right, bottom;
+    int rx, ry, rw, rh;
+    if (variant == 0) { /* yolov8_seg.cpp:17-34 */
+        left = bbox[0];
+        top = bbox[1];
+        right = bbox[0] + bbox[2];
+        bottom = bbox[1] + bbox[3];
+        left = left < 0 ? 0 : left;
+        top = top < 0 ? 0 : top;
+        right = right > net_w ? net_w : right;
+        bottom = bottom > net_h ? net_h : bottom;
+        left /= 4.0f;
+        top /= 4.0f;
+        right /= 4.0f;
+        bottom /= 4.0f;
+        rx = (int)left;
+        ry = (int)top;
+        rw = (int)(right - left);
+        rh = (int)(bottom - top);
+    } else { /* yolov5/src/postprocess.cpp:94-104 */
+        left = bbox[0] - bbox[2] / 2;
+        top = bbox[1] - bbox[3] / 2;
+        right = bbox[0] + bbox[2] / 2;
+        bottom = bbox[1] + bbox[3] / 2;
+        left /= 4.0f;
+        top /= 4.0f;
+        right /= 4.0f;
+        bottom /= 4.0f;
+        rx = (int)round(left);
+        ry = (int)round(top);
+        rw = (int)round(right - left);
+        rh = (int)round(bottom - top);
+    }
+    size_t plane = (size_t)mh * mw; /* proto_size / 32 */
+    for (int x = rx; x < rx + rw; ++x) {
+        for (int y = ry; y < ry + rh; ++y) {
+            if (x < 0 || x >= mw || y < 0 || y >= mh) continue;
+            float e = 0.0f;
+            for (int j = 0; j < nm; ++j) e += coeffs[j] * proto[(size_t)j * plane + (size_t)y * mw + x];
+            m[(size_t)y * mw + x] = 1.0f / (1.0f + expf(-e));
+        }
+    }
+    oracle_resize_bilinear(m, mh, mw, out, net_h, net_w);
+    free(m);
+}
+

@@ -74,6 +74,11 @@ class ImageDesc(C.Structure):
     ]
 
 
+class MaskParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("variant", "net_w", "net_h", "mask_w", "mask_h", "num_coeffs", "row_floats",
+                                         "coeff_offset", "max_masks")]
+
+
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtrtx_hot.so"
 
 # every symbol include/trtx_hot.h declares: (name, restype, argtypes)
@@ -98,6 +103,7 @@ SYMBOLS = {
     "trtx_predictor_decode": (C.c_int64, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), _vp, _sz, _vp]),
     "trtx_batched_nms": (C.c_int64, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _sz, _vp]),
     "trtx_preprocess_batch_enqueue": (_i, [C.POINTER(ImageDesc), _i, _vp, _i, _i, _i, _vp]),
+    "trtx_process_mask_enqueue": (_i, [C.POINTER(MaskParams), _i, _vp, _vp, _i, _vp, _vp]),
     "trtx_letterbox_matrix": (None, [_i, _i, _i, _i, C.POINTER(C.c_float)]),
 }
 # tuning knob exported for the bench sweep; not part of the drop-in ABI

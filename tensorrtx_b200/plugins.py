@@ -352,6 +352,21 @@ def batch_nms_obb(output: torch.Tensor, batch_size: int, output_size: int, conf_
                      max_det=max_det, mode=mode, extra_floats=1, extra_offset=89, return_index=return_index, stream=stream)
 
 
+def process_mask(proto: torch.Tensor, dets: torch.Tensor, max_rows: int, row_floats: int = 39, coeff_offset: int = 7,
+                 max_masks: int = 100, net_w: int = 640, net_h: int = 640, variant: int = L.YOLO_V8, out=None, stream=None):
+    """GPU drop-in for process_mask() (yolov8/yolov8_seg.cpp:36-60, yolov5/src/postprocess.cpp:106-125) for the whole
+    batch: proto [B, 32, net_h/4, net_w/4]; dets [B, 1 + max_rows*row_floats] (count, rows; e.g. batch_nms(...,
+    extra_floats=32, extra_offset=6) output) -> masks [B, max_masks, net_h, net_w]; slots >= count are not written."""
+    lib = L.load()
+    B, nm, mh, mw = proto.shape
+    q = L.MaskParams(variant, net_w, net_h, mw, mh, nm, row_floats, coeff_offset, max_masks)
+    if out is None:
+        out = torch.zeros((B, max_masks, net_h, net_w), dtype=torch.float32, device=proto.device)
+    L.check(lib.trtx_process_mask_enqueue(C.byref(q), B, _ptr(proto), _ptr(dets), max_rows, _ptr(out), _stream(stream)),
+            "trtx_process_mask_enqueue")
+    return out
+
+
 class FusedYoloDecodeNms:
     """YoloLayer inputs -> compact detections in two launches (scan + NMS), no plugin-format round trip.
     Owns its workspace/output buffers (allocated once; enqueue itself allocates nothing)."""

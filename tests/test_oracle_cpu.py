@@ -163,3 +163,49 @@ def test_rpn_decode_topn_and_clip(oracle):
         assert np.array_equal(os_[b][valid], flat[order][valid])
         assert ob[b][:, 0].min() >= 0 and ob[b][:, 2].max() <= 192 and ob[b][:, 3].max() <= 160
         assert np.all(np.diff(flat[order]) <= 0)
+
+
+def test_resize_bilinear_equals_cv2(oracle):
+    """cv::resize(CV_32FC1, INTER_LINEAR) as process_mask uses it (160x160 -> 640x640, yolov8_seg.cpp:55): OpenCV's SIMD
+    build may fuse the multiply-adds, so <= 1 ulp of a value in [0, 1]."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for (sh, sw, dh, dw) in ((160, 160, 640, 640), (96, 160, 384, 640), (40, 24, 160, 96)):
+        src = rng.random((sh, sw), dtype=np.float32)
+        src[rng.random((sh, sw)) < 0.5] = 0.0          # masks are zero outside the box
+        ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        got = oracle.resize_bilinear(src, dh, dw)
+        assert np.abs(got - ref).max() <= 1.2e-7
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_process_mask_against_numpy_and_cv2(oracle, variant):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(6 + variant)
+    proto = rng.standard_normal((32, 160, 160)).astype(np.float32)
+    for bbox in ([100.0, 60.0, 200.0, 120.0], [-30.0, 500.0, 180.0, 300.0], [620.0, 10.0, 5.0, 7.0], [300.0, 300.0, 0.5, 0.5]):
+        coeffs = rng.standard_normal(32).astype(np.float32) * 0.5
+        got = oracle.process_mask(variant, proto, bbox, coeffs)
+        b = np.asarray(bbox, np.float32)
+        if variant == 0:   # yolov8_seg.cpp:17-34: x, y, w, h; clamp; /4; int()
+            l, t, r, bt = b[0], b[1], b[0] + b[2], b[1] + b[3]
+            l, t, r, bt = max(l, np.float32(0)), max(t, np.float32(0)), min(r, np.float32(640)), min(bt, np.float32(640))
+            l, t, r, bt = (np.float32(v) / np.float32(4) for v in (l, t, r, bt))
+            rx, ry, rw, rh = int(l), int(t), int(r - l), int(bt - t)
+        else:              # yolov5 postprocess.cpp:94-104: cx, cy, w, h; /4; round()
+            l, t, r, bt = b[0] - b[2] / 2, b[1] - b[3] / 2, b[0] + b[2] / 2, b[1] + b[3] / 2
+            l, t, r, bt = (np.float32(v) / np.float32(4) for v in (l, t, r, bt))
+            rnd = lambda v: int(np.floor(abs(v) + 0.5) * np.sign(v))  # C round(): half away from zero
+            rx, ry, rw, rh = rnd(l), rnd(t), rnd(r - l), rnd(bt - t)
+        m = np.zeros((160, 160), np.float32)
+        xs, ys = range(max(rx, 0), min(rx + rw, 160)), range(max(ry, 0), min(ry + rh, 160))
+        for y in ys:
+            for x in xs:
+                e = np.float32(0)
+                for j in range(32):
+                    e = np.float32(e + np.float32(coeffs[j] * proto[j, y, x]))
+                m[y, x] = np.float32(1) / (np.float32(1) + np.exp(-e, dtype=np.float32))
+        ref = cv2.resize(m, (640, 640), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(got - ref).max() <= 3e-7
+        assert (got > 0).any() == (len(xs) > 0 and len(ys) > 0)
+

@@ -198,3 +198,38 @@ def test_pipeline_e2e_matches_oracle(oracle, dev):
     g.replay()
     torch.cuda.synchronize()
     assert np.array_equal(pipe.out_host.numpy(), first)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_process_mask_matches_oracle(oracle, dev, variant):
+    """process_mask of the seg drivers (host code in the reference) as one fused GPU launch for the batch."""
+    rng = np.random.default_rng(60 + variant)
+    B, K, M, R = 3, 50, 12, 39
+    proto = rng.standard_normal((B, 32, 160, 160)).astype(np.float32)
+    dets = np.zeros((B, 1 + K * R), np.float32)
+    counts = [12, 0, 5]
+    for b in range(B):
+        dets[b, 0] = counts[b]
+        rows = dets[b, 1:].reshape(K, R)
+        for i in range(counts[b]):
+            if variant == 0:
+                rows[i, :4] = [rng.uniform(-40, 600), rng.uniform(-40, 600), rng.uniform(1, 300), rng.uniform(1, 300)]
+            else:
+                rows[i, :4] = [rng.uniform(20, 620), rng.uniform(20, 620), rng.uniform(1, 300), rng.uniform(1, 300)]
+            rows[i, 4:7] = [0.9, 3.0, 1.0]
+            rows[i, 7:39] = rng.standard_normal(32) * 0.5
+    sentinel = -7.0
+    out = torch.full((B, M, 640, 640), sentinel, dtype=torch.float32, device=dev)
+    got = P.process_mask(torch.from_numpy(proto).to(dev), torch.from_numpy(dets).to(dev), K, R, 7, M, 640, 640,
+                         variant=variant, out=out)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    for b in range(B):
+        rows = dets[b, 1:].reshape(K, R)
+        n = min(counts[b], M)
+        for i in range(n):
+            ref = oracle.process_mask(variant, proto[b], rows[i, :4], rows[i, 7:39])
+            assert np.abs(got[b, i] - ref).max() <= 2e-6   # CUDA expf vs glibc expf inside the sigmoid
+            assert (got[b, i] > 0).sum() == (ref > 0).sum()
+        assert np.all(got[b, n:] == sentinel)              # slots past the image's detections are not written
+
