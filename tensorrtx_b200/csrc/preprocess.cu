@@ -51,12 +51,21 @@ __device__ __forceinline__ float div255(float x) {
 //   * the bilinear sum is written as the reference writes it and left to nvcc's default FMA contraction, exactly
 //     like the reference's own build: the output is BIT-IDENTICAL to the reference kernel's
 //     (tests/test_vs_reference_gpu.py::test_preprocess_vs_reference_kernel).
-static int g_rows_per_thread = 4;  // tuning knob 6 (4 or 8)
-void preprocess_set_rows(int r) { g_rows_per_thread = r == 8 ? 8 : 4; }
+void preprocess_set_rows(int) {}  // tuning knob 6: retired (strip height and conversion mix are fixed, see below)
 
-template <typename OutT, int R>
-__global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
+// u8 -> f32 without the conversion (XU) pipe: for 0 <= i < 2^23, 2^23 + i is exactly representable with i in the
+// mantissa, so OR-ing i into the bits of 2^23 and subtracting 2^23 gives float(i) exactly (two full-rate instructions).
+// The fast path converts every other sample this way so that neither the XU pipe nor the issue slots saturate.
+__device__ __forceinline__ float u8_to_float_alu(uint32_t i) { return __uint_as_float(0x4B000000u | i) - 8388608.0f; }
+
+constexpr int kRowsPerThread = 4;  // 8-row strips measured slower (profiles/r01k_lb_probe.log)
+
+// __launch_bounds__(256, 8): 32 registers -> 64 resident warps per SM.  The kernel is latency-bound once the instruction
+// count is down (no pipe above 60 %), and occupancy is what hides it: 59.4 us at 60 registers, 53.7 at 40, 51.9 at 32.
+template <typename OutT>
+__global__ void __launch_bounds__(256, 8) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
                                                         int first_image) {
+    constexpr int R = kRowsPerThread;
     const int b = blockIdx.z;
     const PreImage& im = a.img[b];
     const int dx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +120,10 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ 
 #pragma unroll
         for (int s = 0; s <= R; ++s) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) t[s][k] = (float)(uint32_t)__ldg(p + k);
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t v = __ldg(p + k);
+                t[s][k] = ((s * 6 + k) & 1) ? u8_to_float_alu(v) : (float)v;
+            }
             p += im.pitch;
         }
 #pragma unroll
@@ -224,20 +236,13 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
             a.img[i].pitch = d.pitch;
             trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, a.img[i].m);
         }
-        const int R = g_rows_per_thread;
+        constexpr int R = kRowsPerThread;
         dim3 block(128, 2, 1);  // 128 columns x (2 x R) rows per block
         dim3 grid((dst_w + 127) / 128, (dst_h + 2 * R - 1) / (2 * R), n);
-        if (out_dtype == TRTX_F32) {
-            if (R == 8)
-                letterbox_kernel<float, 8><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
-            else
-                letterbox_kernel<float, 4><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
-        } else {
-            if (R == 8)
-                letterbox_kernel<__half, 8><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
-            else
-                letterbox_kernel<__half, 4><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
-        }
+        if (out_dtype == TRTX_F32)
+            letterbox_kernel<float><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
+        else
+            letterbox_kernel<__half><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
         int rc = check_launch();
         if (rc) return rc;
     }
