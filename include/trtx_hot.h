@@ -226,6 +226,19 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
 /* The reference's d2s matrix (preprocess.cu:98-110): scale, centre, cv::invertAffineTransform. */
 TRTX_API void trtx_letterbox_matrix(int src_w, int src_h, int dst_w, int dst_h, float d2s[6]);
 
+/* RoIAlign and MaskRcnnInference: replace roiAlign (rcnn/RoiAlign.cu:150-183) and maskRcnnInference
+ * (rcnn/MaskRcnnInference.cu:35-63); same argument meaning, whole batch in one launch, no cudaDeviceSynchronize().
+ * rois_dev [batch, num_proposals, 4] x1,y1,x2,y2; features_dev [batch, out_channels, feature_h, feature_w];
+ * out_dev [batch, num_proposals, out_channels, pooler_resolution, pooler_resolution].  sampling_ratio <= 0: adaptive. */
+TRTX_API int trtx_roi_align(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
+                            float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
+                            int feature_w, trtx_stream_t stream);
+/* indices_dev [batch, detections_per_im] class index as float; masks_dev [batch, detections_per_im, num_classes, S, S];
+ * out_dev [batch, detections_per_im, S, S] = sigmoid of the predicted class' mask (rows with an index outside
+ * [0, num_classes) are left untouched, as in the reference). */
+TRTX_API int trtx_mask_rcnn_inference(int batch, const float* indices_dev, const float* masks_dev, float* out_dev,
+                                      int detections_per_im, int output_size, int num_classes, trtx_stream_t stream);
+
 /* =====================================================================================
  * 6. Instance masks of the segmentation models
  *    replaces the HOST function process_mask(), yolov8/yolov8_seg.cpp:17-60 and

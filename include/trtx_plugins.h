@@ -531,6 +531,95 @@ class RpnNmsPlugin : public RcnnPluginBase {
     size_t pre_;
 };
 
+// rcnn/RoiAlignPlugin.h:27-170
+class RoiAlignPlugin : public RcnnPluginBase {
+   public:
+    RoiAlignPlugin(int pooler_resolution, float spatial_scale, int sampling_ratio, int num_proposals, int out_channels,
+                   int feature_h = 0, int feature_w = 0)
+        : pooler_(pooler_resolution), scale_(spatial_scale), sampling_(sampling_ratio), proposals_(num_proposals),
+          channels_(out_channels), fh_(feature_h), fw_(feature_w) {}
+    RoiAlignPlugin(const void* data, size_t) {  // RoiAlignPlugin.h:37-46
+        const char* d = static_cast<const char*>(data);
+        detail::read(d, pooler_);
+        detail::read(d, scale_);
+        detail::read(d, sampling_);
+        detail::read(d, proposals_);
+        detail::read(d, channels_);
+        detail::read(d, fh_);
+        detail::read(d, fw_);
+    }
+    const char* getPluginType() const TRTX_NOEXCEPT override { return "RoiAlign"; }
+    int getNbOutputs() const TRTX_NOEXCEPT override { return 1; }
+    nvinfer1::Dims getOutputDimensions(int, const nvinfer1::Dims*, int) TRTX_NOEXCEPT override {
+        return nvinfer1::Dims4(proposals_, channels_, pooler_, pooler_);
+    }
+    size_t getWorkspaceSize(int) const TRTX_NOEXCEPT override { return 0; }
+    int enqueue(int batchSize, const void* const* inputs, void* TRTX_CONST_ENQUEUE* outputs, void*, cudaStream_t stream) TRTX_NOEXCEPT override {
+        return trtx_roi_align(batchSize, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
+                              static_cast<float*>(outputs[0]), pooler_, scale_, sampling_, proposals_, channels_, fh_, fw_, stream);
+    }
+    size_t getSerializationSize() const TRTX_NOEXCEPT override { return 6 * sizeof(int) + sizeof(float); }
+    void serialize(void* buffer) const TRTX_NOEXCEPT override {
+        char* d = static_cast<char*>(buffer);
+        detail::write(d, pooler_);
+        detail::write(d, scale_);
+        detail::write(d, sampling_);
+        detail::write(d, proposals_);
+        detail::write(d, channels_);
+        detail::write(d, fh_);
+        detail::write(d, fw_);
+    }
+    void configurePlugin(const nvinfer1::Dims* inputDims, int, const nvinfer1::Dims*, int, const nvinfer1::DataType*, const nvinfer1::DataType*,
+                         const bool*, const bool*, nvinfer1::PluginFormat, int) TRTX_NOEXCEPT override {
+        fh_ = inputDims[1].d[1];  // RoiAlignPlugin.h:151-152
+        fw_ = inputDims[1].d[2];
+    }
+    nvinfer1::IPluginV2Ext* clone() const TRTX_NOEXCEPT override {
+        return new RoiAlignPlugin(pooler_, scale_, sampling_, proposals_, channels_, fh_, fw_);
+    }
+
+   private:
+    int pooler_;
+    float scale_;
+    int sampling_, proposals_, channels_, fh_, fw_;
+};
+
+// rcnn/MaskRcnnInferencePlugin.h:27-140
+class MaskRcnnInferencePlugin : public RcnnPluginBase {
+   public:
+    MaskRcnnInferencePlugin(int detections_per_im, int output_size, int num_classes = 1)
+        : dets_(detections_per_im), size_(output_size), classes_(num_classes) {}
+    MaskRcnnInferencePlugin(const void* data, size_t) {  // MaskRcnnInferencePlugin.h:32-37
+        const char* d = static_cast<const char*>(data);
+        detail::read(d, dets_);
+        detail::read(d, size_);
+        detail::read(d, classes_);
+    }
+    const char* getPluginType() const TRTX_NOEXCEPT override { return "MaskRcnnInference"; }
+    int getNbOutputs() const TRTX_NOEXCEPT override { return 1; }
+    nvinfer1::Dims getOutputDimensions(int, const nvinfer1::Dims*, int) TRTX_NOEXCEPT override { return nvinfer1::Dims4(dets_, 1, size_, size_); }
+    size_t getWorkspaceSize(int) const TRTX_NOEXCEPT override { return 0; }
+    int enqueue(int batchSize, const void* const* inputs, void* TRTX_CONST_ENQUEUE* outputs, void*, cudaStream_t stream) TRTX_NOEXCEPT override {
+        return trtx_mask_rcnn_inference(batchSize, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
+                                        static_cast<float*>(outputs[0]), dets_, size_, classes_, stream);
+    }
+    size_t getSerializationSize() const TRTX_NOEXCEPT override { return 3 * sizeof(int); }
+    void serialize(void* buffer) const TRTX_NOEXCEPT override {
+        char* d = static_cast<char*>(buffer);
+        detail::write(d, dets_);
+        detail::write(d, size_);
+        detail::write(d, classes_);
+    }
+    void configurePlugin(const nvinfer1::Dims* inputDims, int, const nvinfer1::Dims*, int, const nvinfer1::DataType*, const nvinfer1::DataType*,
+                         const bool*, const bool*, nvinfer1::PluginFormat, int) TRTX_NOEXCEPT override {
+        classes_ = inputDims[1].d[1];  // MaskRcnnInferencePlugin.h:119
+    }
+    nvinfer1::IPluginV2Ext* clone() const TRTX_NOEXCEPT override { return new MaskRcnnInferencePlugin(dets_, size_, classes_); }
+
+   private:
+    int dets_, size_, classes_;
+};
+
 class PredictorDecodePlugin : public RcnnPluginBase {
    public:
     PredictorDecodePlugin(unsigned num_boxes, unsigned image_height, unsigned image_width, const std::vector<float>& w)
@@ -649,6 +738,8 @@ struct RpnDecodePluginCreator : RcnnCreator<RpnDecodePlugin> { RpnDecodePluginCr
 struct RpnNmsPluginCreator : RcnnCreator<RpnNmsPlugin> { RpnNmsPluginCreator() : RcnnCreator("RpnNms") {} };
 struct PredictorDecodePluginCreator : RcnnCreator<PredictorDecodePlugin> { PredictorDecodePluginCreator() : RcnnCreator("PredictorDecode") {} };
 struct BatchedNmsPluginCreator : RcnnCreator<BatchedNmsPlugin> { BatchedNmsPluginCreator() : RcnnCreator("BatchedNms") {} };
+struct RoiAlignPluginCreator : RcnnCreator<RoiAlignPlugin> { RoiAlignPluginCreator() : RcnnCreator("RoiAlign") {} };
+struct MaskRcnnInferencePluginCreator : RcnnCreator<MaskRcnnInferencePlugin> { MaskRcnnInferencePluginCreator() : RcnnCreator("MaskRcnnInference") {} };
 
 }  // namespace trtx
 
@@ -664,6 +755,8 @@ REGISTER_TENSORRT_PLUGIN(RpnDecodePluginCreator);
 REGISTER_TENSORRT_PLUGIN(RpnNmsPluginCreator);
 REGISTER_TENSORRT_PLUGIN(PredictorDecodePluginCreator);
 REGISTER_TENSORRT_PLUGIN(BatchedNmsPluginCreator);
+REGISTER_TENSORRT_PLUGIN(RoiAlignPluginCreator);
+REGISTER_TENSORRT_PLUGIN(MaskRcnnInferencePluginCreator);
 }  // namespace trtx
 #endif
 

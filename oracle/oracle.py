@@ -138,6 +138,29 @@ def process_mask(variant, proto, bbox, coeffs, net_w=640, net_h=640):
     return out
 
 
+def roi_align(rois, feat, P, spatial_scale, sampling_ratio):
+    """One image: rois [N,4], feat [C,H,W] -> [N,C,P,P] (RoIAlignForward, rcnn/RoiAlign.cu)."""
+    lib = load()
+    r = np.ascontiguousarray(rois, np.float32)
+    f = np.ascontiguousarray(feat, np.float32)
+    out = np.zeros((r.shape[0], f.shape[0], P, P), np.float32)
+    lib.oracle_roi_align(r.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                         r.shape[0], f.shape[0], f.shape[1], f.shape[2], P, C.c_float(spatial_scale), int(sampling_ratio))
+    return out
+
+
+def mask_rcnn_inference(indices, masks, out=None):
+    """One image: indices [D] (float class ids), masks [D,nc,S,S] -> [D,S,S]."""
+    lib = load()
+    ind = np.ascontiguousarray(indices, np.float32)
+    m = np.ascontiguousarray(masks, np.float32)
+    D, nc, S, _ = m.shape
+    out = np.zeros((D, S, S), np.float32) if out is None else np.ascontiguousarray(out, np.float32)
+    lib.oracle_mask_rcnn_inference(ind.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p),
+                                   out.ctypes.data_as(C.c_void_p), D, S, nc)
+    return out
+
+
 def letterbox_matrix(sw, sh, dw, dh):
     lib = load()
     m = np.zeros(6, np.float32)

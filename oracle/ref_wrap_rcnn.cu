@@ -6,7 +6,9 @@
 #include <vector>
 
 #include "BatchedNmsPlugin.h"
+#include "MaskRcnnInferencePlugin.h"
 #include "PredictorDecodePlugin.h"
+#include "RoiAlignPlugin.h"
 #include "RpnDecodePlugin.h"
 #include "RpnNmsPlugin.h"
 
@@ -69,6 +71,28 @@ REF_API int ref_batched_nms(int method, int batch, const float* scores_dev, cons
     int rc = nvinfer1::batchedNms(method, batch, ins, outs, count, dets, thresh, w, ws, 0);
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(w);
+    return rc != 0 ? rc : (int)e;
+}
+
+// roiAlign (rcnn/RoiAlign.cu:150-183: one launch + cudaDeviceSynchronize per image)
+REF_API int ref_roi_align(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
+                          float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
+                          int feature_w) {
+    const void* ins[2] = {rois_dev, features_dev};
+    void* outs[1] = {out_dev};
+    int rc = nvinfer1::roiAlign(batch, ins, outs, pooler_resolution, spatial_scale, sampling_ratio, num_proposals, out_channels,
+                                feature_h, feature_w, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    return rc != 0 ? rc : (int)e;
+}
+
+// maskRcnnInference (rcnn/MaskRcnnInference.cu:35-63)
+REF_API int ref_mask_rcnn_inference(int batch, const float* indices_dev, const float* masks_dev, float* out_dev,
+                                    int detections_per_im, int output_size, int num_classes) {
+    const void* ins[2] = {indices_dev, masks_dev};
+    void* outs[1] = {out_dev};
+    int rc = nvinfer1::maskRcnnInference(batch, ins, outs, detections_per_im, output_size, num_classes, 0);
+    cudaError_t e = cudaDeviceSynchronize();
     return rc != 0 ? rc : (int)e;
 }
 }

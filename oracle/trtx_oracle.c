@@ -941,3 +941,72 @@ ORACLE_API void oracle_process_mask(int variant, const float* proto, int nm, int
     free(m);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * RoIAlign: RoIAlignForward + bilinear_interpolate, rcnn/RoiAlign.cu:29-149 (one image).
+ * rois [N,4] x1,y1,x2,y2; feat [C,H,W]; out [N,C,P,P].  T = float; the double literals of the reference
+ * (-1.0, `1. - ly`) are kept.
+ * ------------------------------------------------------------------------------------------ */
+static float roi_bilinear(const float* bottom, int height, int width, float y, float x) {
+    if (y < -1.0 || y > height || x < -1.0 || x > width) return 0;
+    if (y <= 0) y = 0;
+    if (x <= 0) x = 0;
+    int y_low = (int)y, x_low = (int)x, y_high, x_high;
+    if (y_low >= height - 1) {
+        y_high = y_low = height - 1;
+        y = (float)y_low;
+    } else {
+        y_high = y_low + 1;
+    }
+    if (x_low >= width - 1) {
+        x_high = x_low = width - 1;
+        x = (float)x_low;
+    } else {
+        x_high = x_low + 1;
+    }
+    float ly = y - y_low, lx = x - x_low;
+    float hy = (float)(1. - ly), hx = (float)(1. - lx);
+    float v1 = bottom[y_low * width + x_low], v2 = bottom[y_low * width + x_high];
+    float v3 = bottom[y_high * width + x_low], v4 = bottom[y_high * width + x_high];
+    float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+    return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+}
+ORACLE_API void oracle_roi_align(const float* rois, const float* feat, float* out, int N, int C, int H, int W, int P,
+                                 float spatial_scale, int sampling_ratio) {
+    for (int n = 0; n < N; ++n) {
+        const float* r = rois + 4 * n;
+        float roi_offset = 0.5f;
+        float roi_start_w = r[0] * spatial_scale - roi_offset, roi_start_h = r[1] * spatial_scale - roi_offset;
+        float roi_end_w = r[2] * spatial_scale - roi_offset, roi_end_h = r[3] * spatial_scale - roi_offset;
+        float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+        float bin_size_h = roi_height / (float)P, bin_size_w = roi_width / (float)P;
+        int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_height / P);
+        int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_width / P);
+        const float count = (float)(gh * gw);
+        for (int c = 0; c < C; ++c) {
+            const float* fm = feat + (size_t)c * H * W;
+            for (int ph = 0; ph < P; ++ph)
+                for (int pw = 0; pw < P; ++pw) {
+                    float acc = 0.f;
+                    for (int iy = 0; iy < gh; iy++) {
+                        const float y = roi_start_h + ph * bin_size_h + (float)(iy + .5f) * bin_size_h / (float)gh;
+                        for (int ix = 0; ix < gw; ix++) {
+                            const float x = roi_start_w + pw * bin_size_w + (float)(ix + .5f) * bin_size_w / (float)gw;
+                            acc += roi_bilinear(fm, H, W, y, x);
+                        }
+                    }
+                    acc /= count;
+                    out[(((size_t)n * C + c) * P + ph) * P + pw] = acc;
+                }
+        }
+    }
+}
+/* MaskRcnnInferenceKernel, rcnn/MaskRcnnInference.cu:8-33 (one image); rows whose class index is out of range stay
+ * as they are in `out`. */
+ORACLE_API void oracle_mask_rcnn_inference(const float* indices, const float* masks, float* out, int D, int S, int nc) {
+    for (int d = 0; d < D; ++d) {
+        int cls = (int)indices[d];
+        if (cls < 0 || cls >= nc) continue;
+        for (int i = 0; i < S * S; ++i) out[(size_t)d * S * S + i] = logist(masks[((size_t)d * nc + cls) * S * S + i]);
+    }
+}
+

@@ -586,6 +586,61 @@ class BatchedNmsPlugin:
 # --------------------------------------------------------------------------------------------------
 # Pre-process (preprocess.h)
 # --------------------------------------------------------------------------------------------------
+class RoiAlignPlugin:
+    """rcnn/RoiAlignPlugin.h:27-170 (plugin "RoiAlign"): inputs proposals [B,N,4], features [B,C,H,W] ->
+    [B, N, C, P, P].  No workspace, no device synchronisation (the reference syncs after every image)."""
+
+    def __init__(self, pooler_resolution: int, spatial_scale: float, sampling_ratio: int, num_proposals: int,
+                 out_channels: int, feature_h: int = 0, feature_w: int = 0):
+        self._lib = L.load()
+        self._pooler_resolution, self._spatial_scale = int(pooler_resolution), float(spatial_scale)
+        self._sampling_ratio, self._num_proposals, self._out_channels = int(sampling_ratio), int(num_proposals), int(out_channels)
+        self._feature_h, self._feature_w = int(feature_h), int(feature_w)
+
+    def configurePlugin(self, inputDims):  # RoiAlignPlugin.h:140-153
+        self._feature_h, self._feature_w = int(inputDims[1][1]), int(inputDims[1][2])
+
+    def getNbOutputs(self) -> int:
+        return 1
+
+    def getOutputDimensions(self, index=0):
+        return (self._num_proposals, self._out_channels, self._pooler_resolution, self._pooler_resolution)
+
+    def getWorkspaceSize(self, maxBatchSize: int) -> int:
+        return 0
+
+    def enqueue(self, batchSize, inputs, outputs, workspace=None, stream=None) -> int:
+        return int(self._lib.trtx_roi_align(batchSize, _ptr(inputs[0]), _ptr(inputs[1]), _ptr(outputs[0]), self._pooler_resolution,
+                                            self._spatial_scale, self._sampling_ratio, self._num_proposals, self._out_channels,
+                                            self._feature_h, self._feature_w, _stream(stream)))
+
+
+class MaskRcnnInferencePlugin:
+    """rcnn/MaskRcnnInferencePlugin.h:27-140 (plugin "MaskRcnnInference"): indices [B,D] (float class ids),
+    masks [B,D,num_classes,S,S] -> [B,D,1,S,S] = sigmoid of the predicted class' mask."""
+
+    def __init__(self, detections_per_im: int, output_size: int, num_classes: int = 1):
+        self._lib = L.load()
+        self._detections_per_im, self._output_size, self._num_classes = int(detections_per_im), int(output_size), int(num_classes)
+
+    def configurePlugin(self, inputDims):  # MaskRcnnInferencePlugin.h:109-120
+        self._num_classes = int(inputDims[1][1])
+
+    def getNbOutputs(self) -> int:
+        return 1
+
+    def getOutputDimensions(self, index=0):
+        return (self._detections_per_im, 1, self._output_size, self._output_size)
+
+    def getWorkspaceSize(self, maxBatchSize: int) -> int:
+        return 0
+
+    def enqueue(self, batchSize, inputs, outputs, workspace=None, stream=None) -> int:
+        return int(self._lib.trtx_mask_rcnn_inference(batchSize, _ptr(inputs[0]), _ptr(inputs[1]), _ptr(outputs[0]),
+                                                      self._detections_per_im, self._output_size, self._num_classes,
+                                                      _stream(stream)))
+
+
 def cuda_batch_preprocess(img_batch: Sequence[torch.Tensor], dst: torch.Tensor, dst_width: int, dst_height: int,
                           stream=None) -> None:
     """Drop-in for cuda_batch_preprocess (yolov8/src/preprocess.cu:119-127) with DEVICE images:

@@ -209,3 +209,20 @@ def test_process_mask_against_numpy_and_cv2(oracle, variant):
         assert np.abs(got - ref).max() <= 3e-7
         assert (got > 0).any() == (len(xs) > 0 and len(ys) > 0)
 
+
+@pytest.mark.parametrize("sampling", [0, 2])
+def test_roi_align_against_torchvision(oracle, sampling):
+    """RoIAlignForward (rcnn/RoiAlign.cu) is detectron2's aligned ROIAlign: torchvision.ops.roi_align(aligned=True)."""
+    tv = pytest.importorskip("torchvision")
+    import torch
+    rng = np.random.default_rng(9)
+    Cc, H, W, Pp, N = 6, 50, 67, 14, 40
+    feat = rng.standard_normal((Cc, H, W)).astype(np.float32)
+    x1 = rng.uniform(0, 900, N); y1 = rng.uniform(0, 700, N)
+    w = np.exp(rng.uniform(np.log(16), np.log(800), N)); h = np.exp(rng.uniform(np.log(16), np.log(600), N))
+    rois = np.stack([x1, y1, x1 + w, y1 + h], -1).astype(np.float32)
+    got = oracle.roi_align(rois, feat, Pp, 1 / 16, sampling)
+    boxes = torch.cat([torch.zeros(N, 1), torch.from_numpy(rois)], 1)
+    ref = tv.ops.roi_align(torch.from_numpy(feat)[None], boxes, (Pp, Pp), 1 / 16, sampling, aligned=True).numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=3e-5)
+

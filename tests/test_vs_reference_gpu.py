@@ -282,3 +282,59 @@ def test_rcnn_predictor_and_batched_nms_vs_reference_functions(dev):
                 f"ref {q1.flatten()[k].item()}")
         np.testing.assert_allclose(p1.cpu().numpy(), q1.cpu().numpy(), rtol=1e-6, atol=0, err_msg=info)
         assert torch.equal(p2, q2) and torch.equal(p3, q3), info
+
+
+def test_roi_align_and_mask_rcnn_inference_vs_reference_functions(dev, oracle):
+    """roiAlign / maskRcnnInference of rcnn/*.cu (one launch + cudaDeviceSynchronize per image there) vs one launch
+    for the batch here: same CUDA compiler, same expressions -> identical floats."""
+    lib = _load("libref_rcnn.so")
+    rng = np.random.default_rng(470)
+    B, N, Cc, H, W, Pp = 2, 96, 80, 50, 67, 14
+    feat = rng.standard_normal((B, Cc, H, W)).astype(np.float32)
+    x1 = rng.uniform(-40, 1000, (B, N)); y1 = rng.uniform(-40, 760, (B, N))
+    w = np.exp(rng.uniform(np.log(8), np.log(900), (B, N))); h = np.exp(rng.uniform(np.log(8), np.log(700), (B, N)))
+    rois = np.stack([x1, y1, x1 + w, y1 + h], -1).astype(np.float32)
+    rois[0, 0] = [100, 100, 100, 100]        # zero-size proposal: count = 0 -> NaN, like the reference
+    rois[0, 1] = [300, 300, 200, 250]        # negative size
+    rois[1, 0] = [-500, -500, -300, -300]    # entirely outside the feature map
+    xi = rng.uniform(0, 700, N); yi = rng.uniform(0, 500, N)
+    wi = np.exp(rng.uniform(np.log(8), np.log(300), N)); hi = np.exp(rng.uniform(np.log(8), np.log(250), N))
+    rois_in = np.stack([xi, yi, xi + wi, yi + hi], -1).astype(np.float32)
+    fd, rd = torch.from_numpy(feat).to(dev), torch.from_numpy(rois).to(dev)
+    for sampling in (0, 2):
+        ref = torch.zeros((B, N, Cc, Pp, Pp), device=dev)
+        assert lib.ref_roi_align(B, C.c_void_p(rd.data_ptr()), C.c_void_p(fd.data_ptr()), C.c_void_p(ref.data_ptr()), Pp,
+                                 C.c_float(1 / 16), sampling, N, Cc, H, W) == 0
+        got = torch.full((B, N, Cc, Pp, Pp), -3.0, device=dev)
+        plug = P.RoiAlignPlugin(Pp, 1 / 16, sampling, N, Cc)
+        plug.configurePlugin([(N, 4), (Cc, H, W)])
+        assert plug.enqueue(B, [rd, fd], [got]) == 0
+        torch.cuda.synchronize()
+        r, g = ref.cpu().numpy(), got.cpu().numpy()
+        assert np.array_equal(np.isnan(r), np.isnan(g))
+        assert np.array_equal(r[~np.isnan(r)], g[~np.isnan(g)])          # bit-identical
+        # CPU restatement (no FMA contraction) on proposals inside the feature map: at the `x > width -> 0` border of
+        # bilinear_interpolate a 1-ulp difference in a sample coordinate flips a whole tap, which only the same-compiler
+        # comparison above can pin
+        orc = oracle.roi_align(rois_in, feat[1], Pp, 1 / 16, sampling)
+        got_in = torch.empty((1, N, Cc, Pp, Pp), device=dev)
+        assert plug.enqueue(1, [torch.from_numpy(rois_in).to(dev), fd[1:2].contiguous()], [got_in]) == 0
+        np.testing.assert_allclose(got_in[0].cpu().numpy(), orc, rtol=0, atol=2e-5)
+    # MaskRcnnInference
+    D, nc, S = 100, 80, 14
+    masks = rng.standard_normal((B, D, nc, S, S)).astype(np.float32) * 3
+    idx = rng.integers(0, nc, (B, D)).astype(np.float32)
+    idx[0, 5] = -1.0
+    idx[1, 7] = float(nc)                      # out of range: the row is not written
+    md, idd = torch.from_numpy(masks).to(dev), torch.from_numpy(idx).to(dev)
+    ref = torch.full((B, D, S, S), 9.0, device=dev)
+    got = torch.full((B, D, S, S), 9.0, device=dev)
+    assert lib.ref_mask_rcnn_inference(B, C.c_void_p(idd.data_ptr()), C.c_void_p(md.data_ptr()), C.c_void_p(ref.data_ptr()),
+                                       D, S, nc) == 0
+    assert P.MaskRcnnInferencePlugin(D, S, nc).enqueue(B, [idd, md], [got]) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got)
+    assert torch.all(got[0, 5] == 9.0) and torch.all(got[1, 7] == 9.0)
+    exp = oracle.mask_rcnn_inference(idx[1], masks[1], out=np.full((D, S, S), 9.0, np.float32))
+    np.testing.assert_allclose(got[1].cpu().numpy(), exp, rtol=3e-7, atol=1e-7)
+

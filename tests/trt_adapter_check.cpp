@@ -128,6 +128,19 @@ int main(int argc, char** argv) {
     bn.configurePlugin(cd, 3, nullptr, 3, nullptr, nullptr, nullptr, nullptr, PluginFormat::kLINEAR, 8);
     CHECK(bn.getSerializationSize() == 4 + 4 + 4 + sizeof(size_t) && bn.getWorkspaceSize(8) > 0);
     CHECK(getPluginRegistry()->getPluginCreator("BatchedNms", "1") != nullptr && getPluginRegistry()->getPluginCreator("RpnNms", "1") != nullptr);
+    trtx::RoiAlignPlugin ra(14, 1.f / 16, 0, 1000, 1024);
+    Dims rd[2];
+    rd[0].nbDims = 2; rd[0].d[0] = 1000; rd[0].d[1] = 4;
+    rd[1].nbDims = 3; rd[1].d[0] = 1024; rd[1].d[1] = 50; rd[1].d[2] = 67;
+    ra.configurePlugin(rd, 2, nullptr, 1, nullptr, nullptr, nullptr, nullptr, PluginFormat::kLINEAR, 8);
+    std::vector<char> rab(ra.getSerializationSize());
+    ra.serialize(rab.data());
+    trtx::RoiAlignPlugin ra2(rab.data(), rab.size());
+    CHECK(rab.size() == 28 && ra2.getOutputDimensions(0, nullptr, 2).d[3] == 14 && ra2.getWorkspaceSize(8) == 0);
+    CHECK(std::string(ra2.getPluginType()) == "RoiAlign" && getPluginRegistry()->getPluginCreator("RoiAlign", "1") != nullptr);
+    trtx::MaskRcnnInferencePlugin mi(100, 14);
+    CHECK(mi.getSerializationSize() == 12 && mi.getOutputDimensions(0, nullptr, 2).d[0] == 100 &&
+          getPluginRegistry()->getPluginCreator("MaskRcnnInference", "1") != nullptr);
 
     if (gpu) {
         // ---- enqueue through both YOLO adapters on the same synthetic heads; outputs must be identical ----

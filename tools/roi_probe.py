@@ -1,0 +1,45 @@
+"""RoIAlign kernel timing at the Faster R-CNN C4 shapes: N=1000 proposals, C=1024, 50x67 features, 14x14 bins."""
+import json, sys
+from pathlib import Path
+import numpy as np, torch
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from tensorrtx_b200 import plugins as P
+dev = torch.device("cuda", 0)
+rng = np.random.default_rng(0)
+B, N, C, H, W, Pp = 2, 1000, 1024, 50, 67, 14
+feat = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(dev)
+x1 = rng.uniform(0, 900, (B, N)); y1 = rng.uniform(0, 700, (B, N))
+w = np.exp(rng.uniform(np.log(16), np.log(600), (B, N))); h = np.exp(rng.uniform(np.log(16), np.log(500), (B, N)))
+rois = torch.from_numpy(np.stack([x1, y1, x1 + w, y1 + h], -1).astype(np.float32)).to(dev)
+out = torch.empty((B, N, C, Pp, Pp), dtype=torch.float32, device=dev)
+for sampling in (0, 2):
+    plug = P.RoiAlignPlugin(Pp, 1 / 16, sampling, N, C, H, W)
+    for _ in range(2):
+        plug.enqueue(B, [rois, feat], [out])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 5
+    e0.record()
+    for _ in range(K):
+        plug.enqueue(B, [rois, feat], [out])
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / K * 1e3
+    print(json.dumps({"kernel": "roi_align", "sampling_ratio": sampling, "images": B, "us": round(us, 1),
+                      "written_GBps": round(out.numel() * 4 / us / 1e3, 1)}), flush=True)
+
+# the reference's own roiAlign (oracle/_ref/libref_rcnn.so, built from /root/reference/rcnn/RoiAlign.cu) on the same inputs
+import ctypes as C, time
+ref = ROOT / "oracle" / "_ref" / "libref_rcnn.so"
+if ref.exists():
+    lib = C.CDLL(str(ref))
+    for sampling in (0, 2):
+        args = (B, C.c_void_p(rois.data_ptr()), C.c_void_p(feat.data_ptr()), C.c_void_p(out.data_ptr()), Pp, C.c_float(1 / 16),
+                sampling, N, C_ if False else 1024, H, W)
+        lib.ref_roi_align(*args)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lib.ref_roi_align(*args)   # synchronises the device itself (RoiAlign.cu:178)
+        us = (time.perf_counter() - t0) / 3 * 1e6
+        print(json.dumps({"kernel": "reference roiAlign", "sampling_ratio": sampling, "images": B, "us": round(us, 1)}), flush=True)
