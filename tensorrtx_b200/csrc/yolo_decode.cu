@@ -3,9 +3,10 @@
 // Replaces CalDetection/forwardGpu of yolov8/plugin/yololayer.cu:178-316 (anchor-free) and
 // yolov5/plugin/yololayer.cu:161-227 (anchor-based) with
 //   (1) ONE streaming "scan" launch over all strides and images: 128-bit coalesced loads along the
-//       anchor axis, class range sliced across the warps of a CTA, sigmoid evaluated only on
-//       running-max logits above the gate logit (bit-identical result, see scan_classes), warp
-//       ballot/scan compaction into a per-tile slot range (no atomics, deterministic order);
+//       anchor axis, class range sliced across the warps of a CTA, the reference's class loop kept
+//       in the logit domain with ONE sigmoid per surviving anchor (bit-identical result, see
+//       scan_classes / finish_best), warp ballot/scan compaction into a per-tile slot range (no
+//       atomics, deterministic order);
 //   (2) a tiny "pack" launch that turns the per-tile candidates into the reference's plugin
 //       buffer [count, Detection rows] (only used by the drop-in plugin ABI; the fused NMS
 //       kernel in nms.cu consumes the tiles directly).
