@@ -39,7 +39,7 @@ MAX_OUT = 1000
 CONF, IOU = 0.5, 0.45
 ALGO_BYTES_PER_IMAGE = (4 + NC) * sum((NET // s) ** 2 for s in STRIDES) * 4  # 2 822 400 B, SURVEY 8d
 # dram__bytes_read.sum + dram__bytes_write.sum of one yolo_v8_scan_kernel launch at b32 on the dense synthetic heads,
-# from the `ncu --set full` capture summarised in profiles/r01k_scan_ncu.csv (90.30 MB read + 2.5 MB written)
+# from the `ncu --set full` capture summarised in profiles/r01k_full_ncu.csv (90.30 MB read + 2.5 MB written)
 NCU_SCAN_DRAM_BYTES_B32 = 92_800_000
 METRIC = "end_to_end_fps_yolov8n_640_b32 (pre-process + fused decode + NMS); decode+NMS us/frame alongside"
 WORKLOAD = "YOLOv8n 640x640 b32/GPU: letterbox preprocess + YoloLayer decode + NMS, synthetic (SURVEY 8d), fp32 heads"
