@@ -225,6 +225,10 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
                                            int dst_h, int out_dtype, trtx_stream_t stream);
 /* The reference's d2s matrix (preprocess.cu:98-110): scale, centre, cv::invertAffineTransform. */
 TRTX_API void trtx_letterbox_matrix(int src_w, int src_h, int dst_w, int dst_h, float d2s[6]);
+/* get_rect (yolov8/src/postprocess.cpp:6-36, yolov5/src/postprocess.cpp:4-29): maps a detection box from network-input
+ * pixels back to the original image: rect = {x, y, width, height} as cv::Rect.  variant TRTX_YOLO_V8: box l,t,r,b,
+ * result clamped to the image; TRTX_YOLO_V5: box cx,cy,w,h.  Host function (no device work). */
+TRTX_API int trtx_get_rect(int variant, int net_w, int net_h, int img_w, int img_h, const float bbox[4], int rect[4]);
 
 /* RoIAlign and MaskRcnnInference: replace roiAlign (rcnn/RoiAlign.cu:150-183) and maskRcnnInference
  * (rcnn/MaskRcnnInference.cu:35-63); same argument meaning, whole batch in one launch, no cudaDeviceSynchronize().

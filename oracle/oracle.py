@@ -161,6 +161,14 @@ def mask_rcnn_inference(indices, masks, out=None):
     return out
 
 
+def get_rect(variant, img_w, img_h, bbox, net_w=640, net_h=640):
+    lib = load()
+    b = np.ascontiguousarray(bbox, np.float32)
+    r = np.zeros(4, np.int32)
+    lib.oracle_get_rect(int(variant), net_w, net_h, img_w, img_h, b.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p))
+    return r
+
+
 def letterbox_matrix(sw, sh, dw, dh):
     lib = load()
     m = np.zeros(6, np.float32)

@@ -33,4 +33,13 @@ __attribute__((visibility("default"))) int ref_v8_batch_nms(float* output_host, 
     }
     return 0;
 }
+// get_rect (postprocess.cpp:4-36): box in network-input pixels -> cv::Rect in the original image (kInputW x kInputH = 640 x 640)
+__attribute__((visibility("default"))) void ref_v8_get_rect(int img_w, int img_h, float* bbox, int* rect_out) {
+    cv::Mat img(img_h, img_w, CV_8UC3, nullptr);
+    cv::Rect r = get_rect(img, bbox);
+    rect_out[0] = r.x;
+    rect_out[1] = r.y;
+    rect_out[2] = r.width;
+    rect_out[3] = r.height;
+}
 }

@@ -1010,3 +1010,68 @@ ORACLE_API void oracle_mask_rcnn_inference(const float* indices, const float* ma
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * get_rect: yolov8/src/postprocess.cpp:6-36 (variant 0: box l,t,r,b; result clamped to the image) and
+ * yolov5/src/postprocess.cpp:4-29 (variant 1: box cx,cy,w,h; no clamping).  `kInputW / (img.cols * 1.0)` is a double
+ * division stored to float; everything after it is float; round() is C round() on the float promoted to double.
+ * ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_get_rect(int variant, int net_w, int net_h, int img_w, int img_h, const float* bbox, int* rect) {
+    float l, r, t, b;
+    float r_w = (float)(net_w / (img_w * 1.0));
+    float r_h = (float)(net_h / (img_h * 1.0));
+    if (variant == 0) {
+        if (r_h > r_w) {
+            l = bbox[0];
+            r = bbox[2];
+            t = bbox[1] - (net_h - r_w * img_h) / 2;
+            b = bbox[3] - (net_h - r_w * img_h) / 2;
+            l = l / r_w;
+            r = r / r_w;
+            t = t / r_w;
+            b = b / r_w;
+        } else {
+            l = bbox[0] - (net_w - r_h * img_w) / 2;
+            r = bbox[2] - (net_w - r_h * img_w) / 2;
+            t = bbox[1];
+            b = bbox[3];
+            l = l / r_h;
+            r = r / r_h;
+            t = t / r_h;
+            b = b / r_h;
+        }
+        l = 0.0f > l ? 0.0f : l; /* std::max(0.0f, l) */
+        t = 0.0f > t ? 0.0f : t;
+        int rw = (int)round(r - l), rl = (int)round(l), rh = (int)round(b - t), rt = (int)round(t);
+        int width = rw < img_w - rl ? rw : img_w - rl;
+        int height = rh < img_h - rt ? rh : img_h - rt;
+        rect[0] = rl;
+        rect[1] = rt;
+        rect[2] = width > 0 ? width : 0;
+        rect[3] = height > 0 ? height : 0;
+    } else {
+        if (r_h > r_w) {
+            l = bbox[0] - bbox[2] / 2.f;
+            r = bbox[0] + bbox[2] / 2.f;
+            t = bbox[1] - bbox[3] / 2.f - (net_h - r_w * img_h) / 2;
+            b = bbox[1] + bbox[3] / 2.f - (net_h - r_w * img_h) / 2;
+            l = l / r_w;
+            r = r / r_w;
+            t = t / r_w;
+            b = b / r_w;
+        } else {
+            l = bbox[0] - bbox[2] / 2.f - (net_w - r_h * img_w) / 2;
+            r = bbox[0] + bbox[2] / 2.f - (net_w - r_h * img_w) / 2;
+            t = bbox[1] - bbox[3] / 2.f;
+            b = bbox[1] + bbox[3] / 2.f;
+            l = l / r_h;
+            r = r / r_h;
+            t = t / r_h;
+            b = b / r_h;
+        }
+        rect[0] = (int)round(l);
+        rect[1] = (int)round(t);
+        rect[2] = (int)round(r - l);
+        rect[3] = (int)round(b - t);
+    }
+}
+

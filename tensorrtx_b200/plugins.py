@@ -684,6 +684,16 @@ class PreprocessPlan:
                                                         _stream(stream)), "trtx_preprocess_batch_enqueue")
 
 
+def get_rect(img_w: int, img_h: int, bbox, net_w: int = 640, net_h: int = 640, variant: int = L.YOLO_V8):
+    """get_rect(img, bbox) of yolov8/src/postprocess.cpp:6-36 (variant YOLO_V5: yolov5/src/postprocess.cpp:4-29):
+    -> (x, y, width, height) in the original image."""
+    lib = L.load()
+    b = (C.c_float * 4)(*[float(v) for v in bbox])
+    r = (C.c_int * 4)()
+    L.check(lib.trtx_get_rect(variant, net_w, net_h, img_w, img_h, b, r), "trtx_get_rect")
+    return tuple(r)
+
+
 def letterbox_matrix(src_w: int, src_h: int, dst_w: int, dst_h: int):
     m = (C.c_float * 6)()
     L.load().trtx_letterbox_matrix(src_w, src_h, dst_w, dst_h, m)

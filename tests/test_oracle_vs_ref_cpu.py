@@ -123,3 +123,25 @@ def test_retina_conf_threshold_is_a_double_compare(oracle):
     mine, _ = oracle.nms(2, buf, tp, 15, 0.1, 0.4)
     ref = _ref_nms(lib.ref_retina_nms, buf, 15, 0.4)
     assert len(ref) == 2 and np.array_equal(mine, ref)
+
+
+@pytest.mark.parametrize("variant,libname,fn", [(0, "libref_yolov8_host.so", "ref_v8_get_rect"),
+                                                (1, "libref_yolov5_host.so", "ref_v5_get_rect")])
+def test_get_rect_equals_reference(oracle, variant, libname, fn):
+    """get_rect (box in 640x640 network pixels -> cv::Rect in the original image): the reference's compiled host code vs
+    the oracle vs the library's host function trtx_get_rect -- identical integers on 4000 boxes and 8 image sizes."""
+    from tensorrtx_b200 import plugins as P
+    lib = _load(libname)
+    rng = np.random.default_rng(50 + variant)
+    for (w, h) in ((1920, 1080), (1080, 1920), (640, 640), (1280, 720), (333, 777), (4000, 3000), (641, 640), (50, 60)):
+        for _ in range(500):
+            if variant == 0:
+                x1, y1 = rng.uniform(-30, 650, 2)
+                bb = np.array([x1, y1, x1 + rng.uniform(-5, 400), y1 + rng.uniform(-5, 400)], np.float32)
+            else:
+                bb = np.array([rng.uniform(-30, 670), rng.uniform(-30, 670), rng.uniform(0, 500), rng.uniform(0, 500)], np.float32)
+            ref = np.zeros(4, np.int32)
+            getattr(lib, fn)(w, h, bb.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(oracle.get_rect(variant, w, h, bb), ref)
+            assert P.get_rect(w, h, bb, variant=variant) == tuple(int(v) for v in ref)
+
