@@ -36,3 +36,21 @@ def test_trt_adapters_enqueue_on_gpu(tmp_path):
     r = subprocess.run([str(exe), "--gpu"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "gpu enqueue ok" in r.stdout
+
+
+def test_preprocess_compat_header_compiles_and_links(tmp_path):
+    """include/trtx_preprocess_compat.h = the reference's preprocess.h API (cuda_preprocess_init / _destroy / cuda_preprocess /
+    cuda_batch_preprocess) on top of the C ABI; compiled here against the OpenCV type shim (no OpenCV in this image)."""
+    from tensorrtx_b200 import _lib as L
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cuda = Path(nvcc).resolve().parents[1]
+    exe = tmp_path / "preprocess_compat_check"
+    cmd = ["g++", "-std=c++14", "-O1", "-Wall", "-I", str(ROOT / "include"), "-I", str(ROOT / "oracle" / "shim"),
+           "-I", str(cuda / "include"), str(ROOT / "tests" / "preprocess_compat_check.cpp"), "-o", str(exe),
+           str(L.LIB_PATH), f"-Wl,-rpath,{L.LIB_PATH.parent}", "-L", str(cuda / "lib64"), "-lcudart", f"-Wl,-rpath,{cuda / 'lib64'}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "preprocess compat check ok" in r.stdout, r.stdout + r.stderr
+
