@@ -182,3 +182,16 @@ def test_bench_reference_arm_prints_contract_json():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_division_free_overlap_test_is_exact(tmp_path):
+    """nms.cu decides `iou > thresh` from the sign of fma(-thresh, denom, inter) unless the quotient is within 1e-5 of the
+    threshold: tools/verify_overlap_test.c replays that rule on random and adversarial (few-ulp) operands against the
+    IEEE division; zero disagreements (3.2e9 cases in the full run, a bounded sample here)."""
+    exe = tmp_path / "verify_overlap"
+    r = subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-o", str(exe), str(ROOT / "tools" / "verify_overlap_test.c"),
+                        "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "2000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches=0" in r.stdout, r.stdout
+
