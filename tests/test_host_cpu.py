@@ -209,3 +209,14 @@ def test_logit_domain_class_loop_equals_reference_loop(tmp_path):
     assert r.returncode == 0 and "mismatches=0" in r.stdout, r.stdout
     assert "collision_replays=0 " not in r.stdout   # the replay path is exercised
 
+
+def test_nms_bitmap_phase_equals_greedy(tmp_path):
+    """nms_kernel phase E (closed-form work-unit layout, one bitmap byte per unit, chunked ballot resolve) replayed in C for
+    random class segments of every length 1..96 against plain greedy NMS: tools/verify_nms_bitmap.c."""
+    exe = tmp_path / "verify_nms"
+    r = subprocess.run(["gcc", "-O2", "-fopenmp", "-o", str(exe), str(ROOT / "tools" / "verify_nms_bitmap.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "20000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches=0" in r.stdout, r.stdout
+
