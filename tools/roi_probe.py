@@ -27,19 +27,3 @@ for sampling in (0, 2):
     us = e0.elapsed_time(e1) / K * 1e3
     print(json.dumps({"kernel": "roi_align", "sampling_ratio": sampling, "images": B, "us": round(us, 1),
                       "written_GBps": round(out.numel() * 4 / us / 1e3, 1)}), flush=True)
-
-# the reference's own roiAlign (oracle/_ref/libref_rcnn.so, built from /root/reference/rcnn/RoiAlign.cu) on the same inputs
-import ctypes as C, time
-ref = ROOT / "oracle" / "_ref" / "libref_rcnn.so"
-if ref.exists():
-    lib = C.CDLL(str(ref))
-    for sampling in (0, 2):
-        args = (B, C.c_void_p(rois.data_ptr()), C.c_void_p(feat.data_ptr()), C.c_void_p(out.data_ptr()), Pp, C.c_float(1 / 16),
-                sampling, N, C_ if False else 1024, H, W)
-        lib.ref_roi_align(*args)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            lib.ref_roi_align(*args)   # synchronises the device itself (RoiAlign.cu:178)
-        us = (time.perf_counter() - t0) / 3 * 1e6
-        print(json.dumps({"kernel": "reference roiAlign", "sampling_ratio": sampling, "images": B, "us": round(us, 1)}), flush=True)
