@@ -220,3 +220,12 @@ def test_nms_bitmap_phase_equals_greedy(tmp_path):
     r = subprocess.run([str(exe), "20000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "mismatches=0" in r.stdout, r.stdout
 
+
+def test_abi_header_is_plain_c(tmp_path):
+    """include/trtx_hot.h is the FFI boundary (cgo / JNI / ctypes bind it): it must compile as C99 without extensions."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "trtx_hot.h"\nint main(void) { trtx_nms_params q; trtx_mask_params m; (void)q; (void)m; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-fsyntax-only",
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
