@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of CUDA graphs")
     ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--no-overlap", action="store_true", help="letterbox, scan and NMS strictly one after another")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -275,7 +276,7 @@ def main():
             def f():
                 if world > 1:
                     ring.launch(prev.fused.out, (j - 1) % R)  # fork: detections of the previous step
-                p.run_device(h)
+                p.run_device(h, overlap=not args.no_overlap)
                 ring.join()                                    # join the side stream (ends the graph's second branch)
             return f
 
@@ -300,7 +301,7 @@ def main():
                 torch.cuda.synchronize(dev)
                 gather_mode = "side-stream, eager"
                 needs_flush = False
-                dgc = [p.capture(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes_dev, head_sets)]
+                dgc = [p.capture(lambda p=p, h=h: p.run_device(h, overlap=not args.no_overlap)) for p, h in zip(pipes_dev, head_sets)]
 
                 def make_eager(j):
                     def f():

@@ -47,6 +47,10 @@ enum {
 TRTX_API const char* trtx_version(void);
 /* cudaError_t of the last failing launch on this thread (0 if none). */
 TRTX_API int trtx_last_cuda_error(void);
+/* sizeof() of the parameter structs as THIS library was compiled, so that an FFI binding (ctypes, cgo, ...) can check its
+ * mirror of the layout: which = 0 trtx_yolo_params, 1 trtx_nms_params, 2 trtx_retina_params, 3 trtx_image_desc,
+ * 4 trtx_mask_params; anything else 0. */
+TRTX_API size_t trtx_abi_sizeof(int which);
 
 /* =====================================================================================
  * 1. YoloLayer_TRT  -- fused per-anchor sigmoid / argmax / gate / box decode / compaction
@@ -77,6 +81,16 @@ typedef struct trtx_yolo_params {
     float kpt_thresh;    /* combinedInfo[2] (int-truncated by the reference builder, block.cpp:271) */
     float gate;          /* 0.1f: literal of yolov8 yololayer.cu:203 / kIgnoreThresh yolov5 config.h:38 */
     int32_t in_dtype;    /* TRTX_F32 (parity mode, what the reference accepts, yololayer.h:32-35) | TRTX_F16 */
+    /* Launch tuning of the scan kernel.  Plain per-call data: the library keeps NO mutable state, so concurrent enqueues
+     * (TensorRT calls enqueue() on clones from several threads, SURVEY 8b "Threading") with different tunings are
+     * independent.  0 everywhere -- what memset / trtx_yolo_params_init_v8 leave -- selects the defaults taken from the
+     * B200 sweep in profiles/.  A combination that is not built returns TRTX_ERR_UNSUPPORTED. */
+    int32_t tune_class_slices;   /* warps of a CTA splitting the class range: 1, 2, 4, 8; 0 = 2 */
+    int32_t tune_rows_in_flight; /* channel rows loaded per group; 0 = 5.  Built (slices, rows): (1,8) (1,16) (2,4) (2,5)
+                                    (2,8) (2,10) (2,20) (4,4) (4,5) (4,10) (4,20) (8,5) (8,10) */
+    int32_t tune_tma_pipeline;   /* 1: persistent TMA-fed scan (v8 layout, 16-byte aligned levels); 0 = register scan */
+    int32_t tune_tma_stages;     /* cap on its pipeline stages; 0 = as many as fit (15) */
+    int32_t tune_box_prefetch;   /* box rows of a tile: 1 on demand, 2 L2 prefetch, 3 into registers up front; 0 = 2 */
 } trtx_yolo_params;
 
 /* Fill grid_h/grid_w from net size and strides (v8) -- convenience, mirrors yololayer.cu:292-296. */
@@ -117,6 +131,8 @@ enum {
     TRTX_NMS_ONESHOT = 1, /* nms_kernel semantics, yolov8/src/postprocess.cu:89-111 */
 };
 
+#define TRTX_NMS_MAX_ROWS 2048 /* rows per image the NMS kernel sorts on chip */
+
 typedef struct trtx_nms_params {
     int32_t box_format;  /* TRTX_BOX_* */
     int32_t mode;        /* TRTX_NMS_* */
@@ -137,7 +153,15 @@ typedef struct trtx_nms_params {
  * order of the reference's `res` vector (std::map iteration + std::sort).
  * GREEDY: only kept rows are written (keep=1), count = number kept.  ONESHOT: all rows above
  * conf_thresh, keep flag 0/1, count = rows.  Rows >= count are zero.
- * At most `max_rows` (trtx_nms_enqueue) / `p->max_out` (fused) highest-conf rows enter NMS.
+ * Rows entering NMS:
+ *   trtx_nms_enqueue: every row i < min(count, max_rows) above conf_thresh, exactly like the reference's nms(), as long
+ *     as max_rows <= TRTX_NMS_MAX_ROWS; with a larger max_rows (e.g. RetinaFace's 16800 priors) the TRTX_NMS_MAX_ROWS
+ *     highest-confidence rows above conf_thresh enter (ties at the cut: lower row index first) -- the reference has no
+ *     such cap, so results only differ when more than TRTX_NMS_MAX_ROWS rows of one image pass conf_thresh;
+ *   fused / split calls: the first p->max_out candidates in ascending anchor order (= the rows the plugin buffer of
+ *     trtx_yolo_decode_enqueue would hold), then the conf_thresh filter: both paths give identical results also when
+ *     an image has more than max_out candidates (the reference's choice there is atomicAdd arrival order).
+ *     p->max_out <= TRTX_NMS_MAX_ROWS or TRTX_ERR_UNSUPPORTED.
  * keep_index_dev (optional, may be NULL): [batch, max_det] int32 flat anchor id of each written row. */
 
 /* NMS over a plugin-format buffer [batch, 1 + max_rows*det_floats] (drop-in for batch_nms()). */

@@ -6,6 +6,7 @@ path raises.  The library is built in-tree by tensorrtx_b200/build.py (nvcc, sm_
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 MAX_LEVELS = 8
@@ -43,6 +44,12 @@ class YoloParams(C.Structure):
         ("kpt_thresh", C.c_float),
         ("gate", C.c_float),
         ("in_dtype", C.c_int32),
+        # per-call launch tuning (0 = default); the library holds no global knobs
+        ("tune_class_slices", C.c_int32),
+        ("tune_rows_in_flight", C.c_int32),
+        ("tune_tma_pipeline", C.c_int32),
+        ("tune_tma_stages", C.c_int32),
+        ("tune_box_prefetch", C.c_int32),
     ]
 
 
@@ -79,7 +86,8 @@ class MaskParams(C.Structure):
                                          "coeff_offset", "max_masks")]
 
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtrtx_hot.so"
+# TRTX_LIB: another build of the same ABI (the probe build of tools/nms_probe.py); default = the in-tree release library
+LIB_PATH = Path(os.environ.get("TRTX_LIB") or Path(__file__).resolve().parent / "lib" / "libtrtx_hot.so")
 
 # every symbol include/trtx_hot.h declares: (name, restype, argtypes)
 _vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
@@ -108,9 +116,8 @@ SYMBOLS = {
     "trtx_mask_rcnn_inference": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "trtx_process_mask_enqueue": (_i, [C.POINTER(MaskParams), _i, _vp, _vp, _i, _vp, _vp]),
     "trtx_letterbox_matrix": (None, [_i, _i, _i, _i, C.POINTER(C.c_float)]),
+    "trtx_abi_sizeof": (_sz, [_i]),
 }
-# tuning knob exported for the bench sweep; not part of the drop-in ABI
-_EXTRA = {"trtx_tune_set": (_i, [_i, _i]), "trtx_tune_set_ptr": (_i, [_vp])}
 
 _lib = None
 
@@ -126,10 +133,14 @@ def load() -> C.CDLL:
             "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for this path."
         )
     lib = C.CDLL(str(LIB_PATH))
-    for name, (res, args) in {**SYMBOLS, **_EXTRA}.items():
+    for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    for which, st in enumerate((YoloParams, NmsParams, RetinaParams, ImageDesc, MaskParams)):
+        if lib.trtx_abi_sizeof(which) != C.sizeof(st):
+            raise TrtxError(f"{LIB_PATH} was built from a different trtx_hot.h: sizeof({st.__name__}) = "
+                            f"{lib.trtx_abi_sizeof(which)} in the library, {C.sizeof(st)} in the binding (rebuild)")
     _lib = lib
     return lib
 

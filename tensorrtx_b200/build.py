@@ -44,22 +44,27 @@ def _stamp(sources: list[Path]) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into tensorrtx_b200/lib/libtrtx_hot.so."""
+def build(force: bool = False, verbose: bool = False, probe: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a into tensorrtx_b200/lib/libtrtx_hot.so.
+    probe=True builds libtrtx_hot_probe.so instead: the same sources with -DTRTX_NMS_PROBE (clock64 phase stamps in
+    nms_kernel + trtx_probe_set_nms_stamps), used by tools/nms_probe.py only."""
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     LIBDIR.mkdir(exist_ok=True)
-    stamp_file = LIBDIR / "libtrtx_hot.stamp"
+    lib = LIBDIR / "libtrtx_hot_probe.so" if probe else LIB
+    stamp_file = lib.with_suffix(".stamp")
     stamp = _stamp(srcs)
-    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
-        return LIB
+    if not force and lib.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return lib
     nvcc = _nvcc()
     objs = []
-    objdir = LIBDIR / "obj"
+    objdir = LIBDIR / ("obj_probe" if probe else "obj")
     objdir.mkdir(exist_ok=True)
     procs = []
     for s in srcs:
         o = objdir / (s.stem + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-I", str(CSRC), "-c", str(s), "-o", str(o)]
+        if probe:
+            cmd.insert(1, "-DTRTX_NMS_PROBE")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -70,12 +75,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {s.name}:\n{out}")
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", *NVCC_FLAGS, "-o", str(LIB), *map(str, objs)]
+    cmd = [nvcc, "-shared", *NVCC_FLAGS, "-o", str(lib), *map(str, objs)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc link failed:\n{r.stdout}")
     stamp_file.write_text(stamp)
-    return LIB
+    return lib
 
 
 def build_oracle() -> Path:

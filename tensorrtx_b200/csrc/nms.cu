@@ -29,11 +29,17 @@
 
 namespace trtx {
 
-static long long* g_nms_dbg = nullptr;
+// Phase stamps (clock64 per image) exist only in the probe build (tensorrtx_b200/build.py build(probe=True), used by
+// tools/nms_probe.py): the release library has no profiling state at all.
+#ifdef TRTX_NMS_PROBE
+static thread_local long long* t_nms_stamps = nullptr;
 #define TRTX_STAMP(k) do { if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 16 + (k)] = clock64(); } while (0)
+#else
+#define TRTX_STAMP(k) do { } while (0)
+#endif
 
 constexpr int kNmsThreads = 1024;
-constexpr int kMaxSort = 2048;  // rows entering NMS per image (>= kMaxNumOutputBbox = 1000)
+constexpr int kMaxSort = TRTX_NMS_MAX_ROWS;  // rows entering NMS per image (>= kMaxNumOutputBbox = 1000)
 constexpr int kClassBins = kNmsThreads;  // bucket sort: one histogram bin per thread
 constexpr int kMaxBucket = 256;           // rows per class the rank-by-counting pass accepts
 constexpr int kShortSeg = 96;  // class segments up to this many rows are resolved by a single warp
@@ -60,7 +66,9 @@ struct NmsArgs {
     int pre_topk;  // rows entering NMS (<= kMaxSort)
     int max_det;
     int extra_floats, extra_offset;
-    long long* dbg;       // profiling aid (trtx_tune_set_ptr): 8 clock64 stamps per image, or null
+#ifdef TRTX_NMS_PROBE
+    long long* dbg;       // 16 clock64 stamps per image, or null
+#endif
     float* out;           // [B, 1 + max_det*(7+extra)]
     int32_t* keep_index;  // [B, max_det] or null
 };
@@ -308,7 +316,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         }
         if (tid == 0) s_tpre[T] = carry;
         __syncthreads();
-        const int n_in = carry;
+        // The reference plugin keeps the first max_out candidates that grab a slot (yololayer.cu:206-208) and its host
+        // nms() filters THOSE by confidence: same here with "first" = ascending anchor order (what
+        // trtx_yolo_decode_enqueue + trtx_nms_enqueue do through the plugin buffer), so both paths agree above max_out.
+        const int n_in = min(carry, a.pre_topk);
         for (int r = tid; r < n_in; r += kNmsThreads) {
             int lo = 0, hi = T;  // largest t with s_tpre[t] <= r
             while (hi - lo > 1) {
@@ -849,7 +860,9 @@ static int nms_validate(const trtx_nms_params* q) {
 }
 
 static int nms_launch(NmsArgs& a, int batch, cudaStream_t st) {
-    a.dbg = g_nms_dbg;
+#ifdef TRTX_NMS_PROBE
+    a.dbg = t_nms_stamps;
+#endif
     if (a.pre_topk > kMaxSort) return TRTX_ERR_UNSUPPORTED;
     const size_t smem = nms_smem_bytes(a.pre_topk, a.from_tiles ? a.tiles_per_image : 0);
     // 227 KB per CTA minus the kernel's static shared memory (histograms, ~18 KB)
@@ -867,11 +880,13 @@ using namespace trtx;
 
 extern "C" {
 
-// profiling aid (not part of the drop-in ABI): device buffer of 16*batch int64 receiving clock64 phase stamps of nms_kernel
-TRTX_API int trtx_tune_set_ptr(void* p) {
-    g_nms_dbg = static_cast<long long*>(p);
+#ifdef TRTX_NMS_PROBE
+// probe build only: device buffer of 16*batch int64 receiving clock64 phase stamps of nms_kernel (this thread's launches)
+TRTX_API int trtx_probe_set_nms_stamps(void* p) {
+    t_nms_stamps = static_cast<long long*>(p);
     return TRTX_OK;
 }
+#endif
 
 TRTX_API size_t trtx_nms_workspace_size(const trtx_nms_params* p, int batch, int max_rows) {
     if (nms_validate(p) || batch <= 0 || max_rows <= 0) return 0;

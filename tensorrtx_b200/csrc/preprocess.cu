@@ -14,8 +14,10 @@
 // offset without a matching `-0.5f`, preprocess.cu:22-23) and, like the reference's own nvcc build,
 // leaves the bilinear sums to the default FMA contraction (<= 1 ulp from the uncontracted oracle).
 #include <limits.h>
+#include <math.h>
+#include <string.h>
 
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace trtx {
 
@@ -24,7 +26,8 @@ constexpr int kMaxImagesPerLaunch = 128;
 struct PreImage {
     const uint8_t* src;
     int sw, sh, pitch;
-    float m[6];  // d2s
+    int dst_idx;  // image slot in dst
+    float m[6];   // d2s
 };
 struct PreArgs {
     PreImage img[kMaxImagesPerLaunch];
@@ -51,7 +54,6 @@ __device__ __forceinline__ float div255(float x) {
 //   * the bilinear sum is written as the reference writes it and left to nvcc's default FMA contraction, exactly
 //     like the reference's own build: the output is BIT-IDENTICAL to the reference kernel's
 //     (tests/test_vs_reference_gpu.py::test_preprocess_vs_reference_kernel).
-void preprocess_set_rows(int) {}  // tuning knob 6: retired (strip height and conversion mix are fixed, see below)
 
 // u8 -> f32 without the conversion (XU) pipe: for 0 <= i < 2^23, 2^23 + i is exactly representable with i in the
 // mantissa, so OR-ing i into the bits of 2^23 and subtracting 2^23 gives float(i) exactly (two full-rate instructions).
@@ -63,8 +65,7 @@ constexpr int kRowsPerThread = 4;  // 8-row strips measured slower (profiles/r01
 // __launch_bounds__(256, 8): 32 registers -> 64 resident warps per SM.  The kernel is latency-bound once the instruction
 // count is down (no pipe above 60 %), and occupancy is what hides it: 59.4 us at 60 registers, 53.7 at 40, 51.9 at 32.
 template <typename OutT>
-__global__ void __launch_bounds__(256, 8) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst,
-                                                        int first_image) {
+__global__ void __launch_bounds__(256, 8) letterbox_kernel(const __grid_constant__ PreArgs a, OutT* __restrict__ dst) {
     constexpr int R = kRowsPerThread;
     const int b = blockIdx.z;
     const PreImage& im = a.img[b];
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256, 8) letterbox_kernel(const __grid_constant
     const int dy0 = (blockIdx.y * blockDim.y + threadIdx.y) * R;
     if (dx >= a.dw || dy0 >= a.dh) return;
     const size_t area = (size_t)a.dw * a.dh;
-    OutT* base = dst + (size_t)(first_image + b) * 3 * area + (size_t)dy0 * a.dw + dx;
+    OutT* base = dst + (size_t)im.dst_idx * 3 * area + (size_t)dy0 * a.dw + dx;
     const float cv = 128.0f;  // const_value_st (:115)
     const uint8_t* __restrict__ img = im.src;
     const int sw = im.sw, sh = im.sh;
@@ -179,6 +180,211 @@ __global__ void __launch_bounds__(256, 8) letterbox_kernel(const __grid_constant
     }
 }
 
+
+// =====================================================================================================================
+// Unit-scale letterbox, TMA-staged (the 640x640 -> 640x640 benchmark and every source that fits the network input in
+// one dimension: scale == 1, the image is only translated / padded).
+//
+// With scale == 1 the d2s matrix is {1, -0, tx, -0, 1, ty} with 2*tx, 2*ty integers (preprocess.cu:98-110), so for every
+// destination pixel  x_low = dx + ox,  y_low = dy + oy  and the bilinear fractions lx, ly are image-wide constants in
+// {0, 0.5}: the four weights are products of {0, 0.5, 1}, every product w*u8 and every partial sum of the reference's
+// expression (preprocess.cu:59-61) is exact in fp32, hence the result does not depend on evaluation order or FMA
+// contraction, and "tap outside the image -> 128" (preprocess.cu:38-57) also reproduces the fully-outside case
+// (:25-30: the weights sum to exactly 1).  The kernel is therefore bit-identical to the reference by construction;
+// tests assert array_equal against the reference's compiled kernel.
+//
+// A CTA owns a TW x TH destination tile.  Its (TH+1) x (TW+1)-pixel source window is fetched by ONE TMA tensor copy
+// (u8 tensor map over the image, box [kBoxBytes, TH+1]; rows/columns outside the image arrive as zeros and are patched
+// to 128 by the few border tiles) -- no per-lane byte loads, no address arithmetic per tap.  Each thread then produces
+// 4 ADJACENT pixels x 4 rows: per source row 4 conflict-free LDS.32 (15 bytes = 5 BGR pixels), every byte converted
+// once with one PRMT (byte -> mantissa of 2^23) + one FADD and shared by the 2x2 destination pixels that use it, and
+// one 16-byte store per plane and row (8 bytes for fp16 output).  Half-warps take row groups 4 rows apart, which puts
+// their LDS on disjoint banks (4 * 52 words = 16 mod 32).
+// Instructions per destination pixel: ~33 (the per-lane-byte-load kernel above: 79).
+constexpr int kUnitTW = 64;                   // destination columns per CTA = 16 lanes x 4 pixels
+constexpr int kUnitBoxBytes = 208;            // >= (kUnitTW + 1) * 3 = 195, multiple of 16 (TMA inner box extent)
+constexpr int kMaxUnitImages = 64;
+
+struct UnitImage {
+    int ox, oy;    // x_low(dx = 0), y_low(dy = 0)
+    int sw, sh;
+    int map, z;    // tensor map index, image coordinate inside that map
+    int dst_idx;
+    float lx, ly;  // bilinear fractions (0 or 0.5), constant over the image
+};
+struct alignas(64) UnitArgs {
+    CUtensorMap map[kMaxUnitImages];
+    UnitImage img[kMaxUnitImages];
+    int dw, dh;
+};
+
+template <typename OutT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) letterbox_unit_kernel(const __grid_constant__ UnitArgs a, OutT* __restrict__ dst) {
+    constexpr int TW = kUnitTW, TH = WARPS * 8, BOXW = kUnitBoxBytes, ROWS = TH + 1;
+    __shared__ __align__(128) uint8_t box[ROWS * BOXW];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const UnitImage& im = a.img[blockIdx.z];
+    const int dx0 = blockIdx.x * TW, dy0 = blockIdx.y * TH;
+    const int sx0 = dx0 + im.ox, sy0 = dy0 + im.oy;  // source pixel under the tile's first tap
+    const int sw = im.sw, sh = im.sh;
+    const bool all_out = sx0 + TW < 0 || sx0 >= sw || sy0 + TH < 0 || sy0 >= sh;
+    const bool interior = sx0 >= 0 && sx0 + TW < sw && sy0 >= 0 && sy0 + TH < sh;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (!all_out) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar, ROWS * BOXW);
+            tma_load_3d(box, &a.map[im.map], sx0 * 3, sy0, im.z, &bar);
+        }
+        mbar_wait(&bar, 0);
+        if (!interior) {
+            // border tile: pixels of the window outside the image -> const_value_st = 128 (preprocess.cu:115)
+            for (int i = tid; i < ROWS * (TW + 1); i += WARPS * 32) {
+                const int r = i / (TW + 1), c = i - r * (TW + 1);
+                const int y = sy0 + r, x = sx0 + c;
+                if (y < 0 || y >= sh || x < 0 || x >= sw) {
+                    uint8_t* q = box + r * BOXW + c * 3;
+                    q[0] = 128;
+                    q[1] = 128;
+                    q[2] = 128;
+                }
+            }
+            __syncthreads();
+        }
+    } else {  // pure padding tile: every tap is the border value
+        for (int i = tid; i < ROWS * BOXW / 4; i += WARPS * 32) reinterpret_cast<uint32_t*>(box)[i] = 0x80808080u;
+        __syncthreads();
+    }
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int k = lane & 15;
+    const int r0 = warp * 8 + (lane >> 4) * 4;  // half-warps 4 rows apart: disjoint banks
+    const int dx = dx0 + 4 * k;
+    if (dx >= a.dw) return;
+    const float lx = im.lx, ly = im.ly, hx = 1 - lx, hy = 1 - ly;
+    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;  // preprocess.cu:34-35
+    const size_t area = (size_t)a.dw * a.dh;
+    OutT* o = dst + (size_t)im.dst_idx * 3 * area + (size_t)(dy0 + r0) * a.dw + dx;
+    const uint8_t* p = box + r0 * BOXW + 12 * k;
+
+    auto load_row = [&](const uint8_t* q, float (&t)[15]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = reinterpret_cast<const uint32_t*>(q)[j];
+#pragma unroll
+        for (int i = 0; i < 15; ++i)  // byte i -> float: 2^23 + v is exact with v in the mantissa
+            t[i] = __uint_as_float(__byte_perm(w[i >> 2], 0x4B000000u, 0x7650u + (i & 3))) - 8388608.0f;
+    };
+    float top[15], bot[15];
+    load_row(p, top);
+    const int rows = a.dh - (dy0 + r0);  // rows of this strip inside the destination
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        load_row(p + (r + 1) * BOXW, bot);
+        if (r < rows) {
+            float v[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)  // :59-61, bgr -> rgb and /255 :64-74
+                    v[c][j] = div255(w1 * top[3 * j + c] + w2 * top[3 * j + 3 + c] + w3 * bot[3 * j + c] + w4 * bot[3 * j + 3 + c]);
+            OutT* orow = o + (size_t)r * a.dw;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                OutT* q = orow + (size_t)(2 - c) * area;
+                if constexpr (sizeof(OutT) == 4) {
+                    *reinterpret_cast<float4*>(q) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+                } else {
+                    const __half2 h0 = __floats2half2_rn(v[c][0], v[c][1]), h1 = __floats2half2_rn(v[c][2], v[c][3]);
+                    uint2 u;
+                    u.x = *reinterpret_cast<const uint32_t*>(&h0);
+                    u.y = *reinterpret_cast<const uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(q) = u;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 15; ++i) top[i] = bot[i];
+    }
+}
+
+// Host: does this image take the unit-scale path?  (scale == 1 exactly, half-integer translation, TMA-compatible.)
+static bool unit_scale_image(const trtx_image_desc& d, const float m[6], UnitImage* u) {
+    if (!(m[0] == 1.0f && m[4] == 1.0f && m[1] == 0.0f && m[3] == 0.0f)) return false;
+    const float tx = m[2] + 0.5f, ty = m[5] + 0.5f;
+    if (!(fabsf(tx) < 1048576.0f && fabsf(ty) < 1048576.0f)) return false;
+    if (2.0f * tx != rintf(2.0f * tx) || 2.0f * ty != rintf(2.0f * ty)) return false;
+    if (reinterpret_cast<uintptr_t>(d.data_dev) % 16 != 0 || d.pitch % 16 != 0) return false;  // TMA base / stride
+    u->ox = (int)floorf(tx);
+    u->oy = (int)floorf(ty);
+    u->lx = tx - floorf(tx);
+    u->ly = ty - floorf(ty);
+    u->sw = d.width;
+    u->sh = d.height;
+    return true;
+}
+
+static bool encode_image_map(CUtensorMap* map, const uint8_t* base, int sw, int sh, int pitch, int n, size_t image_stride,
+                             int box_rows) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)sw * 3u, (cuuint64_t)sh, (cuuint64_t)n};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)image_stride};
+    const cuuint32_t bdim[3] = {(cuuint32_t)kUnitBoxBytes, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, bdim, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr int kUnitWarps = 4;
+
+// Launch the unit-scale kernel for `n` images (descriptors d[i], unit info u[i] already filled but for map/z).
+// Returns TRTX_ERR_UNSUPPORTED when no tensor map can be made (caller falls back to the general kernel).
+static int launch_unit(const trtx_image_desc* const* d, UnitImage* u, int n, void* dst, int dw, int dh, int out_dtype,
+                       cudaStream_t st) {
+    UnitArgs a;
+    a.dw = dw;
+    a.dh = dh;
+    constexpr int box_rows = kUnitWarps * 8 + 1;
+    // one 3-D map for the whole group when the images are equally sized and equally spaced (a frame ring / one batch
+    // tensor): one encode instead of n
+    bool uniform = n > 1;
+    const ptrdiff_t step = n > 1 ? d[1]->data_dev - d[0]->data_dev : 0;
+    for (int i = 1; i < n && uniform; ++i)
+        uniform = d[i]->width == d[0]->width && d[i]->height == d[0]->height && d[i]->pitch == d[0]->pitch &&
+                  d[i]->data_dev - d[i - 1]->data_dev == step;
+    uniform = uniform && step > 0 && step % 16 == 0 && (size_t)step >= (size_t)d[0]->pitch * (size_t)d[0]->height;
+    if (uniform) {
+        if (!encode_image_map(&a.map[0], d[0]->data_dev, d[0]->width, d[0]->height, d[0]->pitch, n, (size_t)step, box_rows))
+            return TRTX_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (uniform) {
+            u[i].map = 0;
+            u[i].z = i;
+        } else {
+            if (!encode_image_map(&a.map[i], d[i]->data_dev, d[i]->width, d[i]->height, d[i]->pitch, 1,
+                                  (size_t)d[i]->pitch * (size_t)d[i]->height, box_rows))
+                return TRTX_ERR_UNSUPPORTED;
+            u[i].map = i;
+            u[i].z = 0;
+        }
+        a.img[i] = u[i];
+    }
+    dim3 grid((dw + kUnitTW - 1) / kUnitTW, (dh + kUnitWarps * 8 - 1) / (kUnitWarps * 8), n);
+    if (out_dtype == TRTX_F32)
+        letterbox_unit_kernel<float, kUnitWarps><<<grid, kUnitWarps * 32, 0, st>>>(a, static_cast<float*>(dst));
+    else
+        letterbox_unit_kernel<__half, kUnitWarps><<<grid, kUnitWarps * 32, 0, st>>>(a, static_cast<__half*>(dst));
+    return check_launch();
+}
+
 }  // namespace trtx
 
 using namespace trtx;
@@ -275,31 +481,69 @@ TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, i
     if (!images_host || batch <= 0 || !dst_dev || dst_w <= 0 || dst_h <= 0) return TRTX_ERR_INVALID;
     if (out_dtype != TRTX_F32 && out_dtype != TRTX_F16) return TRTX_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int first = 0; first < batch; first += kMaxImagesPerLaunch) {
-        const int n = batch - first < kMaxImagesPerLaunch ? batch - first : kMaxImagesPerLaunch;
-        PreArgs a;
-        a.dw = dst_w;
-        a.dh = dst_h;
-        for (int i = 0; i < n; ++i) {
-            const trtx_image_desc& d = images_host[first + i];
-            if (!d.data_dev || d.width <= 0 || d.height <= 0 || d.pitch < 3 * d.width) return TRTX_ERR_INVALID;
-            a.img[i].src = d.data_dev;
-            a.img[i].sw = d.width;
-            a.img[i].sh = d.height;
-            a.img[i].pitch = d.pitch;
-            trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, a.img[i].m);
-        }
+    for (int i = 0; i < batch; ++i) {
+        const trtx_image_desc& d = images_host[i];
+        if (!d.data_dev || d.width <= 0 || d.height <= 0 || d.pitch < 3 * d.width) return TRTX_ERR_INVALID;
+    }
+    // vector stores of the unit-scale kernel: 4 pixels per thread and plane
+    const bool unit_ok = dst_w % 4 == 0 && reinterpret_cast<uintptr_t>(dst_dev) % 16 == 0;
+    PreArgs g;  // general-path group
+    g.dw = dst_w;
+    g.dh = dst_h;
+    int ng = 0;
+    const trtx_image_desc* ud[kMaxUnitImages];
+    UnitImage uu[kMaxUnitImages];
+    int nu = 0;
+    auto flush_general = [&]() -> int {
+        if (!ng) return TRTX_OK;
         constexpr int R = kRowsPerThread;
         dim3 block(128, 2, 1);  // 128 columns x (2 x R) rows per block
-        dim3 grid((dst_w + 127) / 128, (dst_h + 2 * R - 1) / (2 * R), n);
+        dim3 grid((dst_w + 127) / 128, (dst_h + 2 * R - 1) / (2 * R), ng);
         if (out_dtype == TRTX_F32)
-            letterbox_kernel<float><<<grid, block, 0, st>>>(a, static_cast<float*>(dst_dev), first);
+            letterbox_kernel<float><<<grid, block, 0, st>>>(g, static_cast<float*>(dst_dev));
         else
-            letterbox_kernel<__half><<<grid, block, 0, st>>>(a, static_cast<__half*>(dst_dev), first);
-        int rc = check_launch();
+            letterbox_kernel<__half><<<grid, block, 0, st>>>(g, static_cast<__half*>(dst_dev));
+        ng = 0;
+        return check_launch();
+    };
+    auto add_general = [&](int i) -> int {
+        const trtx_image_desc& d = images_host[i];
+        PreImage& im = g.img[ng++];
+        im.src = d.data_dev;
+        im.sw = d.width;
+        im.sh = d.height;
+        im.pitch = d.pitch;
+        im.dst_idx = i;
+        trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, im.m);
+        return ng == kMaxImagesPerLaunch ? flush_general() : TRTX_OK;
+    };
+    auto flush_unit = [&]() -> int {
+        if (!nu) return TRTX_OK;
+        int rc = launch_unit(ud, uu, nu, dst_dev, dst_w, dst_h, out_dtype, st);
+        if (rc == TRTX_ERR_UNSUPPORTED) {  // no tensor map (driver without the encoder): general kernel
+            rc = TRTX_OK;
+            for (int j = 0; j < nu && rc == TRTX_OK; ++j) rc = add_general(uu[j].dst_idx);
+        }
+        nu = 0;
+        return rc;
+    };
+    for (int i = 0; i < batch; ++i) {
+        const trtx_image_desc& d = images_host[i];
+        float m[6];
+        trtx_letterbox_matrix(d.width, d.height, dst_w, dst_h, m);
+        int rc = TRTX_OK;
+        if (unit_ok && unit_scale_image(d, m, &uu[nu])) {
+            ud[nu] = &d;
+            uu[nu].dst_idx = i;
+            if (++nu == kMaxUnitImages) rc = flush_unit();
+        } else {
+            rc = add_general(i);
+        }
         if (rc) return rc;
     }
-    return TRTX_OK;
+    int rc = flush_unit();
+    if (rc) return rc;
+    return flush_general();
 }
 
 }  // extern "C"

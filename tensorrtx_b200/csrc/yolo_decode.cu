@@ -20,15 +20,6 @@ namespace trtx {
 
 thread_local int g_last_cuda_error = 0;
 
-// tuning knobs (set through trtx_tune_set; defaults chosen from the B200 sweep in profiles/)
-static int g_slices = 2;
-static int g_unroll = 5;
-static int g_use_pipe = 0;      // 1: TMA-pipelined persistent scan (yolo_scan_pipe.cu) when the shape allows it
-static int g_prefetch_box = 1;  // L2-prefetch the 4 box rows while the class rows stream
-void yolo_pipe_set_consumers(int n);
-void yolo_pipe_set_debug(int v);
-void preprocess_set_rows(int r);
-
 // --------------------------------------------------------------------------------------------
 // scan_classes: running (max logit, first argmax, max before it) over `nrows` channel rows for VEC
 // adjacent anchors (Best / finish_best in yolo_layout.cuh turn that into the reference's result
@@ -119,9 +110,9 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
     const int per = (a.nc + SLICES - 1) / SLICES;
     const int c0 = warp * per;
     const int c1 = min(a.nc, c0 + per);
-    // box rows of this tile.  prefetch_box = 2: warp 0 loads them into registers up front, so the epilogue of a tile
+    // box rows of this tile.  prefetch_box = 3: warp 0 loads them into registers up front, so the epilogue of a tile
     // with candidates has no dependent memory round trip left (the kernel's tail is such an epilogue);
-    // 1: only pull them towards L2; 0: load on demand.
+    // 2: only pull them towards L2; 1: load on demand.
     float d[4][VEC];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -142,9 +133,9 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
         }
     };
     if (warp == 0 && active) {
-        if (a.prefetch_box == 2) {
+        if (a.prefetch_box == 3) {
             load_box();
-        } else if (a.prefetch_box == 1) {
+        } else if (a.prefetch_box == 2) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * g + a0));
         }
@@ -197,7 +188,7 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
     int off = warp_excl_scan(__popc(flags), lane, &total);
     if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
     if (flags) {
-        if (a.prefetch_box != 2) load_box();
+        if (a.prefetch_box != 3) load_box();
         const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE;
         const float fs = (float)L.stride;
         // this epilogue is the kernel's tail (a lone warp, every instruction at full latency): one division per
@@ -553,9 +544,15 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
     const int vec = yolo_pick_vec(p, inputs_dev);
     // The TMA pipeline scan splits every 128-anchor stage over four warps of 32 anchors, i.e. it runs on the
     // 32-cell tile layout (the same one as the scalar kernels, which are its fallback).
-    const bool pipe = g_use_pipe && p->variant == TRTX_YOLO_V8 && vec == 4 && yolo_pipe_supported(p, inputs_dev);
+    if (p->tune_class_slices < 0 || p->tune_rows_in_flight < 0 || p->tune_tma_stages < 0 || p->tune_box_prefetch < 0 ||
+        p->tune_box_prefetch > 3 || (p->tune_tma_pipeline != 0 && p->tune_tma_pipeline != 1))
+        return TRTX_ERR_INVALID;
+    const bool pipe = p->tune_tma_pipeline && p->variant == TRTX_YOLO_V8 && vec == 4 && yolo_pipe_supported(p, inputs_dev);
     YoloLayout L = yolo_layout(p, batch, pipe ? 1 : vec);
     L.pipe = pipe ? 1 : 0;
+    L.slices = p->tune_class_slices ? p->tune_class_slices : 2;
+    L.unroll = p->tune_rows_in_flight ? p->tune_rows_in_flight : 5;
+    L.pipe_stages = p->tune_tma_stages;
     if (workspace_bytes < L.total_bytes) return TRTX_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0) return TRTX_ERR_INVALID;
     memset(a, 0, sizeof(*a));
@@ -602,7 +599,7 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
         a->x_lo = 10.0f;
     else
         a->x_lo = logf(p->gate / (1.0f - p->gate)) - 0.05f;
-    a->prefetch_box = g_prefetch_box;
+    a->prefetch_box = p->tune_box_prefetch ? p->tune_box_prefetch : 2;
     a->tile_count = reinterpret_cast<int*>(static_cast<char*>(workspace_dev) + L.off_tile_count);
     a->cand = reinterpret_cast<float4*>(static_cast<char*>(workspace_dev) + L.off_cand);
     *Lo = L;
@@ -610,11 +607,11 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
 }
 
 template <typename T, int VEC>
-static void launch_v8(const YoloArgs& a, int grid, cudaStream_t st) {
+static int launch_v8(const YoloArgs& a, const YoloLayout& L, int grid, cudaStream_t st) {
 #define TRTX_V8_CASE(S, UU)                                                        \
-    if (g_slices == S && g_unroll == UU) {                                         \
+    if (L.slices == S && L.unroll == UU) {                                         \
         yolo_v8_scan_kernel<T, VEC, S, UU><<<grid, 32 * S, 0, st>>>(a);            \
-        return;                                                                    \
+        return TRTX_OK;                                                            \
     }
     TRTX_V8_CASE(1, 8)
     TRTX_V8_CASE(1, 16)
@@ -630,7 +627,7 @@ static void launch_v8(const YoloArgs& a, int grid, cudaStream_t st) {
     TRTX_V8_CASE(8, 5)
     TRTX_V8_CASE(8, 10)
 #undef TRTX_V8_CASE
-    yolo_v8_scan_kernel<T, VEC, 2, 5><<<grid, 64, 0, st>>>(a);
+    return TRTX_ERR_UNSUPPORTED;  // (slices, rows in flight) pair that is not built
 }
 
 int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {
@@ -640,17 +637,12 @@ int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int b
         if (rc != TRTX_ERR_UNSUPPORTED) return rc;  // else: scalar kernels on the same 32-cell layout
     }
     if (a.variant == TRTX_YOLO_V8) {
-        if (in_dtype == TRTX_F32) {
-            if (L.vec == 4)
-                launch_v8<float, 4>(a, grid, st);
-            else
-                launch_v8<float, 1>(a, grid, st);
-        } else {
-            if (L.vec == 4)
-                launch_v8<__half, 4>(a, grid, st);
-            else
-                launch_v8<__half, 1>(a, grid, st);
-        }
+        int rc;
+        if (in_dtype == TRTX_F32)
+            rc = L.vec == 4 ? launch_v8<float, 4>(a, L, grid, st) : launch_v8<float, 1>(a, L, grid, st);
+        else
+            rc = L.vec == 4 ? launch_v8<__half, 4>(a, L, grid, st) : launch_v8<__half, 1>(a, L, grid, st);
+        if (rc) return rc;
     } else {
         if (in_dtype == TRTX_F32) {
             if (L.vec == 4)
@@ -675,19 +667,15 @@ extern "C" {
 
 TRTX_API const char* trtx_version(void) { return "trtx_hot 0.1 (sm_100a)"; }
 TRTX_API int trtx_last_cuda_error(void) { return g_last_cuda_error; }
-
-// tuning knobs for the bench sweep (not part of the drop-in ABI):
-// 0 = class slices, 1 = unroll (register scan); 2 = use the TMA pipeline scan; 3 = its consumer warps
-TRTX_API int trtx_tune_set(int key, int value) {
-    if (key == 0) g_slices = value;
-    else if (key == 1) g_unroll = value;
-    else if (key == 2) g_use_pipe = value;
-    else if (key == 3) yolo_pipe_set_consumers(value);
-    else if (key == 4) yolo_pipe_set_debug(value);
-    else if (key == 5) g_prefetch_box = value;
-    else if (key == 6) preprocess_set_rows(value);
-    else return TRTX_ERR_INVALID;
-    return TRTX_OK;
+TRTX_API size_t trtx_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(trtx_yolo_params);
+        case 1: return sizeof(trtx_nms_params);
+        case 2: return sizeof(trtx_retina_params);
+        case 3: return sizeof(trtx_image_desc);
+        case 4: return sizeof(trtx_mask_params);
+        default: return 0;
+    }
 }
 
 TRTX_API int trtx_yolo_params_init_v8(trtx_yolo_params* p, int num_classes, int net_w, int net_h, int max_out,

@@ -52,6 +52,7 @@ struct YoloArgs {
 struct YoloLayout {
     int vec;
     int pipe;  // 1: the TMA pipeline scan runs on this layout (tile_cells = 32, four tiles per 128-anchor stage)
+    int slices, unroll, pipe_stages;  // launch tuning resolved from trtx_yolo_params.tune_* (per call, no global state)
     int tile_cells;
     int apc;
     int tiles_per_image;

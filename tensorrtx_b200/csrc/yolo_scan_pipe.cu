@@ -19,8 +19,7 @@
 //
 // The arithmetic is the same bit-exact running-max scheme as yolo_decode.cu::scan_classes.
 // HBM traffic = algorithmic bytes (every row is read exactly once); candidates add <= 4%.
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
-
+#include "tma.cuh"
 #include "yolo_layout.cuh"
 
 namespace trtx {
@@ -28,40 +27,6 @@ namespace trtx {
 constexpr int kTileAnchors = 64;   // anchors per TMA stage (box [1, C, 64]; 256-byte rows stream as fast as 512-byte ones)
 constexpr int kMaxStages = 15;     // 2 consumer warps per stage + the producer warp <= 32 warps
 
-// ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(tx) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                "selp.u32 %0, 1, 0, p;\n"
-                "}\n"
-                : "=r"(done)
-                : "r"(addr), "r"(parity)
-                : "memory");
-    } while (!done);
-}
-// TMA: global [B, C, g] box -> shared, bytes counted on `bar`
-__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                    smem_u32(dst_smem)),
-            "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-            : "memory");
-}
 struct alignas(64) TmaMaps {
     CUtensorMap m[TRTX_MAX_LEVELS];
 };
@@ -100,7 +65,7 @@ __device__ __forceinline__ float lds1<__half>(const __half* p) {
 template <typename T>
 __global__ void __launch_bounds__(1024, 1)
         yolo_v8_scan_pipe_kernel(const __grid_constant__ YoloArgs a, const __grid_constant__ TmaMaps maps,
-                                 const __grid_constant__ PipeGeom geo, int total_stiles, int stages, int stage_bytes, int dbg) {
+                                 const __grid_constant__ PipeGeom geo, int total_stiles, int stages, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -113,7 +78,7 @@ __global__ void __launch_bounds__(1024, 1)
             mbar_init(&full_bar[s], 1);           // producer's arrive.expect_tx
             mbar_init(&empty_bar[s], kSubWarps);  // the stage's consumer warps
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
@@ -158,9 +123,7 @@ __global__ void __launch_bounds__(1024, 1)
         st.bx[0] = active ? a.x_lo : INFINITY;  // TMA zero-fills columns past the level: those lanes never update
         st.b2[0] = st.bx[0];
         st.bc[0] = 0;
-        if (dbg == 1) {  // profiling aid: copy engine only
-            if (lane == 0 && cell0 < L.g) a.tile_count[(size_t)b * a.tiles_per_image + L.tile_begin + (cell0 >> 5)] = 0;
-        } else if (cell0 < L.g) {
+        if (cell0 < L.g) {
             // Fast path: one max over a group of U class rows and ONE compare/branch per group (fmaxf ignores NaN,
             // exactly like the reference's `p > max` never fires on NaN); the per-class update only runs for groups
             // whose max beats the running maximum logit, i.e. around real candidates.
@@ -206,28 +169,10 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
-static int g_pipe_debug = 0;  // tuning knob 4 (profiling aid): 1 = consumers only release the stages
-void yolo_pipe_set_debug(int v) { g_pipe_debug = v; }
-static int g_pipe_max_stages = kMaxStages;  // tuning knob 3: cap on stages (= consumer warps)
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encoder() {
-    static EncodeTiledFn fn = nullptr;  // process-wide driver entry point; resolving it twice is harmless
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
 
 template <typename T>
 static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaStream_t st) {
-    EncodeTiledFn enc = get_encoder();
+    EncodeTiledFn enc = tma_encoder();
     if (!enc) return TRTX_ERR_UNSUPPORTED;
     int dev = 0, sms = 0, max_smem = 0;
     cudaGetDevice(&dev);
@@ -235,7 +180,7 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int stage_bytes = a.C * kTileAnchors * (int)sizeof(T);
     const int fixed = 2 * kMaxStages * (int)sizeof(uint64_t);
-    int stages = g_pipe_max_stages < kMaxStages ? g_pipe_max_stages : kMaxStages;
+    int stages = L.pipe_stages >= 2 && L.pipe_stages < kMaxStages ? L.pipe_stages : kMaxStages;  // tune_tma_stages
     if (stages * kSubWarps + 1 > 32) stages = 31 / kSubWarps;  // 1024-thread CTA limit
     while (stages >= 2 && (size_t)stages * stage_bytes + fixed + 128 > (size_t)max_smem) --stages;
     if (stages < 2) return TRTX_ERR_UNSUPPORTED;
@@ -262,11 +207,9 @@ static int launch_pipe(const YoloArgs& a, const YoloLayout& L, int batch, cudaSt
     const int grid = total_stiles < sms ? total_stiles : sms;
     auto kern = yolo_v8_scan_pipe_kernel<T>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, 32 * (stages * kSubWarps + 1), smem, st>>>(a, maps, geo, total_stiles, stages, stage_bytes, g_pipe_debug);
+    kern<<<grid, 32 * (stages * kSubWarps + 1), smem, st>>>(a, maps, geo, total_stiles, stages, stage_bytes);
     return check_launch();
 }
-
-void yolo_pipe_set_consumers(int n) { g_pipe_max_stages = n < 2 ? 2 : n; }
 
 bool yolo_pipe_supported(const trtx_yolo_params* p, const void* const* inputs_dev) {
     if (p->variant != TRTX_YOLO_V8) return false;
@@ -278,7 +221,7 @@ bool yolo_pipe_supported(const trtx_yolo_params* p, const void* const* inputs_de
         if (inputs_dev && reinterpret_cast<uintptr_t>(inputs_dev[l]) % 16 != 0) return false;
         if (g % (p->in_dtype == TRTX_F16 ? 8 : 4) != 0) return false;
     }
-    return get_encoder() != nullptr;
+    return tma_encoder() != nullptr;
 }
 
 int yolo_scan_pipe_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int batch, cudaStream_t st) {

@@ -37,6 +37,8 @@ class DetectionPipeline:
         self.d2h_bytes = self.out_host.numel() * 4
         # descriptors of the (persistent) device frame buffers are built once, not per step
         self.pre = PreprocessPlan(list(self.frames_dev.unbind(0)), self.net_input, net_w, net_h)
+        # decode + NMS of the heads run on a high-priority side stream next to the letterbox (see run_device)
+        self._side = torch.cuda.Stream(self.device, priority=-1) if self.device.type == "cuda" else None
 
     def run(self, frames_host: torch.Tensor, heads: Sequence[torch.Tensor] | None = None, stream=None) -> torch.Tensor:
         """frames_host: pinned uint8 [B, H, W, 3] BGR.  heads: the backbone's per-stride outputs when no
@@ -49,10 +51,25 @@ class DetectionPipeline:
         self.out_host.copy_(out, non_blocking=True)
         return self.out_host
 
-    def run_device(self, heads: Sequence[torch.Tensor], stream=None) -> torch.Tensor:
-        """Device-resident step: pre-process the frames already in HBM + decode + NMS (no host copies)."""
-        self.pre.enqueue(stream)
-        out, _ = self.fused.enqueue(self.batch, heads, stream)
+    def run_device(self, heads: Sequence[torch.Tensor], stream=None, overlap: bool = True) -> torch.Tensor:
+        """Device-resident step: pre-process the frames already in HBM + decode + NMS (no host copies).
+
+        The letterbox of this batch does not depend on the decode/NMS of the head tensors (with a real backbone the heads
+        of batch i are decoded while the frames of batch i+1 are pre-processed), so the two halves are issued as
+        parallel branches: scan -> NMS on a high-priority side stream forked from the current stream, the letterbox on
+        the current stream, joined at the end.  Captured into a CUDA graph this becomes two concurrent branches; the
+        latency-bound NMS (one CTA per image, 32 of 148 SMs) then runs underneath the HBM-bound letterbox instead of
+        after it."""
+        if not overlap or self._side is None or stream is not None:
+            self.pre.enqueue(stream)
+            out, _ = self.fused.enqueue(self.batch, heads, stream)
+            return out
+        cur = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur)                  # fork
+        with torch.cuda.stream(self._side):
+            out, _ = self.fused.enqueue(self.batch, heads)
+        self.pre.enqueue()
+        cur.wait_stream(self._side)                  # join
         return out
 
     # ---- overlapped host pipeline: H2D of batch i+1 runs on a copy stream while batch i is decoded ----

@@ -43,6 +43,13 @@ def _stream(stream=None) -> int:
     return int(stream)
 
 
+def _tune(params, slices: int = 0, rows: int = 0, tma: int = 0, stages: int = 0, box: int = 0) -> None:
+    """Per-plugin launch tuning of the scan kernel (trtx_yolo_params.tune_*; 0 = default).  Plain data inside the
+    plugin's own parameter block -- nothing global, clones / other plugins are unaffected."""
+    params.tune_class_slices, params.tune_rows_in_flight = int(slices), int(rows)
+    params.tune_tma_pipeline, params.tune_tma_stages, params.tune_box_prefetch = int(tma), int(stages), int(box)
+
+
 def float_le_threshold(x: float) -> float:
     """Largest fp32 t with t <= x: `(double)conf <= x`  <=>  `conf <= t` in fp32 (retinaface 0.1 / 0.02 literals)."""
     t = struct.unpack("f", struct.pack("f", x))[0]
@@ -90,6 +97,10 @@ class YoloLayerPlugin:
         self.params = p
 
     # ---- IPluginV2 surface ----
+    def tune(self, **kw) -> "YoloLayerPlugin":
+        _tune(self.params, **kw)
+        return self
+
     def getNbOutputs(self) -> int:
         return 1
 
@@ -251,6 +262,10 @@ class YoloLayerPluginV5:
         p.gate = 0.1  # kIgnoreThresh, yolov5/src/config.h:38
         p.in_dtype = in_dtype
         self.params = p
+
+    def tune(self, **kw) -> "YoloLayerPlugin":
+        _tune(self.params, **kw)
+        return self
 
     def getNbOutputs(self) -> int:
         return 1

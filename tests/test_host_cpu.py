@@ -28,9 +28,28 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.trtx_version()
     out = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
-    assert declared <= exported
-    # nothing but the C ABI (and the tuning knob) is exported: no C++ symbols leak
-    assert all(s.startswith("trtx_") for s in exported), [s for s in exported if not s.startswith("trtx_")]
+    # exactly the declared C ABI is exported: no C++ symbols, no undeclared tuning / profiling hooks
+    assert declared == exported, declared ^ exported
+
+
+def test_no_mutable_globals_and_struct_sizes_match_the_binding():
+    """SURVEY 8b "Threading": enqueue must not depend on process-global mutable state.  The launch tuning lives in
+    trtx_yolo_params (per call); the only writable data of the library is the thread-local last-error slot and lazily
+    resolved driver entry points.  Also: the ctypes mirrors have the size the library was compiled with."""
+    import ctypes as C
+
+    from tensorrtx_b200 import _lib as L
+
+    lib = L.load()
+    for which, st in enumerate((L.YoloParams, L.NmsParams, L.RetinaParams, L.ImageDesc, L.MaskParams)):
+        assert lib.trtx_abi_sizeof(which) == C.sizeof(st), st.__name__
+    assert lib.trtx_abi_sizeof(99) == 0
+    out = subprocess.run(["nm", "-C", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    writable = [l.split(maxsplit=2)[2] for l in out.splitlines()
+                if len(l.split(maxsplit=2)) == 3 and l.split()[1] in ("b", "B", "d", "D") and "trtx::" in l]
+    # thread-local error slot; function-local static holding the driver entry point of cuTensorMapEncodeTiled
+    allowed = ("g_last_cuda_error", "tma_encoder", "guard variable")
+    assert all(any(a in w for a in allowed) for w in writable), writable
 
 
 def test_no_torch_types_in_abi():

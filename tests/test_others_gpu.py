@@ -148,7 +148,7 @@ def test_rcnn_workspace_idiom(dev):
 
 
 # ------------------------------------------------------------------ pre-process ---------------
-@pytest.mark.parametrize("h,w", [(640, 640), (1080, 1920), (517, 333), (64, 48)])
+@pytest.mark.parametrize("h,w", [(640, 640), (1080, 1920), (517, 333), (64, 48), (640, 480), (400, 640), (640, 636)])
 @pytest.mark.parametrize("odt", [torch.float32, torch.float16])
 def test_letterbox_parity(oracle, dev, h, w, odt):
     B = 3

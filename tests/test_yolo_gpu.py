@@ -124,19 +124,27 @@ def test_v8_fp16_inputs(oracle, dev):
 
 @pytest.mark.parametrize("slices,unroll", [(1, 8), (1, 16), (2, 4), (2, 8), (2, 10), (2, 20), (4, 4), (4, 5), (4, 10), (4, 20), (8, 5), (8, 10)])
 def test_v8_all_register_scan_variants(oracle, dev, slices, unroll):
-    lib = L.load()
     heads = synth.yolov8_heads(2, seed=11)
     ref, _ = oracle.yolov8_decode(heads)
-    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
-    try:
-        lib.trtx_tune_set(2, 0)  # register-path scan instead of the TMA pipeline
-        lib.trtx_tune_set(0, slices)
-        lib.trtx_tune_set(1, unroll)
-        got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
-    finally:
-        lib.trtx_tune_set(0, 2)
-        lib.trtx_tune_set(1, 5)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32)).tune(slices=slices, rows=unroll)
+    got = _decode_gpu(plug, _to_dev(heads, dev), 2, dev)
     _check_rows(got, ref, 2, 90, 6, 1000)
+
+
+def test_v8_unbuilt_tuning_is_refused_and_tunings_are_per_plugin(oracle, dev):
+    """trtx_yolo_params.tune_* is per-call data: a pair that is not built -> TRTX_ERR_UNSUPPORTED (no silent default),
+    and two plugins with different tunings used alternately give the same (oracle) rows -- no shared state."""
+    heads = synth.yolov8_heads(2, seed=14)
+    hd = _to_dev(heads, dev)
+    ref, _ = oracle.yolov8_decode(heads)
+    bad = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32)).tune(slices=3, rows=7)
+    out = torch.zeros((2, bad.output_elems()), dtype=torch.float32, device=dev)
+    ws = torch.empty(bad.getWorkspaceSize(2), dtype=torch.uint8, device=dev)
+    assert bad.enqueue(2, hd, [out], ws) == L.ERR_UNSUPPORTED
+    a = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32)).tune(slices=4, rows=10, box=3)
+    b = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32)).tune(tma=1, stages=3)
+    for plug in (a, b, a, b):
+        _check_rows(_decode_gpu(plug, hd, 2, dev), ref, 2, 90, 6, 1000)
 
 
 @pytest.mark.parametrize("consumers", [2, 3, 15])  # cap on pipeline stages
@@ -144,20 +152,13 @@ def test_v8_all_register_scan_variants(oracle, dev, slices, unroll):
 @pytest.mark.parametrize("B", [1, 7, 40])
 def test_v8_tma_pipeline_scan(oracle, dev, consumers, dtype, B):
     """The persistent TMA-fed scan (yolo_scan_pipe.cu): every CTA loops over many tiles, stages wrap around."""
-    lib = L.load()
     heads = synth.yolov8_heads(B, seed=13 + B, n_obj=40)
     if dtype == "f16":
         heads = [h.astype(np.float16).astype(np.float32) for h in heads]
     ref, _ = oracle.yolov8_decode(heads)
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32),
-                             in_dtype=L.F16 if dtype == "f16" else L.F32)
-    try:
-        lib.trtx_tune_set(2, 1)
-        lib.trtx_tune_set(3, consumers)
-        got = _decode_gpu(plug, _to_dev(heads, dev, torch.float16 if dtype == "f16" else torch.float32), B, dev)
-    finally:
-        lib.trtx_tune_set(3, 15)
-        lib.trtx_tune_set(2, 0)
+                             in_dtype=L.F16 if dtype == "f16" else L.F32).tune(tma=1, stages=consumers)
+    got = _decode_gpu(plug, _to_dev(heads, dev, torch.float16 if dtype == "f16" else torch.float32), B, dev)
     _check_rows(got, ref, B, 90, 6, 1000)
 
 
@@ -171,21 +172,13 @@ def test_first_argmax_on_sigmoid_collisions(oracle, dev):
     h[0, 4 + 20, 200] = 6.0000  # exact tie -> first class wins
     ref, _ = oracle.yolov8_decode(heads)
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
-    lib = L.load()
-    try:
-        for pipe, slices, unroll in ((1, 2, 5), (0, 2, 5), (0, 4, 10), (0, 1, 8)):
-            lib.trtx_tune_set(2, pipe)
-            lib.trtx_tune_set(0, slices)
-            lib.trtx_tune_set(1, unroll)
-            got = _decode_gpu(plug, _to_dev(heads, dev), 1, dev)
-            assert got[0, 0] == ref[0, 0] == 2
-            g = got[0, 1:181].reshape(2, 90)
-            assert g[0, 5] == 3 and g[1, 5] == 20
-            _check_rows(got, ref, 1, 90, 6, 1000)
-    finally:
-        lib.trtx_tune_set(2, 0)
-        lib.trtx_tune_set(0, 2)
-        lib.trtx_tune_set(1, 5)
+    for pipe, slices, unroll in ((1, 2, 5), (0, 2, 5), (0, 4, 10), (0, 1, 8)):
+        plug.tune(tma=pipe, slices=slices, rows=unroll)
+        got = _decode_gpu(plug, _to_dev(heads, dev), 1, dev)
+        assert got[0, 0] == ref[0, 0] == 2
+        g = got[0, 1:181].reshape(2, 90)
+        assert g[0, 5] == 3 and g[1, 5] == 20
+        _check_rows(got, ref, 1, 90, 6, 1000)
 
 
 # ------------------------------------------------------------------ NMS ------------------------
@@ -314,28 +307,58 @@ def test_nms_obb_oneshot_mode(oracle, dev):
         assert np.array_equal(rows[i, [0, 1, 2, 3, 4, 5, 7]], exp_rows[idx[0, i], [0, 1, 2, 3, 4, 5, 7]])
 
 
-def test_nms_topk_select_when_overflowing(oracle, dev):
-    # fused path with > max_out candidates above conf_thresh: the top max_out by conf enter NMS
-    B = 1
+def test_overflow_fused_equals_two_stage_equals_oracle(oracle, dev):
+    """More candidates than the plugin capacity (max_out): the reference plugin keeps the first max_out that grab a slot
+    (yololayer.cu:206-208; ours: ascending anchor order) and nms() filters those.  The fused call, the two-stage call
+    (plugin buffer -> batch_nms) and the oracle (decode with the same capacity -> nms) must give the same rows."""
+    B = 2
     heads = synth.yolov8_heads(B, seed=41, n_obj=300)
-    big, big_idx = oracle.yolov8_decode(heads, max_out=8400)
-    n_all = int(big[0, 0])
-    rows = big[0, 1:1 + n_all * 90].reshape(n_all, 90)
-    valid = np.where(rows[:, 4] > 0.5)[0]
-    assert len(valid) > 1000
-    order = sorted(valid, key=lambda i: (-rows[i, 4], big_idx[0, i]))[:1000]   # ties -> smaller anchor id
-    order = sorted(order)                                                       # back to anchor order
-    sub = np.zeros((1 + 1000 * 90,), np.float32)
-    sub[0] = 1000
-    sub[1:].reshape(1000, 90)[:] = rows[order]
-    res, src = oracle.nms(0, sub, 1000, 90, 0.5, 0.45)
-    exp_anchor = big_idx[0][np.asarray(order)[src]]
+    hd = _to_dev(heads, dev)
+    ref, ref_idx = oracle.yolov8_decode(heads)
+    assert ref[:, 0].min() > 1000
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
     fused = P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev)
-    comp, idx = fused.enqueue(B, _to_dev(heads, dev))
-    n = int(comp[0, 0].item())
-    assert n == len(res)
-    assert np.array_equal(idx[0, :n].cpu().numpy(), exp_anchor)
+    comp, idx = fused.enqueue(B, hd)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    out = torch.zeros((B, plug.output_elems()), dtype=torch.float32, device=dev)
+    ws = torch.empty(plug.getWorkspaceSize(B), dtype=torch.uint8, device=dev)
+    assert plug.enqueue(B, hd, [out], ws) == 0
+    two = P.batch_nms(out, B, plug.output_elems(), 0.5, 0.45).cpu().numpy()
+    assert np.array_equal(two, comp)                      # identical bytes, both paths
+    for b in range(B):
+        one = ref[b].copy()
+        one[0] = min(one[0], 1000)                        # the host reader must not run past the buffer (count is clamped)
+        res, src = oracle.nms(0, one, 1000, 90, 0.5, 0.45)
+        n = int(comp[b, 0])
+        assert n == len(res) and n > 20
+        assert np.array_equal(idx[b, :n], ref_idx[b][src])
+        np.testing.assert_allclose(comp[b, 1:1 + n * 7].reshape(n, 7)[:, :6], res[:, :6], atol=ATOL, rtol=0)
+
+
+def test_nms_row_cap_above_2048_rows(oracle, dev):
+    """trtx_nms_enqueue with max_rows > TRTX_NMS_MAX_ROWS (2048): the 2048 highest-confidence rows above conf_thresh enter
+    NMS (documented in trtx_hot.h; the reference has no cap).  3000 rows above the threshold, distinct confidences."""
+    rng = np.random.default_rng(77)
+    n_rows, F = 3000, 15
+    buf = np.zeros((1, 1 + n_rows * F), np.float32)
+    buf[0, 0] = n_rows
+    rows = buf[0, 1:].reshape(n_rows, F)
+    cx, cy = rng.uniform(50, 590, n_rows), rng.uniform(50, 590, n_rows)
+    w, h = rng.uniform(8, 60, n_rows), rng.uniform(8, 60, n_rows)
+    rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3] = cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2
+    rows[:, 4] = rng.permutation(n_rows).astype(np.float32) / n_rows * 0.8 + 0.15   # all > 0.1, distinct
+    rows[:, 5:] = rng.standard_normal((n_rows, 10))
+    top = np.sort(np.argsort(-rows[:, 4], kind="stable")[:2048])
+    sub = np.zeros(1 + 2048 * F, np.float32)
+    sub[0] = 2048
+    sub[1:].reshape(2048, F)[:] = rows[top]
+    res, src = oracle.nms(2, sub, 2048, F, 0.1, 0.4)
+    comp, idx = P.batch_nms(torch.from_numpy(buf).to(dev), 1, buf.shape[1], 0.1, 0.4, det_floats=F, box_format=L.BOX_RETINA,
+                            max_det=2048, return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    n = int(comp[0, 0])
+    assert n == len(res) and n > 100
+    assert np.array_equal(idx[0, :n], top[src])
 
 
 # ------------------------------------------------------------------ v5 -------------------------

@@ -14,7 +14,6 @@ for (h, w) in ((640, 640), (1080, 1920)):
         dst = torch.empty((B, 3, 640, 640), dtype=odt, device=dev)
         plans = [P.PreprocessPlan(list(f.unbind(0)), dst, 640, 640) for f in frames]
         for rows in (0,):
-            lib.trtx_tune_set(6, rows)
             for i in range(10):
                 plans[i % len(plans)].enqueue()
             torch.cuda.synchronize()

@@ -1,4 +1,6 @@
-"""Phase timing of nms_kernel from clock64 stamps (thread 0 of every CTA)."""
+"""Phase timing of nms_kernel from clock64 stamps (thread 0 of every CTA).
+Needs the probe build of the library: python -c "from tensorrtx_b200 import build; build.build(probe=True)" writes
+tensorrtx_b200/lib/libtrtx_hot_probe.so (release builds carry no stamps); run with TRTX_LIB=<that path>."""
 import sys
 from pathlib import Path
 import torch
@@ -13,7 +15,9 @@ plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 1
 fused = P.FusedYoloDecodeNms(plug, B, device=dev)
 dbg = torch.zeros(B * 16, dtype=torch.int64, device=dev)
 fused.enqueue(B, heads); torch.cuda.synchronize()
-lib.trtx_tune_set_ptr(dbg.data_ptr())
+import ctypes as C
+lib.trtx_probe_set_nms_stamps.argtypes = [C.c_void_p]
+lib.trtx_probe_set_nms_stamps(dbg.data_ptr())
 # stamp ids in program order (nms.cu TRTX_STAMP): label = phase that ends at the stamp
 order = [(0, "start"), (1, "A collect+stash"), (2, "C sort"), (8, "D permute"), (3, "E segment table"),
          (4, "E long segments"), (9, "E unit list"), (7, "E IoU bitmaps"), (5, "E resolve"), (6, "F output")]
@@ -25,7 +29,7 @@ for _ in range(N):
     for k in range(1, len(order)):
         acc[k] += (d[:, order[k][0]] - d[:, order[k - 1][0]]).mean().item()
     acc[0] += (d[:, 6] - d[:, 0]).max().item()
-lib.trtx_tune_set_ptr(None)
+lib.trtx_probe_set_nms_stamps(None)
 for k in range(1, len(order)):
     v = acc[k].item() / N
     print(f"{order[k][1]:24s} {v:10.0f} cycles  {v / 1965.0:7.2f} us")

@@ -1,4 +1,4 @@
-"""Probe the TMA pipeline scan: copy-only mode vs full, stages sweep, background-only vs dense data."""
+"""Probe the TMA pipeline scan: stages sweep, background-only vs dense data."""
 import json, sys
 from pathlib import Path
 import torch
@@ -20,10 +20,8 @@ for name, nobj in (("dense(64 obj)", 64), ("background only", 0)):
     sets = [[torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=i, n_obj=nobj)] for i in range(R)]
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-    for dbg in (1, 0):
-        for stages in (5, 8, 10, 12, 15):
-            lib.trtx_tune_set(2, 1); lib.trtx_tune_set(3, stages); lib.trtx_tune_set(4, dbg)
-            print(json.dumps({"data": name, "copy_only": dbg, "stages": stages, "us": round(timeit(fused, sets), 2)}), flush=True)
-    lib.trtx_tune_set(4, 0); lib.trtx_tune_set(3, 8); lib.trtx_tune_set(2, 0); lib.trtx_tune_set(0, 4); lib.trtx_tune_set(1, 5)
+    for stages in (5, 8, 10, 12, 15):   # (the copy-only mode of round 1 lives on in tools/tma_bench.cu)
+        plug.tune(tma=1, stages=stages)
+        print(json.dumps({"data": name, "stages": stages, "us": round(timeit(fused, sets), 2)}), flush=True)
+    plug.tune(slices=4, rows=5)
     print(json.dumps({"data": name, "register_kernel_4x5_us": round(timeit(fused, sets), 2)}), flush=True)
-    lib.trtx_tune_set(2, 1)

@@ -20,11 +20,9 @@ for name, nobj in (("dense", 64), ("typical(8 obj)", 8), ("background", 0)):
     sets = [[torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=i, n_obj=nobj)] for i in range(R)]
     plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
-    lib.trtx_tune_set(2, 0)
-    for pf in (1, 2):
-        lib.trtx_tune_set(5, pf)
+    for pf in (2, 3):
         for sl, u in ((4, 5), (2, 4), (2, 5), (2, 8), (1, 8), (1, 16)):
-            lib.trtx_tune_set(0, sl); lib.trtx_tune_set(1, u)
+            plug.tune(slices=sl, rows=u, box=pf)
             print(json.dumps({"data": name, "prefetch": pf, "slices": sl, "unroll": u, "us": round(timeit(fused, sets), 2)}), flush=True)
-    lib.trtx_tune_set(2, 1); lib.trtx_tune_set(3, 15)
+    plug.tune(tma=1, stages=15)
     print(json.dumps({"data": name, "pipe_us": round(timeit(fused, sets), 2)}), flush=True)

@@ -24,12 +24,9 @@ for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
     fused = P.FusedYoloDecodeNms(plug, B, device=dev)
     for slices, unroll in [(-1, 15), (1, 8), (1, 16), (2, 5), (2, 10), (2, 20), (4, 5), (4, 10), (4, 20), (8, 5)]:
         if slices < 0:   # TMA pipeline kernel, `unroll` = cap on stages (= consumer warps)
-            lib.trtx_tune_set(2, 1)
-            lib.trtx_tune_set(3, unroll)
+            plug.tune(tma=1, stages=unroll)
         else:
-            lib.trtx_tune_set(2, 0)
-            lib.trtx_tune_set(0, slices)
-            lib.trtx_tune_set(1, unroll)
+            plug.tune(slices=slices, rows=unroll)
         for i in range(10):
             fused.enqueue_scan(B, ss[i % R])
         torch.cuda.synchronize()
@@ -44,10 +41,6 @@ for dt, ss, nb in ((L.F32, sets, nbytes), (L.F16, sets16, nbytes // 2)):
              "GBps": round(nb / us / 1e3, 1)}
         res.append(r)
         print(json.dumps(r), flush=True)
-lib.trtx_tune_set(0, 2)
-lib.trtx_tune_set(1, 5)
-lib.trtx_tune_set(2, 0)
-lib.trtx_tune_set(3, 15)
 # NMS alone and preprocess alone
 plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32))
 fused = P.FusedYoloDecodeNms(plug, B, device=dev)
