@@ -58,17 +58,32 @@ TRTX_API size_t trtx_abi_sizeof(int which);
  *      yolov8/plugin/yololayer.cu:178-316 (anchor-free: yolov8, yolo11, yolov12, yolov13, yolov9/10 subsets)
  *      yolov5/plugin/yololayer.cu:161-227 (anchor-based: yolov5, yolov7, yolov5-lite, yolop)
  * ===================================================================================== */
-enum { TRTX_YOLO_V8 = 0, TRTX_YOLO_V5 = 1 };
+enum {
+    TRTX_YOLO_V8 = 0,
+    TRTX_YOLO_V5 = 1,
+    /* SURVEY 8f rank 4 -- older / other YoloLayer variants through the same scan / pack / NMS kernels: */
+    TRTX_YOLO_V3 = 2,  /* yolov3, yolov3-spp, yolov4 (yolov3-spp/yololayer.cu:148-191): anchor-based like V5, but box =
+                          ((col + sigmoid(x)) * stride, ..., exp(w) * anchor_w, ...), class AND objectness gated, rows of 7
+                          floats x,y,w,h, det_confidence, class_id, class_confidence (yololayer.h:47-53).  `strides` and
+                          `anchors` are both used; det_floats >= 7 */
+    TRTX_YOLO_V26 = 3, /* yolo26 NMS-free gatherKernel (yolo26/plugin/yololayer.cu:178-245): ONE input
+                          [batch, anchors, 4 + num_classes (+1 angle when is_obb)], row-major per anchor, scores are
+                          probabilities already; argmax `>` from (0, class -1), rows with score < gate dropped, 90-float
+                          rows, everything the kernel does not write is zero (the reference memsets the buffer).
+                          num_levels = 1, grid_h[0] * grid_w[0] = anchor count.  The reference decodes image 0 only
+                          (":185 TODO"); this build decodes every image of the batch */
+};
 enum { TRTX_F32 = 0, TRTX_F16 = 1 };
 
 typedef struct trtx_yolo_params {
-    int32_t variant;     /* TRTX_YOLO_V8 | TRTX_YOLO_V5 */
+    int32_t variant;     /* TRTX_YOLO_V8 | TRTX_YOLO_V5 | TRTX_YOLO_V3 | TRTX_YOLO_V26 */
     int32_t num_classes; /* combinedInfo[0] (yolov8/src/block.cpp:268) | netinfo[0] (yolov5/src/model.cpp:249) */
     int32_t net_w;       /* kInputW */
     int32_t net_h;       /* kInputH */
     int32_t max_out;     /* kMaxNumOutputBbox: capacity of the plugin output, rows per image */
     int32_t det_floats;  /* sizeof(Detection)/4 of the model dir: 90 (yolov8/include/types.h:4-12),
-                            38 (yolov5/src/types.h:11-16), 6 (yolov7/10/13) */
+                            38 (yolov5/src/types.h:11-16), 6 (yolov7/10/13: yolov7/include/types.h:11-16),
+                            7 (yolov3-spp/yololayer.h:47-53) */
     int32_t num_levels;  /* number of input tensors (strides) */
     int32_t grid_h[TRTX_MAX_LEVELS]; /* v8: net_h/stride (yololayer.cu:294); v5: YoloKernel.height */
     int32_t grid_w[TRTX_MAX_LEVELS];
@@ -79,7 +94,8 @@ typedef struct trtx_yolo_params {
     int32_t is_obb;      /* v8: rotated box */
     int32_t num_kpts;    /* combinedInfo[1] */
     float kpt_thresh;    /* combinedInfo[2] (int-truncated by the reference builder, block.cpp:271) */
-    float gate;          /* 0.1f: literal of yolov8 yololayer.cu:203 / kIgnoreThresh yolov5 config.h:38 */
+    float gate;          /* 0.1f: literal of yolov8 yololayer.cu:203 / kIgnoreThresh yolov5 config.h:38 / IGNORE_THRESH
+                            yolov3-spp yololayer.h:15; V26: the confidence threshold (d_confThreshold, yololayer.cu:9,32) */
     int32_t in_dtype;    /* TRTX_F32 (parity mode, what the reference accepts, yololayer.h:32-35) | TRTX_F16 */
     /* Launch tuning of the scan kernel.  Plain per-call data: the library keeps NO mutable state, so concurrent enqueues
      * (TensorRT calls enqueue() on clones from several threads, SURVEY 8b "Threading") with different tunings are
@@ -190,10 +206,19 @@ TRTX_API int trtx_yolo_nms_after_scan_enqueue(const trtx_yolo_params* p, const t
  * 3. Decode_TRT (RetinaFace) -- replaces retinaface/decode.cu:110-199
  *    inputs_dev[l] : [batch, 32, (in_h/s)*(in_w/s)] fp32, s = 8,16,32, channels [bbox 2x4 | cls 2x2 | lmk 2x10]
  *    output_dev    : [batch, 1 + total_priors*15] fp32, rows x1,y1,x2,y2,conf,lmk[10]
+ *    (TRTX_RETINA_ANTICOV: [batch, 38, g] inputs, [batch, 1 + total_priors*16] output)
  * ===================================================================================== */
+enum {
+    TRTX_RETINA_FACE = 0,    /* retinaface/decode.cu */
+    TRTX_RETINA_ANTICOV = 1, /* retinafaceAntiCov/decode.cu:110-172: inputs [batch, 38, g] =
+                                [cls 4 | bbox 2x4 | lmk 2x10 | type 6], all soft-maxed by the network; rows of 16 floats
+                                x1,y1,x2,y2,conf,lmk[10],mask_conf (decode.h:13-18); gate is the literal `conf < 0.5`;
+                                the reference decodes batch 1 only, this build every image */
+};
 typedef struct trtx_retina_params {
     int32_t in_h, in_w; /* decodeplugin::INPUT_H / INPUT_W (compile-time 480x640 in decode.h:16-17) */
-    float gate;         /* 0.02 (decode.cu:131); compared as `conf <= gate` */
+    float gate;         /* 0.02 (decode.cu:131); compared as `conf <= gate`.  Unused by TRTX_RETINA_ANTICOV */
+    int32_t variant;    /* TRTX_RETINA_FACE (0, what a zeroed struct selects) | TRTX_RETINA_ANTICOV */
 } trtx_retina_params;
 
 TRTX_API int trtx_retina_total_priors(const trtx_retina_params* p);

@@ -87,6 +87,43 @@ def retina_decode(heads, in_h=640, in_w=640, gate=0.02):
     return out, idx
 
 
+def yolov3_decode(heads, anchors, strides=(32, 16, 8), nc=80, max_out=1000, ignore_thresh=0.1):
+    """heads: per level [B, 3*(5+nc), gh, gw] in the given level order.  -> (out [B, 1+max_out*7], anchor_idx [B, max_out])."""
+    lib = load()
+    B = heads[0].shape[0]
+    gh = [h.shape[2] for h in heads]
+    gw = [h.shape[3] for h in heads]
+    flat = [np.ascontiguousarray(h.reshape(B, h.shape[1], -1), np.float32) for h in heads]
+    anc = np.ascontiguousarray(np.asarray(anchors, np.float32).reshape(-1))
+    out = np.zeros((B, 1 + max_out * 7), np.float32)
+    idx = np.full((B, max_out), -1, np.int32)
+    lib.oracle_yolov3_decode(_pp(flat), B, len(flat), _ia(gh), _ia(gw), _ia(strides), anc.ctypes.data_as(C.c_void_p), nc,
+                             max_out, C.c_float(ignore_thresh), out.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p))
+    return out, idx
+
+
+def yolo26_gather(rows, nc=80, obb=False, max_out=300, det_floats=90, conf_thresh=0.4):
+    """rows [B, A, 4+nc(+1)] -> (out [B, 1+max_out*det_floats], anchor_idx [B, max_out])."""
+    lib = load()
+    x = np.ascontiguousarray(rows, np.float32)
+    B, A = x.shape[0], x.shape[1]
+    out = np.zeros((B, 1 + max_out * det_floats), np.float32)
+    idx = np.full((B, max_out), -1, np.int32)
+    lib.oracle_yolo26_gather(x.ctypes.data_as(C.c_void_p), B, A, nc, int(obb), max_out, det_floats, C.c_float(conf_thresh),
+                             out.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p))
+    return out, idx
+
+
+def anticov_decode(heads, in_h=640, in_w=640):
+    lib = load()
+    B = heads[0].shape[0]
+    total = sum((in_h // s) * (in_w // s) * 2 for s in (8, 16, 32))
+    out = np.zeros((B, 1 + total * 16), np.float32)
+    idx = np.full((B, total), -1, np.int32)
+    lib.oracle_anticov_decode(_pp(heads), B, in_h, in_w, out.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p))
+    return out, idx
+
+
 def nms(variant, plugin_out_img, max_rows, det_floats, conf_thresh, nms_thresh):
     """One image. variant 0 v8 / 1 v5 / 2 retinaface / 3 v8-obb (nms_obb, probiou). -> (res [n, det_floats], src_row [n])."""
     lib = load()

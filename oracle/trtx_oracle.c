@@ -275,6 +275,171 @@ ORACLE_API void oracle_retina_decode(const float* const* inputs, int batch, int 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * YOLOv3 / v3-spp / v4 anchor-based decode.  Restates CalDetection,
+ * yolov3-spp/yololayer.cu:148-191 (yolov3, yolov4 carry the same kernel).
+ * inputs[l] : [B, 3*(5+classes), gh*gw] fp32 (:159-160), levels in the caller's order (the plugin's own order is
+ *             stride 32, 16, 8, yololayer.h:27-44); anchors[l*6 + 2k (+1)]; strides[l].
+ * out rows  : Detection of yololayer.h:47-53 = x,y,w,h, det_confidence, class_id, class_confidence -> 7 floats.
+ * Class loop first (all classes, sigmoid, strict `>` from 0), THEN both gates (:171), exp() for w/h (:185-186).
+ * Flat anchor id = level_off + cell*3 + k.
+ * ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_yolov3_decode(const float* const* inputs, int batch, int num_levels, const int* grid_h,
+                                     const int* grid_w, const int* strides, const float* anchors, int classes, int max_out,
+                                     float ignore_thresh, float* out, int32_t* anchor_idx) {
+    const int det_floats = 7;
+    const int out_elem = 1 + max_out * det_floats;
+    const int info_len_i = 5 + classes;
+    memset(out, 0, sizeof(float) * (size_t)batch * out_elem);
+    int level_off = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const int yw = grid_w[l], yh = grid_h[l];
+        const int total_grid = yw * yh;
+        const float* anc = anchors + l * 6;
+        for (int t = 0; t < batch * total_grid; ++t) {
+            const int bn = t / total_grid;
+            const int idx = t - total_grid * bn;
+            const float* cur = inputs[l] + (size_t)bn * ((size_t)info_len_i * total_grid * 3);
+            float* o = out + (size_t)bn * out_elem;
+            for (int k = 0; k < 3; ++k) {
+                const float* ck = cur + (size_t)k * info_len_i * total_grid;
+                int class_id = 0;
+                float max_cls_prob = 0.0f;
+                for (int i = 5; i < info_len_i; ++i) { /* :162-168 */
+                    float p = logist(ck[idx + (size_t)i * total_grid]);
+                    if (p > max_cls_prob) {
+                        max_cls_prob = p;
+                        class_id = i - 5;
+                    }
+                }
+                float box_prob = logist(ck[idx + 4 * (size_t)total_grid]);             /* :170 */
+                if (max_cls_prob < ignore_thresh || box_prob < ignore_thresh) continue; /* :171 */
+                int count = (int)o[0];
+                o[0] += 1.0f;                /* :174 */
+                if (count >= max_out) break; /* :175 `return` */
+                float* det = o + 1 + (size_t)count * det_floats;
+                if (anchor_idx) anchor_idx[(size_t)bn * max_out + count] = level_off + idx * 3 + k;
+                const int row = idx / yw, col = idx % yw;
+                det[0] = (col + logist(ck[idx + 0 * (size_t)total_grid])) * strides[l]; /* :183-186 */
+                det[1] = (row + logist(ck[idx + 1 * (size_t)total_grid])) * strides[l];
+                det[2] = expf(ck[idx + 2 * (size_t)total_grid]) * anc[2 * k];
+                det[3] = expf(ck[idx + 3 * (size_t)total_grid]) * anc[2 * k + 1];
+                det[4] = box_prob;
+                det[5] = (float)class_id;
+                det[6] = max_cls_prob;
+            }
+        }
+        level_off += total_grid * 3;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * yolo26 NMS-free gather.  Restates gatherKernel, yolo26/plugin/yololayer.cu:178-245.
+ * input : [B, anchor_count, 4 + classes (+1 angle when is_obb)] fp32, ROW-major per anchor (AoS): xmin,ymin,xmax,ymax,
+ *         class confidences (already probabilities), angle.  The reference handles batch index 0 only (:185 "TODO"); the
+ *         restatement applies the same per-anchor code to every image.
+ * out   : [B, 1 + max_out*det_floats] (Detection of yolo26/include/types.h: 90 floats, the angle is the last one);
+ *         argmax: `conf > score` from score = 0, class_id = -1 (:201-209); gate `score < thresh` -> skip (:211).
+ * ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_yolo26_gather(const float* input, int batch, int anchor_count, int classes, int is_obb, int max_out,
+                                     int det_floats, float conf_thresh, float* out, int32_t* anchor_idx) {
+    const int out_elem = 1 + max_out * det_floats;
+    const int asz = (is_obb ? 5 : 4) + classes;
+    memset(out, 0, sizeof(float) * (size_t)batch * out_elem);
+    for (int b = 0; b < batch; ++b) {
+        float* o = out + (size_t)b * out_elem;
+        for (int idx = 0; idx < anchor_count; ++idx) {
+            const float* a = input + ((size_t)b * anchor_count + idx) * asz;
+            float score = 0.0f;
+            int class_id = -1;
+            for (int c = 0; c < classes; ++c) {
+                float conf = a[4 + c];
+                if (conf > score) {
+                    score = conf;
+                    class_id = c;
+                }
+            }
+            if (score < conf_thresh) continue;
+            int count = (int)o[0];
+            o[0] += 1.0f;
+            if (count >= max_out) continue;
+            float* det = o + 1 + (size_t)count * det_floats;
+            if (anchor_idx) anchor_idx[(size_t)b * max_out + count] = idx;
+            det[0] = a[0];
+            det[1] = a[1];
+            det[2] = a[2];
+            det[3] = a[3];
+            det[4] = score;
+            det[5] = (float)class_id;
+            if (is_obb) det[det_floats - 1] = a[4 + classes];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * RetinaFace anti-cov decode.  Restates CalDetection, retinafaceAntiCov/decode.cu:110-155 and
+ * forwardGpu :157-172, with INPUT_H/INPUT_W (decode.h:20-21) made runtime and the batch index added (the reference is
+ * batch 1 only: no image offset anywhere).
+ * inputs[l] : [B, 38, h*w] fp32 = [cls 4 (softmaxed in the network; face prob of anchor k at channel 2+k) | bbox 2x4 |
+ *             lmk 2x10 | type 6 (mask prob of anchor k at channel 36+k)] (:120-123)
+ * out rows  : x1,y1,x2,y2, class_confidence, lmk[10], mask_confidence -> 16 floats (decode.h:13-18)
+ * Literals 7.5, 0.2, 0.5 are doubles; `anchor * 2 / (k + 1)` is INTEGER arithmetic (:137).
+ * ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_anticov_decode(const float* const* inputs, int batch, int in_h, int in_w, float* out,
+                                      int32_t* anchor_idx) {
+    int total_priors = 0;
+    for (int s = 8; s <= 32; s *= 2) total_priors += (in_h / s) * (in_w / s) * 2;
+    const int out_elem = 1 + total_priors * 16;
+    memset(out, 0, sizeof(float) * (size_t)batch * out_elem);
+    int step = 8, anchor = 16, level_off = 0;
+    for (int l = 0; l < 3; ++l) {
+        const int h = in_h / step, w = in_w / step;
+        const int num_elem = h * w;
+        for (int bn = 0; bn < batch; ++bn) {
+            const float* input = inputs[l] + (size_t)bn * 38 * num_elem;
+            const float* cls_reg = input + 2 * (size_t)num_elem;
+            const float* bbox_reg = input + 4 * (size_t)num_elem;
+            const float* lmk_reg = input + 12 * (size_t)num_elem;
+            const float* mask_reg = input + 36 * (size_t)num_elem;
+            float* o = out + (size_t)bn * out_elem;
+            for (int idx = 0; idx < num_elem; ++idx) {
+                const int y = idx / w, x = idx % w;
+                for (int k = 0; k < 2; ++k) {
+                    float conf = cls_reg[idx + k * num_elem];
+                    if ((double)conf < 0.5) continue; /* :127 */
+                    int count = (int)o[0];
+                    o[0] += 1.0f;
+                    float* det = o + 1 + (size_t)count * 16;
+                    if (anchor_idx) anchor_idx[(size_t)bn * total_priors + count] = level_off + idx * 2 + k;
+                    float prior[4]; /* :134-138 */
+                    prior[0] = (float)(7.5 + (double)(float)(x * step));
+                    prior[1] = (float)(7.5 + (double)(float)(y * step));
+                    prior[2] = (float)(anchor * 2 / (k + 1));
+                    prior[3] = prior[2];
+                    det[0] = prior[0] + bbox_reg[idx + k * num_elem * 4] * prior[2]; /* :141-148 */
+                    det[1] = prior[1] + bbox_reg[idx + k * num_elem * 4 + num_elem] * prior[3];
+                    det[2] = prior[2] * expf(bbox_reg[idx + k * num_elem * 4 + num_elem * 2]);
+                    det[3] = prior[3] * expf(bbox_reg[idx + k * num_elem * 4 + num_elem * 3]);
+                    det[0] -= (det[2] - 1) / 2;
+                    det[1] -= (det[3] - 1) / 2;
+                    det[2] += det[0];
+                    det[3] += det[1];
+                    det[4] = conf;
+                    for (int i = 0; i < 10; i += 2) { /* :150-153: float * 0.2 is a double product */
+                        det[5 + i] = (float)(prior[0] + (double)lmk_reg[idx + k * num_elem * 10 + num_elem * i] * 0.2 * prior[2]);
+                        det[5 + i + 1] =
+                                (float)(prior[1] + (double)lmk_reg[idx + k * num_elem * 10 + num_elem * (i + 1)] * 0.2 * prior[3]);
+                    }
+                    det[15] = mask_reg[idx + k * num_elem];
+                }
+            }
+        }
+        level_off += num_elem * 2;
+        step *= 2;
+        anchor *= 4;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * CPU greedy NMS.  Restates
  *   variant 0 (v8) : yolov8/src/postprocess.cpp:71-121  iou ltrb, cmp conf desc then bbox[0] asc,
  *                    filter `conf <= thr || isnan(conf)`

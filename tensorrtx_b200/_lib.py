@@ -12,10 +12,11 @@ from pathlib import Path
 MAX_LEVELS = 8
 
 OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = range(5)
-YOLO_V8, YOLO_V5 = 0, 1
+YOLO_V8, YOLO_V5, YOLO_V3, YOLO_V26 = 0, 1, 2, 3
 F32, F16 = 0, 1
 BOX_LTRB, BOX_CXCYWH, BOX_RETINA, BOX_OBB = 0, 1, 2, 3
 NMS_GREEDY, NMS_ONESHOT = 0, 1
+RETINA_FACE, RETINA_ANTICOV = 0, 1
 
 _ERR = {1: "TRTX_ERR_INVALID", 2: "TRTX_ERR_WORKSPACE", 3: "TRTX_ERR_CUDA", 4: "TRTX_ERR_UNSUPPORTED"}
 
@@ -68,7 +69,7 @@ class NmsParams(C.Structure):
 
 
 class RetinaParams(C.Structure):
-    _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32), ("gate", C.c_float)]
+    _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32), ("gate", C.c_float), ("variant", C.c_int32)]
 
 
 class ImageDesc(C.Structure):

@@ -10,6 +10,11 @@
 //
 // The reference's literals 0.5, 0.1, 0.2 are doubles: those expressions are evaluated in fp64 here too
 // (a handful of DFMA per candidate; irrelevant for throughput).
+//
+// variant TRTX_RETINA_ANTICOV = retinafaceAntiCov/decode.cu:110-172 through the same two kernels: [B, 38, g] inputs
+// (cls 4 | bbox 8 | lmk 20 | type 6; the network already soft-maxed cls/type, :124-127), 2 cls rows streamed, pixel-unit
+// priors (7.5 + x*step, anchor*2/(k+1) in INTEGER arithmetic), 16-float rows ending in the mask confidence.  The
+// reference handles batch 1 only (no image offset); here every image of the batch is decoded.
 #include "common.cuh"
 
 namespace trtx {
@@ -23,6 +28,7 @@ struct RetinaLevel {
 };
 struct RetinaArgs {
     RetinaLevel lv[3];
+    int det_floats;  // 15 (retinaface/decode.h:11-15) | 16 (retinafaceAntiCov/decode.h:13-18)
     int tiles_per_image, slots_per_image, tile_cells;
     int in_h, in_w;
     float gate;
@@ -132,6 +138,96 @@ __global__ void __launch_bounds__(128) retina_scan_kernel(const __grid_constant_
     }
 }
 
+// retinafaceAntiCov/decode.cu:110-155.  Same tiling; the face probability of prior k is channel 2+k as it comes.
+template <int VEC>
+__global__ void __launch_bounds__(128) anticov_scan_kernel(const __grid_constant__ RetinaArgs a, int batch) {
+    constexpr int TILE = 32 * VEC;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (gw >= batch * a.tiles_per_image) return;
+    const int b = gw / a.tiles_per_image;
+    const int t = gw - b * a.tiles_per_image;
+    int l = 0;
+    while (l + 1 < 3 && t >= a.lv[l + 1].tile_begin) ++l;
+    const RetinaLevel& L = a.lv[l];
+    const int tile = t - L.tile_begin;
+    const int a0 = tile * TILE + lane * VEC;
+    const size_t g = (size_t)L.g;
+    const bool active = a0 < L.g;
+    const float* cur = L.in + (size_t)b * 38 * g;
+    const float* cls_reg = cur + 2 * g;  // :120
+    float c[2][VEC];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) c[r][j] = 0.0f;
+        if (active) {
+            if constexpr (VEC == 4) {
+                float4 v = ldg_stream_f4(cls_reg + (size_t)r * g + a0);
+                c[r][0] = v.x;
+                c[r][1] = v.y;
+                c[r][2] = v.z;
+                c[r][3] = v.w;
+            } else {
+                c[r][0] = ldg_stream_f1(cls_reg + (size_t)r * g + a0);
+            }
+        }
+    }
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)  // :127 `if (conf < 0.5) continue;` (0.5 is exact in fp32: the double compare is the float compare)
+            if (active && (a0 + j < L.g) && !(c[k][j] < 0.5f)) flags |= 1u << (j * 2 + k);
+    int total;
+    int off = warp_excl_scan(__popc(flags), lane, &total);
+    if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
+    if (!flags) return;
+    const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE * 2;
+    const float* bbox_reg = cur + 4 * g;
+    const float* lmk_reg = cur + 12 * g;
+    const float* mask_reg = cur + 36 * g;
+    const int step = a.in_w / L.w;  // 8, 16, 32 (:162-170)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!(flags & (1u << (j * 2 + k)))) continue;
+            const int idx = a0 + j;
+            const int y = idx / L.w, x = idx - y * L.w;
+            float prior[4];  // :134-138
+            prior[0] = (float)(7.5 + (double)(float)(x * step));
+            prior[1] = (float)(7.5 + (double)(float)(y * step));
+            prior[2] = (float)(L.anchor * 2 / (k + 1));
+            prior[3] = prior[2];
+            float d[16];
+            const float* br = bbox_reg + idx + (size_t)k * 4 * g;
+            d[0] = prior[0] + __ldg(br) * prior[2];  // :141-148 (float; contracted like the reference build)
+            d[1] = prior[1] + __ldg(br + g) * prior[3];
+            d[2] = prior[2] * expf(__ldg(br + 2 * g));
+            d[3] = prior[3] * expf(__ldg(br + 3 * g));
+            d[0] -= (d[2] - 1) / 2;
+            d[1] -= (d[3] - 1) / 2;
+            d[2] += d[0];
+            d[3] += d[1];
+            d[4] = c[k][j];
+            const float* lr = lmk_reg + idx + (size_t)k * 10 * g;
+#pragma unroll
+            for (int i = 0; i < 10; i += 2) {  // :150-153: `* 0.2` promotes to double
+                d[5 + i] = (float)(prior[0] + (double)__ldg(lr + (size_t)i * g) * 0.2 * prior[2]);
+                d[5 + i + 1] = (float)(prior[1] + (double)__ldg(lr + (size_t)(i + 1) * g) * 0.2 * prior[3]);
+            }
+            d[15] = __ldg(mask_reg + idx + (size_t)k * g);  // :154
+            float4* rec = reinterpret_cast<float4*>(a.cand + (slot0 + off) * 16);
+            rec[0] = make_float4(d[0], d[1], d[2], d[3]);
+            rec[1] = make_float4(d[4], d[5], d[6], d[7]);
+            rec[2] = make_float4(d[8], d[9], d[10], d[11]);
+            rec[3] = make_float4(d[12], d[13], d[14], d[15]);
+            ++off;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) retina_pack_kernel(const __grid_constant__ RetinaArgs a, float* __restrict__ out) {
     extern __shared__ int s_prefix[];
     const int b = blockIdx.x;
@@ -150,7 +246,8 @@ __global__ void __launch_bounds__(256) retina_pack_kernel(const __grid_constant_
         if (lane == 0) s_prefix[T_] = carry;
     }
     __syncthreads();
-    float* o = out + (size_t)b * (1 + (size_t)a.total_priors * 15);
+    const int F = a.det_floats;
+    float* o = out + (size_t)b * (1 + (size_t)a.total_priors * F);
     if (threadIdx.x == 0) o[0] = (float)s_prefix[T_];
     const int tile_slots = a.tile_cells * 2;
     for (int t = warp; t < T_; t += nwarps) {
@@ -160,10 +257,10 @@ __global__ void __launch_bounds__(256) retina_pack_kernel(const __grid_constant_
         while (l + 1 < 3 && t >= a.lv[l + 1].tile_begin) ++l;
         const size_t slot0 =
                 (size_t)b * a.slots_per_image + a.lv[l].slot_begin + (size_t)(t - a.lv[l].tile_begin) * tile_slots;
-        // n records x 15 floats, copied by the whole warp
-        for (int e = lane; e < n * 15; e += 32) {
-            const int j = e / 15, f = e - j * 15;
-            o[1 + (size_t)(s_prefix[t] + j) * 15 + f] = a.cand[(slot0 + j) * 16 + f];
+        // n records x F floats, copied by the whole warp
+        for (int e = lane; e < n * F; e += 32) {
+            const int j = e / F, f = e - j * F;
+            o[1 + (size_t)(s_prefix[t] + j) * F + f] = a.cand[(slot0 + j) * 16 + f];
         }
     }
 }
@@ -213,6 +310,7 @@ TRTX_API int trtx_retina_decode_enqueue(const trtx_retina_params* p, int batch, 
                                         trtx_stream_t stream) {
     if (!p || batch <= 0 || !inputs_dev || !output_dev || !workspace_dev) return TRTX_ERR_INVALID;
     if (p->in_h < 32 || p->in_w < 32) return TRTX_ERR_INVALID;
+    if (p->variant != TRTX_RETINA_FACE && p->variant != TRTX_RETINA_ANTICOV) return TRTX_ERR_INVALID;
     int vec = 4, step = 8;
     for (int l = 0; l < 3; ++l, step *= 2) {
         if (!inputs_dev[l]) return TRTX_ERR_INVALID;
@@ -242,9 +340,15 @@ TRTX_API int trtx_retina_decode_enqueue(const trtx_retina_params* p, int batch, 
     a.tile_count = static_cast<int*>(workspace_dev);
     a.cand = reinterpret_cast<float*>(static_cast<char*>(workspace_dev) + L.off_cand);
     a.total_priors = trtx_retina_total_priors(p);
+    a.det_floats = p->variant == TRTX_RETINA_ANTICOV ? 16 : 15;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = batch * L.tiles;
-    if (vec == 4)
+    if (p->variant == TRTX_RETINA_ANTICOV) {
+        if (vec == 4)
+            anticov_scan_kernel<4><<<(warps + 3) / 4, 128, 0, st>>>(a, batch);
+        else
+            anticov_scan_kernel<1><<<(warps + 3) / 4, 128, 0, st>>>(a, batch);
+    } else if (vec == 4)
         retina_scan_kernel<4><<<(warps + 3) / 4, 128, 0, st>>>(a, batch);
     else
         retina_scan_kernel<1><<<(warps + 3) / 4, 128, 0, st>>>(a, batch);

@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
 }
 
 // --------------------------------------------------------------------------------------------
-// Anchor-based scan (yolov5 family).  CTA = 4 warps over a tile of 32*VEC cells x 3 anchors.
+// Anchor-based scan (yolov5 family; variant TRTX_YOLO_V3 = yolov3 / v3-spp / v4, yolov3-spp/yololayer.cu:148-191: the
+// class probability is gated too (:171), boxes use exp() for w/h and the stride for x/y (:183-186), and the record's
+// spare float carries the class confidence).  CTA = 4 warps over a tile of 32*VEC cells x 3 anchors.
 // Objectness rows are read first; the class rows of anchor k are only streamed when some cell of
 // the tile passes the objectness gate for k (the reference skips its class loop per thread,
 // yololayer.cu:176-177; here the skip is per tile so that the loads stay coalesced).
@@ -336,12 +338,13 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
     }
     if (warp > 0) return;
     // ---- compaction in ascending (cell, k) order + box decode (yololayer.cu:188-208) ----
+    const bool v3 = a.variant == TRTX_YOLO_V3;
     unsigned flags = 0;
 #pragma unroll
     for (int j = 0; j < VEC; ++j)
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (s_obj[k][lane * VEC + j] >= 0.0f) flags |= 1u << (j * 3 + k);
+        for (int k = 0; k < 3; ++k)  // v3: `max_cls_prob < IGNORE_THRESH || box_prob < IGNORE_THRESH` -> skip
+            if (s_obj[k][lane * VEC + j] >= 0.0f && !(v3 && s_fp[k][lane * VEC + j] < a.gate)) flags |= 1u << (j * 3 + k);
     int total;
     int off = warp_excl_scan(__popc(flags), lane, &total);
     if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
@@ -355,6 +358,17 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
                     const int e = a0 + j;
                     const int row = e / L.gw, col = e - row * L.gw;
                     const T* ck = base + (size_t)k * ilen * g + e;
+                    if (v3) {  // yolov3-spp/yololayer.cu:183-189
+                        const float fs = (float)L.stride;
+                        const float bx = ((float)col + logist(Elem<T>::ld1_cached(ck))) * fs;
+                        const float by = ((float)row + logist(Elem<T>::ld1_cached(ck + g))) * fs;
+                        const float bw = expf(Elem<T>::ld1_cached(ck + 2 * g)) * L.anc[2 * k];
+                        const float bh = expf(Elem<T>::ld1_cached(ck + 3 * g)) * L.anc[2 * k + 1];
+                        store_record(a.cand, slot0 + off, bx, by, bw, bh, s_obj[k][lane * VEC + j], s_fc[k][lane * VEC + j],
+                                     L.slot_begin + e * 3 + k, s_fp[k][lane * VEC + j]);
+                        ++off;
+                        continue;
+                    }
                     float t0 = logist(Elem<T>::ld1_cached(ck));
                     float t1 = logist(Elem<T>::ld1_cached(ck + g));
                     float t2 = logist(Elem<T>::ld1_cached(ck + 2 * g));
@@ -373,6 +387,75 @@ __global__ void __launch_bounds__(128) yolo_v5_scan_kernel(const __grid_constant
                 }
             }
         }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// yolo26 NMS-free gather (variant TRTX_YOLO_V26, yolo26/plugin/yololayer.cu:178-245).  The input is row-major per anchor
+// ([B, A, C], C = 4 + classes (+ angle)), so a tile of 32 anchors is ONE contiguous block of 32*C floats: the warp
+// streams it with coalesced 128-bit loads into shared memory (row pitch C|1: conflict-free), then lane i scans the class
+// scores of anchor i with the reference's loop (`conf > score` from score = 0, class -1), gates (`score < thresh`) and
+// the survivors are ballot-compacted into the tile's slot range like every other scan.  HBM-bound: C*4 bytes per anchor.
+// --------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(128) yolo26_gather_kernel(const __grid_constant__ YoloArgs a, int batch, int warps_per_cta) {
+    extern __shared__ float s_rows[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * warps_per_cta + warp;
+    if (warp >= warps_per_cta || gw >= batch * a.tiles_per_image) return;
+    const int b = gw / a.tiles_per_image, t = gw - b * a.tiles_per_image;
+    const LevelArg& L = a.lv[0];
+    const int C = a.C, Cp = C | 1;
+    float* rows = s_rows + (size_t)warp * 32 * Cp;
+    const int a0 = t * 32;
+    const int n = min(32, L.g - a0);
+    const float* src = static_cast<const float*>(L.in) + ((size_t)b * L.g + a0) * C;
+    const int total = n * C;
+    if constexpr (VEC == 4) {
+        constexpr int U = 7;  // loads in flight per lane
+        for (int i0 = lane; i0 < total / 4; i0 += 32 * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + 32 * u < total / 4) v[u] = ldg_stream_f4(src + 4 * (size_t)(i0 + 32 * u));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = 4 * (i0 + 32 * u);
+                if (e < total) {
+                    const int r = e / C, c = e - r * C;  // C % 4 == 0: a float4 never straddles two anchors
+                    float* q = rows + r * Cp + c;
+                    q[0] = v[u].x;
+                    q[1] = v[u].y;
+                    q[2] = v[u].z;
+                    q[3] = v[u].w;
+                }
+            }
+        }
+    } else {
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / C, c = e - r * C;
+            rows[r * Cp + c] = ldg_stream_f1(src + e);
+        }
+    }
+    __syncwarp();
+    float score = 0.0f;  // :199-209
+    int cls = -1;
+    const float* mine = rows + lane * Cp;
+    if (lane < n) {
+        for (int c = 0; c < a.nc; ++c) {
+            const float conf = mine[4 + c];
+            if (conf > score) {
+                score = conf;
+                cls = c;
+            }
+        }
+    }
+    const bool keep = lane < n && !(score < a.gate);  // :211
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = __popc(bal);
+    if (keep) {
+        const size_t slot = (size_t)b * a.slots_per_image + a0 + __popc(bal & ((1u << lane) - 1u));
+        store_record(a.cand, slot, mine[0], mine[1], mine[2], mine[3], score, cls, a0 + lane, a.is_obb ? mine[4 + a.nc] : 0.0f);
     }
 }
 
@@ -470,6 +553,8 @@ __global__ void __launch_bounds__(256) yolo_pack_rows_kernel(const __grid_consta
     const int out_elem = 1 + a.max_out * a.det_floats;
     float* o = out + (size_t)b * out_elem;
     if (threadIdx.x == 0) o[0] = (float)min(total, a.max_out);  // clamped (see trtx_hot.h)
+    if (a.variant == TRTX_YOLO_V26)  // yolo26/plugin/yololayer.cu:258: the whole buffer is memset before the gather
+        for (int i = min(total, a.max_out) * a.det_floats + threadIdx.x; i < a.max_out * a.det_floats; i += blockDim.x) o[1 + i] = 0.0f;
     const int tile_slots = a.tile_cells * a.apc;
     for (int t = warp; t < T_; t += nwarps) {
         const int n = s_prefix[t + 1] - s_prefix[t];
@@ -493,8 +578,13 @@ __global__ void __launch_bounds__(256) yolo_pack_rows_kernel(const __grid_consta
             const int anchor_id = __float_as_int(r1.z);
             if (a.variant == TRTX_YOLO_V8) {
                 if (a.is_seg | a.is_pose | a.is_obb) write_extras_v8<T>(a, b, anchor_id, det);
-            } else {
+            } else if (a.variant == TRTX_YOLO_V5) {
                 write_extras_v5<T>(a, b, anchor_id, det);
+            } else if (a.variant == TRTX_YOLO_V3) {
+                det[6] = r1.w;  // class_confidence
+            } else {            // V26: the reference memsets the buffer, so the fields gatherKernel skips are zero
+                for (int f = 6; f < a.det_floats; ++f) det[f] = 0.0f;
+                if (a.is_obb) det[a.det_floats - 1] = r1.w;
             }
         }
     }
@@ -515,7 +605,7 @@ int yolo_pick_vec(const trtx_yolo_params* p, const void* const* inputs_dev) {
 
 static int validate(const trtx_yolo_params* p, int batch) {
     if (!p || batch <= 0) return TRTX_ERR_INVALID;
-    if (p->variant != TRTX_YOLO_V8 && p->variant != TRTX_YOLO_V5) return TRTX_ERR_INVALID;
+    if (p->variant < TRTX_YOLO_V8 || p->variant > TRTX_YOLO_V26) return TRTX_ERR_INVALID;
     if (p->num_levels <= 0 || p->num_levels > TRTX_MAX_LEVELS) return TRTX_ERR_INVALID;
     if (p->num_classes <= 0 || p->max_out <= 0 || p->det_floats < 6) return TRTX_ERR_INVALID;
     if (p->in_dtype != TRTX_F32 && p->in_dtype != TRTX_F16) return TRTX_ERR_INVALID;
@@ -527,9 +617,18 @@ static int validate(const trtx_yolo_params* p, int batch) {
         if (p->is_obb) need = (need > 7 ? need : 7);
         if (p->det_floats < need) return TRTX_ERR_INVALID;
         if (p->is_pose && p->num_kpts <= 0) return TRTX_ERR_INVALID;
-    } else {
+    } else if (p->variant == TRTX_YOLO_V5) {
         if (p->is_seg && p->det_floats < 38) return TRTX_ERR_INVALID;
         if (p->is_pose || p->is_obb) return TRTX_ERR_UNSUPPORTED;
+    } else if (p->variant == TRTX_YOLO_V3) {
+        if (p->det_floats < 7) return TRTX_ERR_INVALID;
+        if (p->is_seg || p->is_pose || p->is_obb) return TRTX_ERR_UNSUPPORTED;
+        for (int l = 0; l < p->num_levels; ++l)
+            if (p->strides[l] <= 0) return TRTX_ERR_INVALID;
+    } else {  // V26: one AoS input; seg / pose tails are "TODO" in the reference too (yololayer.cu:244)
+        if (p->num_levels != 1 || p->in_dtype != TRTX_F32) return TRTX_ERR_UNSUPPORTED;
+        if (p->is_seg || p->is_pose) return TRTX_ERR_UNSUPPORTED;
+        if (p->is_obb && p->det_floats < 7) return TRTX_ERR_INVALID;
     }
     return TRTX_OK;
 }
@@ -541,7 +640,7 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
     if (!inputs_dev || !workspace_dev) return TRTX_ERR_INVALID;
     for (int l = 0; l < p->num_levels; ++l)
         if (!inputs_dev[l]) return TRTX_ERR_INVALID;
-    const int vec = yolo_pick_vec(p, inputs_dev);
+    const int vec = p->variant == TRTX_YOLO_V26 ? 1 : yolo_pick_vec(p, inputs_dev);  // V26: 32-anchor tiles
     // The TMA pipeline scan splits every 128-anchor stage over four warps of 32 anchors, i.e. it runs on the
     // 32-cell tile layout (the same one as the scalar kernels, which are its fallback).
     if (p->tune_class_slices < 0 || p->tune_rows_in_flight < 0 || p->tune_tma_stages < 0 || p->tune_box_prefetch < 0 ||
@@ -578,6 +677,12 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
         // yololayer.cu:186
         a->info_len = 4 + p->num_classes + (p->is_seg ? 32 : 0) + (p->is_pose ? p->num_kpts * 3 : 0) + (p->is_obb ? 1 : 0);
         a->C = a->info_len;
+    } else if (p->variant == TRTX_YOLO_V26) {
+        a->info_len = 4 + p->num_classes + (p->is_obb ? 1 : 0);  // yolo26 yololayer.cu:189-194
+        a->C = a->info_len;
+    } else if (p->variant == TRTX_YOLO_V3) {
+        a->info_len = 5 + p->num_classes;  // yolov3-spp yololayer.cu:159
+        a->C = 3 * a->info_len;
     } else {
         a->info_len = 5 + p->num_classes + (p->is_seg ? 32 : 0);  // yolov5 yololayer.cu:170-171
         a->C = 3 * a->info_len;
@@ -636,7 +741,17 @@ int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int b
         const int rc = yolo_scan_pipe_launch(a, L, in_dtype, batch, st);
         if (rc != TRTX_ERR_UNSUPPORTED) return rc;  // else: scalar kernels on the same 32-cell layout
     }
-    if (a.variant == TRTX_YOLO_V8) {
+    if (a.variant == TRTX_YOLO_V26) {
+        const int Cp = a.C | 1;
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * 32 * Cp * sizeof(float) > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * 32 * Cp * sizeof(float);
+        if (smem > 200 * 1024) return TRTX_ERR_UNSUPPORTED;
+        const bool v4 = a.C % 4 == 0 && reinterpret_cast<uintptr_t>(a.lv[0].in) % 16 == 0;
+        auto kern = v4 ? yolo26_gather_kernel<4> : yolo26_gather_kernel<1>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(grid + wpc - 1) / wpc, 128, smem, st>>>(a, batch, wpc);
+    } else if (a.variant == TRTX_YOLO_V8) {
         int rc;
         if (in_dtype == TRTX_F32)
             rc = L.vec == 4 ? launch_v8<float, 4>(a, L, grid, st) : launch_v8<float, 1>(a, L, grid, st);

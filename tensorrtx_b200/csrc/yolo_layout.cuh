@@ -5,7 +5,7 @@
 //   inputs      : per level l, [B, C, g_l] channel-major (the reference's plugin input)
 //   tile_count  : [B, tiles_per_image] int32   -- candidates found in each 32*VEC-slot tile
 //   cand        : [B, slots_per_image] records of 32 B (two float4):
-//                 {b0,b1,b2,b3} {conf, cls, anchor_id (int bits), 0}
+//                 {b0,b1,b2,b3} {conf, cls, anchor_id (int bits), spare (v3 class confidence / v26 angle)}
 //                 tile t of image b owns slots [tile_slot_begin(t), +tile_slots); its candidates are
 //                 written densely from the tile's first slot, in ascending anchor order.
 //   list        : [B, slots_per_image] uint2 (conf key, slot) -- scratch of the fused NMS kernel
@@ -34,7 +34,7 @@ struct YoloArgs {
     int tiles_per_image;
     int slots_per_image;
     int tile_cells;  // cells per tile = 32*VEC
-    int apc;         // anchors per cell: 1 (v8) / 3 (v5)
+    int apc;         // anchors per cell: 1 (v8, v26) / 3 (v5, v3)
     int C;           // channels per image per level (v8: info_len; v5: 3*info_len_i)
     int info_len;    // v8: 4+nc+extras ; v5: 5+nc(+32)
     int nc;
@@ -70,7 +70,7 @@ inline YoloLayout yolo_layout(const trtx_yolo_params* p, int batch, int vec) {
     YoloLayout L{};
     L.vec = vec;
     L.tile_cells = 32 * vec;
-    L.apc = (p->variant == TRTX_YOLO_V5) ? 3 : 1;
+    L.apc = (p->variant == TRTX_YOLO_V5 || p->variant == TRTX_YOLO_V3) ? 3 : 1;
     int tiles = 0, slots = 0;
     for (int l = 0; l < p->num_levels; ++l) {
         int g = p->grid_h[l] * p->grid_w[l];
@@ -147,10 +147,11 @@ __device__ __forceinline__ float finish_best(float bx, float b2, int& cls, float
     return P;
 }
 
+// `spare`: v3 class confidence / v26 obb angle (0 elsewhere)
 __device__ __forceinline__ void store_record(float4* cand, size_t slot, float b0, float b1, float b2, float b3,
-                                             float conf, int cls, int anchor_id) {
+                                             float conf, int cls, int anchor_id, float spare = 0.0f) {
     cand[2 * slot] = make_float4(b0, b1, b2, b3);
-    cand[2 * slot + 1] = make_float4(conf, (float)cls, __int_as_float(anchor_id), 0.0f);
+    cand[2 * slot + 1] = make_float4(conf, (float)cls, __int_as_float(anchor_id), spare);
 }
 
 int yolo_pick_vec(const trtx_yolo_params* p, const void* const* inputs_dev);

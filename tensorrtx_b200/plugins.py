@@ -322,6 +322,218 @@ class YoloLayerPluginV5:
         return p
 
 
+class YoloLayerPluginV7(YoloLayerPluginV5):
+    """yolov7/plugin/yololayer.h:9-73 (same kernel arithmetic as yolov5, yolov7/plugin/yololayer.cu:152-200, but
+    Detection = 6 floats, yolov7/include/types.h:11-16; also yolov10 / yolov13 style rows).  No segmentation flag:
+    ctor (classCount, netWidth, netHeight, maxOut, vYoloKernel), serialization without the bool."""
+    DET_FLOATS = 6
+
+    def __init__(self, classCount: int, netWidth: int, netHeight: int, maxOut: int, vYoloKernel: Sequence[YoloKernel],
+                 in_dtype: int = L.F32):
+        super().__init__(classCount, netWidth, netHeight, maxOut, False, vYoloKernel, in_dtype)
+
+    def clone(self) -> "YoloLayerPluginV7":
+        p = YoloLayerPluginV7(self.mClassCount, self.mYoloV5NetWidth, self.mYoloV5NetHeight, self.mMaxOutObject,
+                              self.mYoloKernel, self.params.in_dtype)
+        p.mPluginNamespace = self.mPluginNamespace
+        return p
+
+    def serialize(self) -> bytes:  # yolov7/plugin/yololayer.cu:62-77
+        d = struct.pack("<iiiiii", self.mClassCount, self.mThreadCount, self.mKernelCount, self.mYoloV5NetWidth,
+                        self.mYoloV5NetHeight, self.mMaxOutObject)
+        for k in self.mYoloKernel:
+            d += struct.pack("<ii6f", k.width, k.height, *k.anchors)
+        return d
+
+    def getSerializationSize(self) -> int:
+        return 24 + 32 * self.mKernelCount
+
+    @classmethod
+    def deserialize(cls, data: bytes) -> "YoloLayerPluginV7":
+        cc, tc, kc, w, h, mo = struct.unpack_from("<iiiiii", data, 0)
+        if 24 + 32 * kc != len(data):
+            raise L.TrtxError("YoloLayerPluginV7.deserialize: length mismatch")
+        ks = []
+        for i in range(kc):
+            v = struct.unpack_from("<ii6f", data, 24 + 32 * i)
+            ks.append(YoloKernel(v[0], v[1], v[2:]))
+        p = cls(cc, w, h, mo, ks)
+        p.mThreadCount = tc
+        return p
+
+
+class YoloKernelV3:
+    """Yolo::YoloKernel of yolov3-spp/yololayer.h:20-26: width, height (dynamic, -1 until enqueue), stride, anchors."""
+
+    def __init__(self, width: int, height: int, stride: int, anchors: Sequence[float]):
+        self.width, self.height, self.stride = int(width), int(height), int(stride)
+        self.anchors = [float(a) for a in anchors]
+        assert len(self.anchors) == 6
+
+
+# yolo1..3 of yolov3-spp/yololayer.h:27-44 (the plugin's level order: stride 32, 16, 8)
+YOLOV3_KERNELS = (YoloKernelV3(-1, -1, 32, (116, 90, 156, 198, 373, 326)),
+                  YoloKernelV3(-1, -1, 16, (30, 61, 62, 45, 59, 119)),
+                  YoloKernelV3(-1, -1, 8, (10, 13, 16, 30, 33, 23)))
+
+
+class YoloLayerPluginV3:
+    """yolov3-spp/yololayer.h:58-121 (IPluginV2DynamicExt "YoloLayer_TRT" v1; yolov3 / yolov4 carry the same plugin).
+    The reference compiles CLASS_NUM, the kernels and MAX_OUTPUT_BBOX_COUNT in; here they are constructor arguments with
+    the reference's values as defaults.  enqueue() takes the grids from the input tensors like the reference
+    (yololayer.cu:207-216)."""
+    PLUGIN_TYPE = "YoloLayer_TRT"
+    PLUGIN_VERSION = "1"
+    DET_FLOATS = 7  # x,y,w,h, det_confidence, class_id, class_confidence (yololayer.h:47-53)
+
+    def __init__(self, classCount: int = 80, kernels: Sequence[YoloKernelV3] = YOLOV3_KERNELS, maxOut: int = 1000,
+                 in_dtype: int = L.F32):
+        self.mClassCount, self.mYoloKernel, self.mMaxOutObject = int(classCount), list(kernels), int(maxOut)
+        self.mKernelCount, self.mThreadCount, self.mPluginNamespace = len(self.mYoloKernel), 256, ""
+        self._lib = L.load()
+        p = L.YoloParams()
+        p.variant = L.YOLO_V3
+        p.num_classes, p.max_out, p.det_floats, p.num_levels = self.mClassCount, self.mMaxOutObject, self.DET_FLOATS, self.mKernelCount
+        for i, k in enumerate(self.mYoloKernel):
+            p.strides[i] = k.stride
+            p.grid_w[i], p.grid_h[i] = max(k.width, 1), max(k.height, 1)
+            for j in range(6):
+                p.anchors[i][j] = k.anchors[j]
+        p.gate = 0.1  # IGNORE_THRESH, yololayer.h:15
+        p.in_dtype = in_dtype
+        self.params = p
+
+    def tune(self, **kw) -> "YoloLayerPluginV3":
+        _tune(self.params, **kw)
+        return self
+
+    def getNbOutputs(self) -> int:
+        return 1
+
+    def output_elems(self) -> int:
+        return 1 + self.mMaxOutObject * self.DET_FLOATS
+
+    def configure(self, inputs) -> None:
+        """grid = dims 2, 3 of every input tensor [B, 3*(5+nc), gh, gw] (yololayer.cu:209-212)."""
+        for i, t in enumerate(inputs):
+            self.params.grid_h[i], self.params.grid_w[i] = int(t.shape[2]), int(t.shape[3])
+
+    def getWorkspaceSize(self, maxBatchSize: int) -> int:
+        return int(self._lib.trtx_yolo_workspace_size(C.byref(self.params), int(maxBatchSize)))
+
+    def enqueue(self, inputs, outputs, workspace=None, stream=None) -> int:
+        """IPluginV2DynamicExt::enqueue: batch = inputs[0].shape[0]."""
+        self.configure(inputs)
+        batch = int(inputs[0].shape[0])
+        if workspace is None:
+            workspace = torch.empty(self.getWorkspaceSize(batch), dtype=torch.uint8, device=inputs[0].device)
+        ptrs = L.ptr_array([_ptr(t) for t in inputs])
+        return int(self._lib.trtx_yolo_decode_enqueue(C.byref(self.params), batch, ptrs, _ptr(outputs[0]), _ptr(workspace),
+                                                      workspace.numel() * workspace.element_size(), _stream(stream)))
+
+    def getPluginType(self) -> str:
+        return self.PLUGIN_TYPE
+
+    def getPluginVersion(self) -> str:
+        return self.PLUGIN_VERSION
+
+    def clone(self) -> "YoloLayerPluginV3":
+        p = YoloLayerPluginV3(self.mClassCount, self.mYoloKernel, self.mMaxOutObject, self.params.in_dtype)
+        p.mPluginNamespace = self.mPluginNamespace
+        return p
+
+    # byte layout of yolov3-spp/yololayer.cu:36-71: classCount, threadCount, kernelCount, kernels {w, h, stride, anchors[6]}
+    def serialize(self) -> bytes:
+        d = struct.pack("<iii", self.mClassCount, self.mThreadCount, self.mKernelCount)
+        for k in self.mYoloKernel:
+            d += struct.pack("<iii6f", k.width, k.height, k.stride, *k.anchors)
+        return d
+
+    def getSerializationSize(self) -> int:
+        return 12 + 36 * self.mKernelCount
+
+    @classmethod
+    def deserialize(cls, data: bytes) -> "YoloLayerPluginV3":
+        cc, tc, kc = struct.unpack_from("<iii", data, 0)
+        if 12 + 36 * kc != len(data):
+            raise L.TrtxError("YoloLayerPluginV3.deserialize: length mismatch")
+        ks = []
+        for i in range(kc):
+            v = struct.unpack_from("<iii6f", data, 12 + 36 * i)
+            ks.append(YoloKernelV3(v[0], v[1], v[2], v[3:]))
+        p = cls(cc, ks)
+        p.mThreadCount = tc
+        return p
+
+
+class YoloLayerPlugin26:
+    """yolo26/plugin/yololayer.h:10-77 ("YoloLayer_TRT" v1 of the NMS-free yolo26 heads): ctor (classCount, numberOfPoints,
+    maxDetections, isDetection, isSegmentation, isPose, isObb, anchor_count); setPluginDeviceParams(confThreshold) of the
+    reference is the `conf_thresh` argument here (no device global).  One input [B, anchor_count, 4+nc(+1)]."""
+    PLUGIN_TYPE = "YoloLayer_TRT"
+    PLUGIN_VERSION = "1"
+    DET_FLOATS = 90  # yolo26/include/types.h
+
+    def __init__(self, classCount: int, numberOfPoints: int, maxDetections: int, isDetection: bool, isSegmentation: bool,
+                 isPose: bool, isObb: bool, anchor_count: int, conf_thresh: float = 0.4):
+        self.mClassCount, self.mNumberOfPoints, self.mMaxDetections = int(classCount), int(numberOfPoints), int(maxDetections)
+        self.mIsDetection, self.mIsSegmentation, self.mIsPose, self.mIsObb = bool(isDetection), bool(isSegmentation), bool(isPose), bool(isObb)
+        self.mAnchorCount, self.mThreadCount, self.mPluginNamespace = int(anchor_count), 256, ""
+        self._lib = L.load()
+        p = L.YoloParams()
+        p.variant = L.YOLO_V26
+        p.num_classes, p.max_out, p.det_floats, p.num_levels = self.mClassCount, self.mMaxDetections, self.DET_FLOATS, 1
+        p.grid_h[0], p.grid_w[0] = 1, self.mAnchorCount
+        p.is_seg, p.is_pose, p.is_obb = int(self.mIsSegmentation), int(self.mIsPose), int(self.mIsObb)
+        p.num_kpts = self.mNumberOfPoints
+        p.gate = float(conf_thresh)  # d_confThreshold, yololayer.cu:9 / setPluginDeviceParams :31-33
+        p.in_dtype = L.F32
+        self.params = p
+
+    def getNbOutputs(self) -> int:
+        return 1
+
+    def output_elems(self) -> int:
+        return 1 + self.mMaxDetections * self.DET_FLOATS
+
+    def getWorkspaceSize(self, maxBatchSize: int) -> int:
+        return int(self._lib.trtx_yolo_workspace_size(C.byref(self.params), int(maxBatchSize)))
+
+    def enqueue(self, batchSize: int, inputs, outputs, workspace, stream=None) -> int:
+        ptrs = L.ptr_array([_ptr(inputs[0])])
+        return int(self._lib.trtx_yolo_decode_enqueue(C.byref(self.params), int(batchSize), ptrs, _ptr(outputs[0]), _ptr(workspace),
+                                                      workspace.numel() * workspace.element_size(), _stream(stream)))
+
+    def getPluginType(self) -> str:
+        return self.PLUGIN_TYPE
+
+    def getPluginVersion(self) -> str:
+        return self.PLUGIN_VERSION
+
+    def clone(self) -> "YoloLayerPlugin26":
+        p = YoloLayerPlugin26(self.mClassCount, self.mNumberOfPoints, self.mMaxDetections, self.mIsDetection, self.mIsSegmentation,
+                              self.mIsPose, self.mIsObb, self.mAnchorCount, self.params.gate)
+        p.mPluginNamespace = self.mPluginNamespace
+        return p
+
+    # byte layout of yolo26/plugin/yololayer.cu:68-100 (4 ints, 4 bools, 1 int)
+    def serialize(self) -> bytes:
+        return struct.pack("<iiii????i", self.mClassCount, self.mNumberOfPoints, self.mThreadCount, self.mMaxDetections,
+                           self.mIsDetection, self.mIsSegmentation, self.mIsPose, self.mIsObb, self.mAnchorCount)
+
+    def getSerializationSize(self) -> int:
+        return 24
+
+    @classmethod
+    def deserialize(cls, data: bytes, conf_thresh: float = 0.4) -> "YoloLayerPlugin26":
+        if len(data) != 24:
+            raise L.TrtxError("YoloLayerPlugin26.deserialize: length mismatch")
+        cc, nk, tc, md, d, sg, po, ob, ac = struct.unpack("<iiii????i", data)
+        p = cls(cc, nk, md, d, sg, po, ob, ac, conf_thresh)
+        p.mThreadCount = tc
+        return p
+
+
 # --------------------------------------------------------------------------------------------------
 # NMS helpers (postprocess.h)
 # --------------------------------------------------------------------------------------------------
@@ -432,19 +644,22 @@ class DecodePlugin:
     PLUGIN_TYPE = "Decode_TRT"
     PLUGIN_VERSION = "1"
 
-    def __init__(self, input_h: int = 480, input_w: int = 640):
+    def __init__(self, input_h: int = 480, input_w: int = 640, anticov: bool = False):
+        """anticov=True: the Decode_TRT of retinafaceAntiCov/decode.cu (38-channel inputs, 16-float rows, 640x640 there)."""
         self._lib = L.load()
         p = L.RetinaParams()
         p.in_h, p.in_w = int(input_h), int(input_w)
         p.gate = float_le_threshold(0.02)  # `conf2 <= 0.02` with a double literal (decode.cu:131)
+        p.variant = L.RETINA_ANTICOV if anticov else L.RETINA_FACE
         self.params = p
+        self.det_floats = 16 if anticov else 15
         self.total_priors = int(self._lib.trtx_retina_total_priors(C.byref(p)))
 
     def getNbOutputs(self) -> int:
         return 1
 
     def output_elems(self) -> int:
-        return 1 + self.total_priors * 15
+        return 1 + self.total_priors * self.det_floats
 
     def getOutputDimensions(self, index=0, inputs=None, nbInputDims=0):
         return (self.output_elems(), 1, 1)  # decode.cu:33-41
@@ -465,7 +680,7 @@ class DecodePlugin:
         return self.PLUGIN_VERSION
 
     def clone(self) -> "DecodePlugin":
-        return DecodePlugin(self.params.in_h, self.params.in_w)
+        return DecodePlugin(self.params.in_h, self.params.in_w, self.params.variant == L.RETINA_ANTICOV)
 
     def serialize(self) -> bytes:  # the reference serializes nothing (decode.cu:23-31); the runtime size is new state
         return struct.pack("<ii", self.params.in_h, self.params.in_w)

@@ -109,6 +109,76 @@ def retina_heads(batch: int, seed: int = 0, in_h: int = 640, in_w: int = 640, n_
     return heads
 
 
+def yolov3_heads(batch: int, seed: int = 0, nc: int = 80, net_w: int = 608, net_h: int = 608, strides=(32, 16, 8),
+                 n_obj: int = 48):
+    """-> list over levels (the plugin's order: stride 32, 16, 8) of float32 [batch, 3*(5+nc), gh, gw] (yolov3-spp plugin
+    input, yololayer.cu:148-160).  Planted anchors get objectness ~N(2,1) and one class ~N(1.5,1); a third of them keep a
+    weak class row (so the class gate of :171 really drops rows the objectness gate alone would keep)."""
+    rng = _rng(seed)
+    ilen = 5 + nc
+    heads = []
+    for s in strides:
+        gw, gh = net_w // s, net_h // s
+        h = rng.standard_normal((batch, 3, ilen, gh * gw), dtype=np.float32)
+        h[:, :, 4:] += np.float32(-7.0)
+        h[:, :, 2:4] *= np.float32(0.5)  # w/h logits go through expf
+        heads.append(h)
+    for b in range(batch):
+        for _ in range(n_obj):
+            cls = int(rng.integers(0, nc))
+            cx, cy = rng.uniform(0, net_w), rng.uniform(0, net_h)
+            for li, s in enumerate(strides):
+                gw, gh = net_w // s, net_h // s
+                for (c, r) in _plant_cells(rng, gw, gh, cx, cy, s):
+                    e = r * gw + c
+                    k = int(rng.integers(0, 3))
+                    heads[li][b, k, 4, e] = np.float32(rng.normal(2.0, 1.0))
+                    if rng.uniform() < 2.0 / 3.0:
+                        heads[li][b, k, 5 + cls, e] = np.float32(rng.normal(1.5, 1.0))
+    return [h.reshape(batch, 3 * ilen, net_h // s, net_w // s) for h, s in zip(heads, strides)]
+
+
+def yolo26_rows(batch: int, seed: int = 0, nc: int = 80, anchors: int = 8400, obb: bool = False, n_obj: int = 60):
+    """-> float32 [batch, anchors, 4+nc(+1)]: the yolo26 head output, one row per anchor = x1,y1,x2,y2, class
+    PROBABILITIES (background ~U(0, 0.05)), angle (yolo26/plugin/yololayer.cu:189-199)."""
+    rng = _rng(seed)
+    C = 4 + nc + (1 if obb else 0)
+    x = rng.uniform(0, 0.05, (batch, anchors, C)).astype(np.float32)
+    ctr = rng.uniform(0, 640, (batch, anchors, 2))
+    wh = rng.uniform(8, 200, (batch, anchors, 2))
+    x[..., 0:2] = (ctr - wh / 2).astype(np.float32)
+    x[..., 2:4] = (ctr + wh / 2).astype(np.float32)
+    if obb:
+        x[..., 4 + nc] = rng.uniform(-0.78, 2.35, (batch, anchors)).astype(np.float32)
+    for b in range(batch):
+        for i in rng.choice(anchors, size=min(n_obj, anchors), replace=False):
+            x[b, i, 4 + int(rng.integers(0, nc))] = np.float32(rng.uniform(0.2, 0.99))
+    return x
+
+
+def anticov_heads(batch: int, seed: int = 0, in_h: int = 640, in_w: int = 640, n_obj: int = 32):
+    """-> list over strides 8/16/32 of float32 [batch, 38, h*w] = [cls 4 | bbox 2x4 | lmk 2x10 | type 6], cls / type already
+    soft-maxed (retinafaceAntiCov.cpp: reshapeSoftmax), face probability of prior k at channel 2+k, mask probability at 36+k
+    (retinafaceAntiCov/decode.cu:120-127,154)."""
+    rng = _rng(seed)
+    heads = []
+    for s in (8, 16, 32):
+        g = (in_h // s) * (in_w // s)
+        h = rng.standard_normal((batch, 38, g)).astype(np.float32)
+        h[:, 0:4] = rng.uniform(0.0, 0.3, (batch, 4, g)).astype(np.float32)
+        h[:, 4:12] *= np.float32(0.5)
+        h[:, 32:38] = rng.uniform(0.0, 1.0, (batch, 6, g)).astype(np.float32)
+        heads.append(h)
+    for b in range(batch):
+        for _ in range(n_obj):
+            cx, cy = rng.uniform(0, in_w), rng.uniform(0, in_h)
+            for li, s in enumerate((8, 16, 32)):
+                gw, gh = in_w // s, in_h // s
+                for (c, r) in _plant_cells(rng, gw, gh, cx, cy, s):
+                    heads[li][b, 2 + int(rng.integers(0, 2)), r * gw + c] = np.float32(rng.uniform(0.5, 1.0))
+    return heads
+
+
 def frames(batch: int, seed: int = 0, h: int = 640, w: int = 640):
     """-> uint8 [batch, h, w, 3] BGR frames ~U{0..255} (worst case for bilinear parity)."""
     return _rng(seed).integers(0, 256, (batch, h, w, 3), dtype=np.uint8)

@@ -182,6 +182,19 @@ class DimsExprs {
     const IDimensionExpr* d[Dims::MAX_DIMS];
 };
 
+// logger / profiler interfaces (the reference's yolov3-spp/Utils.h derives from them)
+class ILogger {
+   public:
+    enum class Severity : int32_t { kINTERNAL_ERROR = 0, kERROR = 1, kWARNING = 2, kINFO = 3, kVERBOSE = 4 };
+    virtual void log(Severity severity, const AsciiChar* msg) TRTX_NX = 0;
+    virtual ~ILogger() = default;
+};
+class IProfiler {
+   public:
+    virtual void reportLayerTime(const char* layerName, float ms) TRTX_NX = 0;
+    virtual ~IProfiler() = default;
+};
+
 // ---------------------------------------------------------------------------------------------
 class IPluginV2 {
    public:
@@ -251,8 +264,8 @@ class IPluginV2DynamicExt : public IPluginV2Ext {
     virtual size_t getWorkspaceSize(const PluginTensorDesc* inputs, int32_t nbInputs, const PluginTensorDesc* outputs,
                                     int32_t nbOutputs) const TRTX_NX = 0;
     virtual int32_t enqueue(const PluginTensorDesc* inputDesc, const PluginTensorDesc* outputDesc,
-                            const void* const* inputs, void* TRTX_CE* outputs, void* workspace,
-                            cudaStream_t stream) TRTX_NX = 0;
+                            const void* const* inputs, void* const* outputs, void* workspace,
+                            cudaStream_t stream) TRTX_NX = 0;  // `void* const*` in TensorRT 7 as well
 
    private:
     // implicit-batch entry points are sealed off, as in TensorRT

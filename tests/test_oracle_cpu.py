@@ -226,3 +226,90 @@ def test_roi_align_against_torchvision(oracle, sampling):
     ref = tv.ops.roi_align(torch.from_numpy(feat)[None], boxes, (Pp, Pp), 1 / 16, sampling, aligned=True).numpy()
     np.testing.assert_allclose(got, ref, rtol=0, atol=3e-5)
 
+
+
+# ------------------------------------------------------------------ SURVEY 8f rank 4 variants: numpy re-derivations
+def _sig(x):
+    return (1.0 / (1.0 + np.exp(-x.astype(np.float64))))
+
+
+def test_yolov3_decode_oracle_vs_numpy(oracle):
+    """yolov3-spp/yololayer.cu:148-191 re-derived with numpy (fp64 sigmoid/exp, so values to 1e-4; counts, classes, anchor ids exact)."""
+    from tensorrtx_b200 import plugins  # noqa: F401  (YOLOV3_KERNELS needs the library; skip cleanly if it is not built)
+    B = 2
+    heads = synth.yolov3_heads(B, seed=5, net_w=416, net_h=320)
+    anchors = [(116, 90, 156, 198, 373, 326), (30, 61, 62, 45, 59, 119), (10, 13, 16, 30, 33, 23)]
+    out, idx = oracle.yolov3_decode(heads, anchors)
+    exp = [[] for _ in range(B)]
+    off = 0
+    for h, s, anc in zip(heads, (32, 16, 8), anchors):
+        gh, gw = h.shape[2], h.shape[3]
+        x = h.reshape(B, 3, 85, gh * gw)
+        obj = _sig(x[:, :, 4])
+        cls_p = _sig(x[:, :, 5:])
+        best, arg = cls_p.max(2), cls_p.argmax(2)
+        for b in range(B):
+            for e in range(gh * gw):
+                for k in range(3):
+                    if np.float32(best[b, k, e]) < np.float32(0.1) or np.float32(obj[b, k, e]) < np.float32(0.1):
+                        continue
+                    row, col = divmod(e, gw)
+                    exp[b].append((off + e * 3 + k, (col + _sig(x[b, k, 0, e])) * s, (row + _sig(x[b, k, 1, e])) * s,
+                                   np.exp(np.float64(x[b, k, 2, e])) * anc[2 * k], np.exp(np.float64(x[b, k, 3, e])) * anc[2 * k + 1],
+                                   obj[b, k, e], arg[b, k, e], best[b, k, e]))
+        off += gh * gw * 3
+    for b in range(B):
+        n = int(out[b, 0])
+        assert n == len(exp[b]) and n > 20
+        rows = out[b, 1:1 + n * 7].reshape(n, 7)
+        e = np.asarray(sorted(exp[b]), dtype=np.float64)        # the oracle walks level by level, cell by cell: same order
+        assert np.array_equal(idx[b, :n], e[:, 0].astype(np.int32))
+        np.testing.assert_allclose(rows[:, :4], e[:, 1:5], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(rows[:, [4, 6]], e[:, [5, 7]], atol=1e-6)
+        assert np.array_equal(rows[:, 5], e[:, 6])
+
+
+def test_yolo26_gather_oracle_vs_numpy(oracle):
+    rows = synth.yolo26_rows(2, seed=6, nc=15, anchors=2000, obb=True)
+    out, idx = oracle.yolo26_gather(rows, nc=15, obb=True, max_out=300, conf_thresh=0.3)
+    for b in range(2):
+        sc = rows[b, :, 4:19]
+        best, arg = sc.max(1), sc.argmax(1)
+        keep = np.where(~(best < np.float32(0.3)))[0]
+        n = int(out[b, 0])
+        assert n == len(keep) and n > 20
+        r = out[b, 1:1 + n * 90].reshape(n, 90)
+        assert np.array_equal(idx[b, :n], keep)
+        assert np.array_equal(r[:, :4], rows[b, keep, :4]) and np.array_equal(r[:, 4], best[keep])
+        assert np.array_equal(r[:, 5], arg[keep].astype(np.float32)) and np.array_equal(r[:, 89], rows[b, keep, 19])
+        assert np.all(r[:, 6:89] == 0) and np.all(out[b, 1 + n * 90:] == 0)
+
+
+def test_anticov_decode_oracle_vs_numpy(oracle):
+    heads = synth.anticov_heads(2, seed=7)
+    out, idx = oracle.anticov_decode(heads)
+    for b in range(2):
+        exp = []
+        off = 0
+        for h, step, anchor in zip(heads, (8, 16, 32), (16, 64, 256)):
+            w = 640 // step
+            g = h.shape[2]
+            for e in range(g):
+                for k in range(2):
+                    conf = h[b, 2 + k, e]
+                    if conf < 0.5:
+                        continue
+                    y, x = divmod(e, w)
+                    p0, p1, p2 = 7.5 + x * step, 7.5 + y * step, float(anchor * 2 // (k + 1))
+                    bx = h[b, 4 + 4 * k:8 + 4 * k, e].astype(np.float64)
+                    bw, bh = p2 * np.exp(bx[2]), p2 * np.exp(bx[3])
+                    x1, y1 = p0 + bx[0] * p2 - (bw - 1) / 2, p1 + bx[1] * p2 - (bh - 1) / 2
+                    lm = h[b, 12 + 10 * k:22 + 10 * k, e].astype(np.float64)
+                    lmk = [(p0 if i % 2 == 0 else p1) + lm[i] * 0.2 * p2 for i in range(10)]
+                    exp.append([off + e * 2 + k, x1, y1, x1 + bw, y1 + bh, conf] + lmk + [h[b, 36 + k, e]])
+            off += g * 2
+        n = int(out[b, 0])
+        assert n == len(exp) and n > 50
+        e = np.asarray(exp, np.float64)
+        assert np.array_equal(idx[b, :n], e[:, 0].astype(np.int32))
+        np.testing.assert_allclose(out[b, 1:1 + n * 16].reshape(n, 16), e[:, 1:], rtol=1e-5, atol=1e-3)
