@@ -48,6 +48,9 @@ inline void read(const char*& b, T& v) {
     std::memcpy(&v, b, sizeof(T));
     b += sizeof(T);
 }
+// trtx_rpn_decode & co. answer a NULL / zero-sized workspace with the required size (> 0) and launch nothing
+// (the reference idiom, rcnn/RpnNms.cu:63-80): inside enqueue that is a failure, not a success.
+inline int rcnn_rc(int64_t rc) { return rc == 0 ? 0 : (rc < 0 ? (int)-rc : TRTX_ERR_WORKSPACE); }
 }  // namespace detail
 
 // ================================================================================================
@@ -201,20 +204,16 @@ class YoloLayerPluginDynamic : public nvinfer1::IPluginV2DynamicExt {
     }
     int initialize() TRTX_NOEXCEPT override { return 0; }
     void terminate() TRTX_NOEXCEPT override {}
+    // TensorRT asks with the MAXIMUM dims of the optimisation profile; the layout is derived from the tensor dims exactly
+    // as enqueue derives it, and the size grows with batch and grid, so what is granted here covers every runtime shape.
     size_t getWorkspaceSize(const nvinfer1::PluginTensorDesc* in, int, const nvinfer1::PluginTensorDesc*, int) const TRTX_NOEXCEPT override {
-        return trtx_yolo_workspace_size(&core_.p, in[0].dims.d[0] > 0 ? in[0].dims.d[0] : 1);
+        const trtx_yolo_params p = bound_params(in);
+        return trtx_yolo_workspace_size(&p, in[0].dims.d[0] > 0 ? in[0].dims.d[0] : 1);
     }
     int enqueue(const nvinfer1::PluginTensorDesc* in, const nvinfer1::PluginTensorDesc*, const void* const* inputs, void* const* outputs,
                 void* workspace, cudaStream_t stream) TRTX_NOEXCEPT override {
-        trtx_yolo_params p = core_.p;                 // per-call copy: enqueue never mutates the plugin
+        const trtx_yolo_params p = bound_params(in);  // per-call copy: enqueue never mutates the plugin
         const int batch = in[0].dims.d[0];
-        for (int i = 0; i < p.num_levels; ++i) {      // grid from the bound tensors (yolov3-spp/yololayer.cu:207-216)
-            if (in[i].dims.nbDims == 4) {
-                p.grid_h[i] = in[i].dims.d[2];
-                p.grid_w[i] = in[i].dims.d[3];
-            }
-            p.in_dtype = in[i].type == nvinfer1::DataType::kHALF ? TRTX_F16 : TRTX_F32;
-        }
         return trtx_yolo_decode_enqueue(&p, batch, inputs, static_cast<float*>(outputs[0]), workspace,
                                         trtx_yolo_workspace_size(&p, batch), stream);
     }
@@ -239,6 +238,18 @@ class YoloLayerPluginDynamic : public nvinfer1::IPluginV2DynamicExt {
     const YoloCore& core() const { return core_; }
 
    private:
+    // grid and input type from the bound tensors (yolov3-spp/yololayer.cu:207-216)
+    trtx_yolo_params bound_params(const nvinfer1::PluginTensorDesc* in) const {
+        trtx_yolo_params p = core_.p;
+        for (int i = 0; i < p.num_levels; ++i) {
+            if (in[i].dims.nbDims == 4) {
+                p.grid_h[i] = in[i].dims.d[2];
+                p.grid_w[i] = in[i].dims.d[3];
+            }
+            p.in_dtype = in[i].type == nvinfer1::DataType::kHALF ? TRTX_F16 : TRTX_F32;
+        }
+        return p;
+    }
     YoloCore core_;
 };
 
@@ -460,7 +471,7 @@ class RpnDecodePlugin : public RcnnPluginBase {
                                            static_cast<float*>(outputs[0]), static_cast<float*>(outputs[1]), (int)height_, (int)width_,
                                            (int)image_height_, (int)image_width_, stride_, anchors_.data(), (int)anchors_.size() / 4,
                                            top_n_, workspace, getWorkspaceSize(batchSize), stream);
-        return rc < 0 ? (int)-rc : 0;
+        return detail::rcnn_rc(rc);
     }
     size_t getSerializationSize() const TRTX_NOEXCEPT override {
         return sizeof(top_n_) + sizeof(size_t) + sizeof(float) * anchors_.size() + sizeof(stride_) + 4 * sizeof(size_t);
@@ -510,7 +521,7 @@ class RpnNmsPlugin : public RcnnPluginBase {
     int enqueue(int batchSize, const void* const* inputs, void* TRTX_CONST_ENQUEUE* outputs, void* workspace, cudaStream_t stream) TRTX_NOEXCEPT override {
         const int64_t rc = trtx_rpn_nms(batchSize, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
                                         static_cast<float*>(outputs[0]), (int)pre_, post_, thresh_, workspace, getWorkspaceSize(batchSize), stream);
-        return rc < 0 ? (int)-rc : 0;
+        return detail::rcnn_rc(rc);
     }
     size_t getSerializationSize() const TRTX_NOEXCEPT override { return sizeof(thresh_) + sizeof(post_) + sizeof(pre_); }
     void serialize(void* buffer) const TRTX_NOEXCEPT override {
@@ -650,7 +661,7 @@ class PredictorDecodePlugin : public RcnnPluginBase {
                                                  static_cast<const float*>(inputs[2]), static_cast<float*>(outputs[0]), static_cast<float*>(outputs[1]),
                                                  static_cast<float*>(outputs[2]), (int)num_boxes_, (int)num_classes_, (int)image_height_,
                                                  (int)image_width_, w_.data(), workspace, getWorkspaceSize(batchSize), stream);
-        return rc < 0 ? (int)-rc : 0;
+        return detail::rcnn_rc(rc);
     }
     size_t getSerializationSize() const TRTX_NOEXCEPT override { return 4 * sizeof(unsigned) + sizeof(size_t) + sizeof(float) * w_.size(); }
     void serialize(void* buffer) const TRTX_NOEXCEPT override {
@@ -696,7 +707,7 @@ class BatchedNmsPlugin : public RcnnPluginBase {
         const int64_t rc = trtx_batched_nms(method_, batchSize, static_cast<const float*>(inputs[0]), static_cast<const float*>(inputs[1]),
                                             static_cast<const float*>(inputs[2]), static_cast<float*>(outputs[0]), static_cast<float*>(outputs[1]),
                                             static_cast<float*>(outputs[2]), (int)count_, dets_, thresh_, workspace, getWorkspaceSize(batchSize), stream);
-        return rc < 0 ? (int)-rc : 0;
+        return detail::rcnn_rc(rc);
     }
     size_t getSerializationSize() const TRTX_NOEXCEPT override { return sizeof(method_) + sizeof(thresh_) + sizeof(dets_) + sizeof(count_); }
     void serialize(void* buffer) const TRTX_NOEXCEPT override {

@@ -147,6 +147,60 @@ def test_rcnn_workspace_idiom(dev):
     assert P.RpnNmsPlugin(0.7, 1000, 6000).getWorkspaceSize(8) > 0
 
 
+def test_retina_full_config_b16(oracle, dev):
+    """BASELINE configs[2]: RetinaFace batch 16 at 640x640 -- decode and NMS of every image against the oracle."""
+    B = 16
+    heads = synth.retina_heads(B, seed=21)
+    ref, _ = oracle.retina_decode(heads, in_h=640, in_w=640, gate=0.02)
+    plug = P.DecodePlugin(640, 640)
+    out = torch.zeros((B, plug.output_elems()), dtype=torch.float32, device=dev)
+    assert plug.enqueue(B, [torch.from_numpy(x).to(dev) for x in heads], [out], _ws(plug.getWorkspaceSize(B), dev)) == 0
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, 0], ref[:, 0]) and ref[:, 0].min() > 50
+    comp, idx = P.batch_nms(out, B, plug.output_elems(), P.float_le_threshold(0.1), 0.4, box_format=L.BOX_RETINA, det_floats=15,
+                            max_det=2048, extra_floats=10, extra_offset=5, return_index=True)
+    comp, idx = comp.cpu().numpy(), idx.cpu().numpy()
+    tp = oracle.retina_total_priors(640, 640)
+    for b in range(B):
+        n = int(ref[b, 0])
+        np.testing.assert_allclose(got[b, 1:1 + n * 15], ref[b, 1:1 + n * 15], atol=ATOL, rtol=RTOL_EXP)
+        res, src = oracle.nms(2, got[b], tp, 15, 0.1, 0.4)    # NMS of OUR rows: kept sets must agree bit for bit
+        k = int(comp[b, 0])
+        assert k == len(res) and np.array_equal(idx[b, :k], src)
+        assert np.array_equal(comp[b, 1:1 + k * 17].reshape(k, 17)[:, :5], res[:, :5])
+
+
+def test_rcnn_full_config_b8_chain(oracle, dev):
+    """BASELINE configs[3]: Faster R-CNN batch 8 -- RpnDecode -> RpnNms -> PredictorDecode -> BatchedNms chained on the
+    device, every stage of every image against the oracle fed with the SAME stage inputs."""
+    B, A, H, W, pre, post, N, Cc = 8, 15, 50, 67, 6000, 1000, 1000, 80
+    anchors = synth.rcnn_anchors()
+    scores, deltas = synth.rpn_inputs(B, seed=31, A=A, H=H, W=W)
+    d_s, d_b = torch.zeros((B, pre), device=dev), torch.zeros((B, pre, 4), device=dev)
+    p1 = P.RpnDecodePlugin(pre, anchors, 16.0, 800, 1067, H, W)
+    assert p1.enqueue(B, [torch.from_numpy(scores).to(dev), torch.from_numpy(deltas).to(dev)], [d_s, d_b],
+                      _ws(p1.getWorkspaceSize(B), dev)) == 0
+    r_s, r_b = oracle.rpn_decode(scores, deltas, 800, 1067, 16.0, anchors, pre)
+    assert np.array_equal(d_s.cpu().numpy(), r_s)
+    np.testing.assert_allclose(d_b.cpu().numpy(), r_b, atol=ATOL, rtol=RTOL_EXP)
+    props = torch.zeros((B, post, 4), device=dev)
+    assert P.RpnNmsPlugin(0.7, post, pre).enqueue(B, [d_s, d_b], [props], _ws(256, dev)) == 0
+    assert np.array_equal(props.cpu().numpy(), oracle.rpn_nms(d_s.cpu().numpy(), d_b.cpu().numpy(), post, 0.7))
+    cls_scores, box_deltas, _ = synth.predictor_inputs(B, seed=32, N=N, Ccls=Cc)
+    w = (10.0, 10.0, 5.0, 5.0)
+    os_, ob, oc = torch.zeros((B, N), device=dev), torch.zeros((B, N, 4), device=dev), torch.zeros((B, N), device=dev)
+    assert P.PredictorDecodePlugin(N, 800, 1067, w, Cc).enqueue(
+        B, [torch.from_numpy(cls_scores).to(dev), torch.from_numpy(box_deltas).to(dev), props], [os_, ob, oc], _ws(256, dev)) == 0
+    rs, rb, rc_ = oracle.predictor_decode(cls_scores, box_deltas, props.cpu().numpy(), 800, 1067, w)
+    assert np.array_equal(os_.cpu().numpy(), rs) and np.array_equal(oc.cpu().numpy(), rc_)
+    np.testing.assert_allclose(ob.cpu().numpy(), rb, atol=ATOL, rtol=RTOL_EXP)
+    for method in (0, 1):
+        fs, fb, fc = torch.zeros((B, 100), device=dev), torch.zeros((B, 100, 4), device=dev), torch.zeros((B, 100), device=dev)
+        assert P.BatchedNmsPlugin(method, 0.5, 100, N).enqueue(B, [os_, ob, oc], [fs, fb, fc], _ws(256, dev)) == 0
+        es, eb, ec = oracle.batched_nms(method, os_.cpu().numpy(), ob.cpu().numpy(), oc.cpu().numpy(), 100, 0.5)
+        assert np.array_equal(fs.cpu().numpy(), es) and np.array_equal(fb.cpu().numpy(), eb) and np.array_equal(fc.cpu().numpy(), ec)
+
+
 # ------------------------------------------------------------------ pre-process ---------------
 @pytest.mark.parametrize("h,w", [(640, 640), (1080, 1920), (517, 333), (64, 48), (640, 480), (400, 640), (640, 636)])
 @pytest.mark.parametrize("odt", [torch.float32, torch.float16])
