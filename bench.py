@@ -1,25 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- detection hot path benchmark (contract: see the task statement / DESIGN.md section 6).
+"""bench.py -- detection hot path benchmark (contract: the task statement / DESIGN.md section 6).
 
-    python bench.py --gpus N --steps K --warmup W            # this build (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU decode+NMS on host cores
+    python bench.py --gpus N --steps K --warmup W                      # this build (sm_100a kernels), default config v8n_b32
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference's CPU path on the host cores
+    python bench.py --config {v8n_b32,v5s_b1,retina_b16,rcnn_b8} ...   # the other BASELINE.json configs (N = 1)
 
-A "step" is one pass of the hot path over one batch of 32 synthetic 640x640 frames per GPU
-(BASELINE.json configs[1]: YOLOv8n b32 640x640): batched letterbox pre-process of the frames +
-fused YoloLayer decode + NMS of the backbone's head tensors (+ the NCCL all-gather of the compact
-detections when N > 1).  The TensorRT backbone is not part of this path; its per-stride outputs are
-synthetic, seeded tensors resident in HBM (in the reference they are produced on the device by
-context.enqueue and handed to the plugin as device pointers, yolov8/yolov8_det.cpp:98).
+Default config = BASELINE.json configs[1], YOLOv8n b32 640x640.  A "step" is one pass of the hot path over one batch of 32
+synthetic frames per GPU: batched letterbox pre-process of the frames + fused YoloLayer decode + NMS of the backbone's head
+tensors (+ the gather of the compact detections over NVLink peer memory when N > 1).  The TensorRT backbone is not on this
+path; its per-stride outputs are synthetic, seeded tensors resident in HBM (in the reference they are produced on the device
+by context.enqueue and handed to the plugin as device pointers, yolov8/yolov8_det.cpp:98).
 
-value = whole-job frames/s with inputs resident in HBM; e2e = the same step through
-DetectionPipeline.run with the frames coming from pinned HOST memory (H2D inside the timed region)
-and the compact detections copied back to the host (D2H inside the timed region).
-Prints ONE JSON line on rank 0.
+value = whole-job frames/s with inputs resident in HBM; e2e = the same step through DetectionPipeline.submit with the frames
+in pinned HOST memory (H2D inside the timed region) and the compact detections copied back (D2H inside the timed region).
+Both arms print the same `config` dict (same workload, same stages: pre-process + decode + NMS).
+
+Timing: W warm-up steps, then blocks of EXACTLY K steps each bracketed by CUDA events (barrier + synchronize on both sides);
+as many blocks as it takes to cover >= 0.35 s, so that the 100 ms clock sampler has samples INSIDE the timed windows;
+ms_per_step = mean block time / K (max over ranks per block).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -31,18 +37,26 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-BATCH = 32
-NET = 640
-NC = 80
-STRIDES = (8, 16, 32)
-MAX_OUT = 1000
-CONF, IOU = 0.5, 0.45
+NET, NC, STRIDES, MAX_OUT = 640, 80, (8, 16, 32), 1000
+CONFIGS = {
+    # BASELINE.json configs[1] -- the headline
+    "v8n_b32": {"workload": "YOLOv8n 640x640 b32/GPU: letterbox pre-process + YoloLayer decode + NMS, synthetic (SURVEY 8d), fp32 heads",
+                "batch": 32, "conf": 0.5, "iou": 0.45, "metric": "end_to_end_fps_yolov8n_640_b32 (pre-process + fused decode + NMS); "
+                                                                  "decode+NMS us/frame alongside"},
+    # configs[0]: the reference's CPU-runnable case, single image
+    "v5s_b1": {"workload": "YOLOv5s 640x640 b1: letterbox pre-process + anchor-based YoloLayer decode + NMS, synthetic, fp32 heads",
+               "batch": 1, "conf": 0.5, "iou": 0.45, "metric": "end_to_end_fps_yolov5s_640_b1 (pre-process + decode + NMS)"},
+    # configs[2]
+    "retina_b16": {"workload": "RetinaFace-R50 640x640 b16: letterbox pre-process + Decode_TRT (landmarks) + NMS, synthetic, fp32 heads",
+                   "batch": 16, "conf": 0.1, "iou": 0.4, "metric": "end_to_end_fps_retinaface_640_b16 (pre-process + decode + NMS)"},
+    # configs[3] (the reference code is R50-C4: SURVEY 8d)
+    "rcnn_b8": {"workload": "Faster R-CNN R50-C4 b8: RpnDecode + RpnNms + PredictorDecode + BatchedNms on synthetic head tensors "
+                            "(800x1067 input, 6000 -> 1000 -> 100)", "batch": 8, "conf": 0.0, "iou": 0.5,
+                "metric": "plugin_chain_fps_faster_rcnn_b8 (RpnDecode + RpnNms + PredictorDecode + BatchedNms)"},
+}
 ALGO_BYTES_PER_IMAGE = (4 + NC) * sum((NET // s) ** 2 for s in STRIDES) * 4  # 2 822 400 B, SURVEY 8d
-# dram__bytes_read.sum + dram__bytes_write.sum of one yolo_v8_scan_kernel launch at b32 on the dense synthetic heads,
-# from the `ncu --set full` capture summarised in profiles/r01k_full_ncu.csv (90.30 MB read + 2.5 MB written)
-NCU_SCAN_DRAM_BYTES_B32 = 92_800_000
-METRIC = "end_to_end_fps_yolov8n_640_b32 (pre-process + fused decode + NMS); decode+NMS us/frame alongside"
-WORKLOAD = "YOLOv8n 640x640 b32/GPU: letterbox preprocess + YoloLayer decode + NMS, synthetic (SURVEY 8d), fp32 heads"
+LETTERBOX_BYTES_PER_IMAGE = NET * NET * 3 + 3 * NET * NET * 4                  # 6 144 000 B, SURVEY 8d
+MIN_TIMED_S = 0.35
 
 
 def _env_int(name, default):
@@ -52,8 +66,23 @@ def _env_int(name, default):
         return default
 
 
+def config_dict(name: str, world: int) -> dict:
+    """Identical in both arms (the driver compares it)."""
+    c = CONFIGS[name]
+    return {"workload": c["workload"], "config": name, "batch_per_gpu": c["batch"], "global_batch": c["batch"] * world,
+            "net": [NET, NET], "num_classes": NC, "max_out": MAX_OUT, "conf_thresh": c["conf"], "nms_thresh": c["iou"],
+            "stages": "plugin chain" if name == "rcnn_b8" else "pre-process + decode + NMS", "data": "synthetic, seeded (tensorrtx_b200/synth.py)"}
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 # --------------------------------------------------------------------------------------------------
-# clocks: sample nvidia-smi DURING the timed regions (B200_PROFILING.md "clocks line")
+# clocks: nvidia-smi sampled DURING the timed regions (B200_PROFILING.md "clocks line")
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -61,17 +90,14 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self._t = threading.Thread(target=self._pump, daemon=True)
-            self._t.start()
+            threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -88,144 +114,393 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, windows):
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, inside = [], [], set(), 0
         for ts, line in self.lines:
-            if not any(a <= ts <= b for a, b in windows):
-                continue
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 9 or not any(a <= ts <= b for a, b in windows):
                 continue
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
             except ValueError:
                 continue
+            inside += 1
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:  # timed regions shorter than the sampling period: fall back to every sample taken
-            for ts, line in self.lines:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[1]))
-                    smax.append(float(f[2]))
-                except (ValueError, IndexError):
-                    pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": inside, "sampled": "inside the timed windows only (100 ms period)"}
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU comparator: the reference's decode (restated, it only exists as a GPU kernel) + its host nms()
-# (oracle/ is test infrastructure; this leg and --impl reference are the only product-side users)
+# CPU side: the reference's own CPU code where it exists (oracle/_ref, compiled from /root/reference: host nms()),
+# the oracle's restatement where the reference only has a GPU kernel (decode), the reference's Python CPU pre-process
+# (yolov8/yolov8_det_trt.py:207-253, cv2).  oracle/ is test infrastructure: only this leg and --impl reference use it.
 # --------------------------------------------------------------------------------------------------
-def cpu_decode_nms_fps(heads_np, total_frames: int, threads: int):
-    """Run oracle decode+nms over `total_frames` frames (cycling through the batch) on `threads` host
-    threads (one frame per call; ctypes releases the GIL).  Returns (fps, kept_checksum)."""
-    import ctypes as C
+class CpuPath:
+    def __init__(self, name: str):
+        import numpy as np
 
+        from oracle import oracle as O
+
+        self.np, self.O, self.name, self.cfg = np, O, name, CONFIGS[name]
+        self.lib = O.load()
+        self.lib.oracle_yolov8_decode_nms_image.restype = C.c_int
+        self.ref, self.ref_O0 = None, None
+        stem = {"v8n_b32": "yolov8", "v5s_b1": "yolov5", "retina_b16": "retina"}.get(name)
+        if stem:
+            for attr, suffix in (("ref", ""), ("ref_O0", "_O0")):
+                p = ROOT / "oracle" / "_ref" / f"libref_{stem}_host{suffix}.so"
+                if p.exists():
+                    try:
+                        setattr(self, attr, C.CDLL(str(p)))
+                    except OSError:
+                        pass
+        self.nms_kind = "reference" if self.ref is not None else "port"
+        try:
+            import cv2
+            cv2.setNumThreads(1)  # one frame per Python thread; cv2 releases the GIL
+            self.cv2 = cv2
+        except Exception:
+            self.cv2 = None
+
+    # ---- stages, one frame each ----
+    def preprocess(self, frame):
+        """preprocess_image of the reference's Python driver (yolov8/yolov8_det_trt.py:207-253): cvtColor, resize, pad 128,
+        /255, HWC->CHW.  Falls back to the oracle's warp-affine restatement when cv2 is missing."""
+        np, cv2 = self.np, self.cv2
+        if cv2 is None:
+            return self.O.warpaffine(frame, NET, NET)
+        h, w = frame.shape[:2]
+        image = cv2.cvtColor(frame, cv2.COLOR_BGR2RGB)
+        r_w, r_h = NET / w, NET / h
+        if r_h > r_w:
+            tw, th = NET, int(r_w * h)
+            tx1 = tx2 = 0
+            ty1 = int((NET - th) / 2)
+            ty2 = NET - th - ty1
+        else:
+            tw, th = int(r_h * w), NET
+            tx1 = int((NET - tw) / 2)
+            tx2 = NET - tw - tx1
+            ty1 = ty2 = 0
+        image = cv2.resize(image, (tw, th))
+        image = cv2.copyMakeBorder(image, ty1, ty2, tx1, tx2, cv2.BORDER_CONSTANT, None, (128, 128, 128))
+        image = image.astype(np.float32)
+        image /= 255.0
+        return np.ascontiguousarray(np.transpose(image, [2, 0, 1]))
+
+    def make_worker_state(self):
+        np = self.np
+        if self.name == "retina_b16":
+            tp = self.O.retina_total_priors(NET, NET)
+            return {"rows": np.zeros(1 + tp * 15, np.float32), "res": np.zeros(tp * 15, np.float32), "tp": tp}
+        F = 38 if self.name == "v5s_b1" else 90
+        return {"rows": np.zeros(1 + MAX_OUT * F, np.float32), "res": np.zeros(MAX_OUT * F, np.float32), "F": F}
+
+    def decode(self, heads, b, st):
+        """Restated CalDetection (the reference has no CPU decode) for image b -> plugin rows in st['rows']."""
+        np, lib = self.np, self.lib
+        ptrs = (C.c_void_p * 3)(*[h[b].ctypes.data for h in heads])
+        g = (C.c_int * 3)(*[NET // s for s in STRIDES])
+        if self.name == "v8n_b32":
+            lib.oracle_yolov8_decode(ptrs, 1, 3, g, g, (C.c_int * 3)(*STRIDES), NC, 17, C.c_float(0.0), 0, 0, 0, MAX_OUT, 90,
+                                     C.c_float(0.1), st["rows"].ctypes.data_as(C.c_void_p), None)
+        elif self.name == "v5s_b1":
+            from tensorrtx_b200 import synth
+            anc = np.ascontiguousarray(np.asarray(synth.V5_ANCHORS, np.float32).reshape(-1))
+            lib.oracle_yolov5_decode(ptrs, 1, 3, g, g, anc.ctypes.data_as(C.c_void_p), NC, NET, NET, 0, MAX_OUT, 38, C.c_float(0.1),
+                                     st["rows"].ctypes.data_as(C.c_void_p), None)
+        else:
+            lib.oracle_retina_decode(ptrs, 1, NET, NET, C.c_double(0.02), st["rows"].ctypes.data_as(C.c_void_p), None)
+
+    def nms(self, st, lib=None) -> int:
+        """The reference's compiled host nms() when oracle/_ref has it, else the oracle's restatement."""
+        lib = self.ref if lib is None else lib
+        rows, res, c = st["rows"], st["res"], self.cfg
+        if lib is not None:
+            if self.name == "v8n_b32":
+                return lib.ref_v8_nms(rows.ctypes.data_as(C.c_void_p), C.c_float(c["conf"]), C.c_float(c["iou"]), res.ctypes.data_as(C.c_void_p))
+            if self.name == "v5s_b1":
+                return lib.ref_v5_nms(rows.ctypes.data_as(C.c_void_p), C.c_float(c["conf"]), C.c_float(c["iou"]), res.ctypes.data_as(C.c_void_p))
+            return lib.ref_retina_nms(rows.ctypes.data_as(C.c_void_p), C.c_float(c["iou"]), res.ctypes.data_as(C.c_void_p))
+        variant, F, mr = (2, 15, st["tp"]) if self.name == "retina_b16" else ((1, 38, MAX_OUT) if self.name == "v5s_b1" else (0, 90, MAX_OUT))
+        self.lib.oracle_nms.restype = C.c_int
+        return self.lib.oracle_nms(variant, rows.ctypes.data_as(C.c_void_p), mr, F, C.c_double(c["conf"]), C.c_float(c["iou"]),
+                                   res.ctypes.data_as(C.c_void_p), None)
+
+    def cv2_nms(self, st) -> int:
+        """Row B3: cv2.dnn.NMSBoxes(Batched) on the decoded boxes (the comparator the north star names)."""
+        np, cv2 = self.np, self.cv2
+        F = 15 if self.name == "retina_b16" else st["F"]
+        n = int(st["rows"][0])
+        n = min(n, (len(st["rows"]) - 1) // F)
+        r = st["rows"][1:1 + n * F].reshape(n, F)
+        if n == 0:
+            return 0
+        if self.name == "v5s_b1":
+            boxes = np.stack([r[:, 0] - r[:, 2] / 2, r[:, 1] - r[:, 3] / 2, r[:, 2], r[:, 3]], 1)
+        else:
+            boxes = np.stack([r[:, 0], r[:, 1], r[:, 2] - r[:, 0], r[:, 3] - r[:, 1]], 1)
+        if self.name == "retina_b16":
+            keep = cv2.dnn.NMSBoxes(boxes.tolist(), r[:, 4].tolist(), float(self.cfg["conf"]), float(self.cfg["iou"]))
+        else:
+            keep = cv2.dnn.NMSBoxesBatched(boxes.tolist(), r[:, 4].tolist(), r[:, 5].astype(int).tolist(), float(self.cfg["conf"]),
+                                           float(self.cfg["iou"]))
+        return len(keep)
+
+    # ---- timed loops ----
+    def run(self, fn, total: int, threads: int) -> float:
+        """fn(frame_index, worker_state); `total` frames over `threads` Python threads (ctypes / cv2 / numpy release the
+        GIL inside the heavy calls).  Returns frames/s."""
+        gate = threading.Barrier(threads + 1)
+
+        def worker(tid):
+            st = self.make_worker_state()
+            fn(tid, st)          # untimed: first touch of the worker's buffers, lazy symbol binding
+            gate.wait()
+            for f in range(tid, total, threads):
+                fn(f, st)
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+        for t in ts:
+            t.start()
+        gate.wait()
+        t0 = time.perf_counter()
+        for t in ts:
+            t.join()
+        return total / (time.perf_counter() - t0)
+
+
+def cpu_inputs(name: str, seed: int = 0):
+    from tensorrtx_b200 import synth
+    B = CONFIGS[name]["batch"]
+    if name == "v8n_b32":
+        heads = synth.yolov8_heads(B, seed=seed, nc=NC, net_w=NET, net_h=NET, strides=STRIDES)
+    elif name == "v5s_b1":
+        heads = synth.yolov5_heads(B, seed=seed)
+    else:
+        heads = synth.retina_heads(B, seed=seed)
+    return heads, synth.frames(B, seed=77 + seed, h=NET, w=NET)
+
+
+def cpu_full_path(cp: CpuPath, heads, frames, total: int, threads: int):
+    """pre-process + decode + NMS per frame -> (frames/s, kept rows)."""
+    B = frames.shape[0]
+    kept = [0]
+
+    def fn(f, st):
+        cp.preprocess(frames[f % B])
+        cp.decode(heads, f % B, st)
+        kept[0] += cp.nms(st)
+    if not getattr(cp, "_warm", False):  # the first multi-threaded pass of a process runs far below speed: untimed
+        cp.run(fn, max(B, threads), threads)
+        cp._warm = True
+        kept[0] = 0
+    return cp.run(fn, total, threads), kept[0]
+
+
+def cpu_rows(cp: CpuPath, heads, frames, cores: int) -> dict:
+    """B1 NMS only (-O2 / -O0, 1 and 8 threads), B2 decode + NMS, B3 cv2.dnn.NMSBoxes; us/frame."""
+    B = frames.shape[0]
+    rows = {}
+    st0 = [cp.make_worker_state() for _ in range(B)]
+    for b in range(B):
+        cp.decode(heads, b, st0[b])
+    decoded = [s["rows"].copy() for s in st0]
+
+    def nms_only(lib):
+        def fn(f, st):
+            st["rows"][:] = decoded[f % B]
+            cp.nms(st, lib)
+        return fn
+    n1, n8 = max(B, 64), max(B, 8 * 32)
+    cp.run(nms_only(cp.ref), n8, min(8, cores))  # untimed: the first multi-threaded pass of a process runs far below speed
+    for label, lib in (("O2", cp.ref), ("O0", cp.ref_O0)):
+        if lib is None and label == "O0":
+            continue
+        rows[f"B1_nms_only_{label}_1thread_us"] = 1e6 / cp.run(nms_only(lib), n1, 1)
+        rows[f"B1_nms_only_{label}_8threads_us"] = 1e6 / cp.run(nms_only(lib), n8, min(8, cores)) * 1.0
+    rows["B1_kind"] = cp.nms_kind + (" (compiled from /root/reference into oracle/_ref)" if cp.ref is not None else " (oracle restatement)")
+
+    def dec_nms(f, st):
+        cp.decode(heads, f % B, st)
+        cp.nms(st)
+    rows["B2_decode_nms_1thread_us"] = 1e6 / cp.run(dec_nms, max(B, 32), 1)
+    rows["B2_decode_nms_8threads_us"] = 1e6 / cp.run(dec_nms, n8, min(8, cores))
+    rows["B2_decode_nms_all_cores_us"] = 1e6 / cp.run(dec_nms, max(n8, 16 * cores), cores)
+    if cp.cv2 is not None:
+        def b3(f, st):
+            st["rows"][:] = decoded[f % B]
+            cp.cv2_nms(st)
+        rows["B3_cv2_dnn_NMSBoxes_1thread_us"] = 1e6 / cp.run(b3, max(B, 32), 1)
+
+        def pre(f, st):
+            cp.preprocess(frames[f % B])
+        rows["preprocess_cv2_1thread_us"] = 1e6 / cp.run(pre, max(B, 32), 1)
+    rows["note"] = ("us per frame; 8-thread / all-core rows = one frame per thread, throughput-equivalent us; decode = restated "
+                    "CalDetection (the reference decodes on the GPU only)")
+    return rows
+
+
+def rcnn_cpu(total_batches: int):
+    """The four rcnn plugins restated on one host thread per image batch (the reference has no CPU path for them)."""
     import numpy as np
 
     from oracle import oracle as O
-
-    lib = O.load()
-    lib.oracle_yolov8_decode_nms_image.restype = C.c_int
-    B = heads_np[0].shape[0]
-    gh = (C.c_int * 3)(*[NET // s for s in STRIDES])
-    gw = (C.c_int * 3)(*[NET // s for s in STRIDES])
-    st = (C.c_int * 3)(*STRIDES)
-    kept = [0] * threads
-
-    def worker(tid):
-        scratch = np.zeros(1 + MAX_OUT * 90, np.float32)
-        res = np.zeros(MAX_OUT * 90, np.float32)
-        ptrs = (C.c_void_p * 3)()
-        for f in range(tid, total_frames, threads):
-            b = f % B
-            for l in range(3):
-                ptrs[l] = heads_np[l][b].ctypes.data
-            kept[tid] += lib.oracle_yolov8_decode_nms_image(ptrs, 3, gh, gw, st, NC, MAX_OUT, 90, C.c_float(0.1),
-                                                            C.c_float(CONF), C.c_float(IOU),
-                                                            scratch.ctypes.data_as(C.c_void_p),
-                                                            res.ctypes.data_as(C.c_void_p))
-
-    ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
+    from tensorrtx_b200 import synth
+    B = CONFIGS["rcnn_b8"]["batch"]
+    anchors = synth.rcnn_anchors()
+    scores, deltas = synth.rpn_inputs(B, seed=0)
+    cls_scores, box_deltas, _ = synth.predictor_inputs(B, seed=1)
     t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    dt = time.perf_counter() - t0
-    return total_frames / dt, sum(kept)
-
-
-def host_cores() -> int:
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+    for _ in range(total_batches):
+        s6, b6 = O.rpn_decode(scores, deltas, 800, 1067, 16.0, anchors, 6000)
+        props = O.rpn_nms(s6, b6, 1000, 0.7)
+        s, b, c = O.predictor_decode(cls_scores, box_deltas, props, 800, 1067, (10.0, 10.0, 5.0, 5.0))
+        O.batched_nms(1, s, b, c, 100, 0.5)
+    return total_batches * B / (time.perf_counter() - t0)
 
 
 def run_reference(args, rank: int, world: int):
-    """--impl reference: the reference's CPU-side decode+NMS on the box's host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the same stages on the box's host cores (rank 0 only):
+    pre-process (the reference's Python/cv2 letterbox) + decode (restated plugin kernel) + nms() (compiled reference code)."""
     if rank != 0:
         return
-    from tensorrtx_b200 import synth
-
-    cores = host_cores()
-    heads = synth.yolov8_heads(BATCH, seed=0, nc=NC, net_w=NET, net_h=NET, strides=STRIDES)
-    frames_per_step = BATCH * max(1, cores // 8)  # bounded sample: ~0.1-0.2 s per step
-    for _ in range(args.warmup if args.warmup < 3 else 3):
-        cpu_decode_nms_fps(heads, frames_per_step, cores)
-    t0 = time.perf_counter()
-    kept = 0
-    for _ in range(args.steps):
-        _, k = cpu_decode_nms_fps(heads, frames_per_step, cores)
-        kept += k
-    dt = time.perf_counter() - t0
-    fps = frames_per_step * args.steps / dt
-    sample = f"{frames_per_step} frames/step x {args.steps} steps of the b32 synthetic set, {cores} threads"
+    name, cores = args.config, host_cores()
+    cfg = CONFIGS[name]
+    if name == "rcnn_b8":
+        per_step = 1
+        for _ in range(min(args.warmup, 2)):
+            rcnn_cpu(1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fps = rcnn_cpu(per_step)
+        dt = time.perf_counter() - t0
+        fps = per_step * cfg["batch"] * args.steps / dt
+        kind, cores_used, sample, kept = "port", 1, f"{per_step} batch of 8 per step x {args.steps} steps, single thread (oracle restatement)", None
+    else:
+        cp = CpuPath(name)
+        heads, frames = cpu_inputs(name)
+        frames_per_step = max(cfg["batch"], cfg["batch"] * max(1, cores // 8))  # bounded sample: ~0.1-0.3 s per step
+        for _ in range(min(args.warmup, 3)):
+            cpu_full_path(cp, heads, frames, frames_per_step, cores)
+        t0 = time.perf_counter()
+        kept = 0
+        for _ in range(args.steps):
+            _, k = cpu_full_path(cp, heads, frames, frames_per_step, cores)
+            kept += k
+        dt = time.perf_counter() - t0
+        fps = frames_per_step * args.steps / dt
+        kind = "port" if cp.nms_kind == "port" else "reference (nms + pre-process) + port (decode)"
+        cores_used = cores
+        sample = (f"{frames_per_step} frames/step x {args.steps} steps of the synthetic set, {cores} threads; pre-process = "
+                  f"{'cv2 letterbox of yolov8_det_trt.py' if cp.cv2 is not None else 'oracle warp-affine'}, decode = restated CalDetection, "
+                  f"nms = {cp.nms_kind}")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU decode (restated CalDetection, the reference has no CPU decode) + "
-                   "reference nms() restatement, oracle/trtx_oracle.c; pre-process not included"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(name, max(1, args.gpus)),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores_used, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "decode_nms_us_per_frame": 1e6 / fps, "kept_rows": kept,
+        "us_per_frame": 1e6 / fps, "kept_rows": kept,
     }))
 
 
 # --------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated to defeat the 126 MB L2")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of CUDA graphs")
-    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"])
-    ap.add_argument("--no-overlap", action="store_true", help="letterbox, scan and NMS strictly one after another")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+# GPU side
+# --------------------------------------------------------------------------------------------------
+def scan_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per yolo_v8_scan_kernel launch, from the committed summary of an
+    `ncu --set full` capture of THIS kernel source (profiles/scan_traffic.json records the source hash); None otherwise."""
+    try:
+        j = json.loads((ROOT / "profiles" / "scan_traffic.json").read_text())
+        h = hashlib.sha256()
+        for f in ("yolo_decode.cu", "yolo_layout.cuh", "common.cuh"):
+            h.update((ROOT / "tensorrtx_b200" / "csrc" / f).read_bytes())
+        if j.get("src_sha256") == h.hexdigest():
+            return j
+    except Exception:
+        pass
+    return None
 
-    rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
 
-    import numpy as np
+def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None):
+    """W warm-up steps, then blocks of exactly K steps; returns (mean ms per block, [(t0, t1) wall windows], n_blocks)."""
+    import torch
+
+    def block(first):
+        if pre is not None:
+            pre()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(stream)
+        for i in range(K):
+            step(first + i)
+        if flush is not None:
+            flush(first + K - 1)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        t1 = time.time()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (t0, t1)
+
+    for i in range(W):
+        step(i)
+    if flush is not None:
+        flush(W - 1)
+    ms0, w0 = block(W)
+    n = max(1, math.ceil(MIN_TIMED_S * 1e3 / max(ms0, 1e-3)))   # same on every rank: ms0 is the max over ranks
+    n = min(n, 4000)
+    res, wins = [ms0], [w0]
+    for b in range(1, n):
+        ms, w = block(W + b * K)
+        res.append(ms)
+        wins.append(w)
+    return sum(res) / len(res), wins, len(res)
+
+
+def time_kernel_loop(fn, n, stream, dev):
+    import torch
+    for i in range(5):
+        fn(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(n):
+        fn(i)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / n
+
+
+def peak_hbm():
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_v8(args, rank, world, local_rank):
+    import numpy as np  # noqa: F401
     import torch
 
     from tensorrtx_b200 import _lib as L
     from tensorrtx_b200 import synth
-    from tensorrtx_b200.pipeline import DetectionPipeline, GatherRing
+    from tensorrtx_b200.pipeline import DetectionPipeline, GatherRing, PeerGather
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    cfg = CONFIGS["v8n_b32"]
+    BATCH, CONF, IOU = cfg["batch"], cfg["conf"], cfg["iou"]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -236,76 +511,84 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     # ---- synthetic inputs: `sets` distinct batches so consecutive steps never hit L2-resident data ----
-    R = max(1, args.sets)
+    R = max(2, args.sets)
     head_dtype = L.F32 if args.head_dtype == "f32" else L.F16
     tdt = torch.float32 if head_dtype == L.F32 else torch.float16
-    heads_np0 = None
-    head_sets, frame_sets_host = [], []
+    head_sets, frame_sets_host, heads_np0, frames_np0 = [], [], None, None
     for i in range(R):
         hn = synth.yolov8_heads(BATCH, seed=1000 * rank + i, nc=NC, net_w=NET, net_h=NET, strides=STRIDES)
+        fn_ = synth.frames(BATCH, seed=77 + 1000 * rank + i, h=NET, w=NET)
         if i == 0:
-            heads_np0 = hn
+            heads_np0, frames_np0 = hn, fn_
         head_sets.append([torch.from_numpy(h).to(dev).to(tdt).contiguous() for h in hn])
-        frame_sets_host.append(torch.from_numpy(synth.frames(BATCH, seed=77 + 1000 * rank + i, h=NET, w=NET)).pin_memory())
-    frame_sets_dev = [f.to(dev) for f in frame_sets_host]
+        frame_sets_host.append(torch.from_numpy(fn_).pin_memory())
     head_bytes = sum(h.numel() * h.element_size() for h in head_sets[0])
     assert head_dtype != L.F32 or head_bytes == BATCH * ALGO_BYTES_PER_IMAGE
 
-    pipe = DetectionPipeline(BATCH, NET, NET, NET, NET, NC, STRIDES, MAX_OUT, CONF, IOU, dev, head_dtype=head_dtype)
+    def new_pipe():
+        return DetectionPipeline(BATCH, NET, NET, NET, NET, NC, STRIDES, MAX_OUT, CONF, IOU, dev, head_dtype=head_dtype)
+    pipe = new_pipe()
     stream = torch.cuda.Stream(dev)
-    gathered = None
-
-    # device-resident step i: frames of set i (already in HBM) -> preprocess -> decode+NMS (-> all-gather)
     pipes_dev = []
     for i in range(R):
-        p = pipe if i == 0 else DetectionPipeline(BATCH, NET, NET, NET, NET, NC, STRIDES, MAX_OUT, CONF, IOU, dev,
-                                                  head_dtype=head_dtype)
-        p.frames_dev.copy_(frame_sets_dev[i])
+        p = pipe if i == 0 else new_pipe()
+        p.frames_dev.copy_(frame_sets_host[i])
         pipes_dev.append(p)
-    del frame_sets_dev
 
     with torch.cuda.stream(stream):
-        # N > 1: the fixed-size all-gather of step i-1 rides a side stream WHILE step i computes, as a parallel branch
-        # of step i's CUDA graph (tensorrtx_b200.pipeline.GatherRing): every step still issues exactly one collective,
-        # and the last step's is flushed before the closing event.
-        ring = GatherRing(world, BATCH, pipe.fused.out.shape[1], dev, slots=R)
+        # ---- N > 1: the gather.  Preferred: fused into the NMS kernel over NVLink peer memory (no collective kernel);
+        #      fallback: one NCCL all-gather per step on a side stream as a parallel graph branch (round 1).
+        peer, ring, gather_mode = None, GatherRing(world, BATCH, pipe.fused.out.shape[1], dev, slots=R), "none"
+        if world > 1 and not args.nccl_gather:
+            try:
+                peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=4)
+                gather_mode = "fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel"
+            except Exception as e:
+                print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
+                peer = None
+            ok = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+            if int(ok.item()) == 0 and peer is not None:
+                peer.close()
+                peer = None
+        use_ring = world > 1 and peer is None
 
         def make_step(j):
             p, h, prev = pipes_dev[j], head_sets[j], pipes_dev[(j - 1) % R]
 
             def f():
-                if world > 1:
+                if use_ring:
                     ring.launch(prev.fused.out, (j - 1) % R)  # fork: detections of the previous step
-                p.run_device(h, overlap=not args.no_overlap)
-                ring.join()                                    # join the side stream (ends the graph's second branch)
+                p.run_device(h, overlap=not args.no_overlap, peer_gather=peer)
+                ring.join()
             return f
 
-        if world > 1:  # NCCL communicator and buffers must exist before anything is captured
+        if use_ring:  # NCCL communicator and buffers must exist before anything is captured
             ring.launch(pipes_dev[0].fused.out, 0)
             ring.join()
             torch.cuda.synchronize(dev)
-        gather_mode = "none" if world == 1 else "graph-branch"
-        needs_flush = world > 1  # make_step() gathers the PREVIOUS step's detections
+            gather_mode = "NCCL all-gather of [32, 1+1000*7] fp32 per step, overlapped with the next step as a graph branch"
+        needs_flush = use_ring  # make_step() gathers the PREVIOUS step's detections
+        if world > 1:
+            dist.barrier()  # ranks enter the (eager warm-up + capture) steps together: the gather's wait kernel gives up after ~2 s
         if args.no_graph:
             dev_steps = [make_step(j) for j in range(R)]
-            gather_mode = "none" if world == 1 else "side-stream"
         else:
             try:
                 dg = [pipe.capture(make_step(j), "thread_local" if world > 1 else "global") for j in range(R)]
                 dev_steps = [g.replay for g in dg]
             except Exception as e:  # NCCL refused to be captured: graphs for the kernels, eager collective on the side stream
-                if world == 1:
+                if not use_ring:
                     raise
-                print(f"[bench] capturing the all-gather failed ({type(e).__name__}: {e}); falling back to an eager gather",
-                      file=sys.stderr)
+                print(f"[bench] capturing the all-gather failed ({type(e).__name__}: {e}); eager gather", file=sys.stderr)
                 torch.cuda.synchronize(dev)
-                gather_mode = "side-stream, eager"
+                gather_mode += " (eager, not captured)"
                 needs_flush = False
                 dgc = [p.capture(lambda p=p, h=h: p.run_device(h, overlap=not args.no_overlap)) for p, h in zip(pipes_dev, head_sets)]
 
                 def make_eager(j):
                     def f():
-                        ring.reuse(j)  # the collective that last read this slot must be done before it is overwritten
+                        ring.reuse(j)
                         dgc[j].replay()
                         ring.launch(pipes_dev[j].fused.out, j)
                     return f
@@ -317,87 +600,41 @@ def main():
         def flush_dev(i_last):
             if needs_flush:
                 ring.launch(pipes_dev[i_last % R].fused.out, i_last % R)
-                ring.join()
+            ring.join()
 
         def step_e2e(i):
-            # public API call with HOST frames: H2D (copy stream, double-buffered) + preprocess + decode + NMS + D2H
-            ring.join()  # one pipeline, one output buffer: the previous step's collective must have read it
-            pipe.submit(frame_sets_host[i % R], head_sets[i % R])
-            if world > 1:
-                ring.launch(pipe.fused.out, i % R)
-
-        def timed(step, K, W, flush=None):
-            for i in range(W):
-                step(i)
+            # public API call with HOST frames: H2D (copy stream, double-buffered) + pre-process + decode + NMS + D2H
             ring.join()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.time()
-            e0.record(stream)
-            for i in range(K):
-                step(W + i)
-            if flush is not None:
-                flush(W + K - 1)  # the last step's collective
-            ring.join()  # every collective of the timed steps completes inside the timed region
-            e1.record(stream)
-            torch.cuda.synchronize(dev)
-            t1 = time.time()
-            if world > 1:
-                dist.barrier()
-            ms = e0.elapsed_time(e1)
-            if world > 1:
-                t = torch.tensor([ms], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            return ms, (t0, t1)
+            pipe.submit(frame_sets_host[i % R], head_sets[i % R], peer_gather=peer)
+            if use_ring:
+                ring.launch(pipe.fused.out, i % R)
 
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
             time.sleep(0.25)
         K, W = args.steps, args.warmup
-        ms_dev, win_dev = timed(step_dev, K, W, flush_dev)
-        ms_e2e, win_e2e = timed(step_e2e, K, W)
+        ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev)
+        ms_e2e, win_e2e, nb_e2e = timed_blocks(step_e2e, K, W, stream, dev, world, dist, lambda i: ring.join())
+        gather_err = peer.error() if peer is not None else 0
 
-        # ---- decode+NMS only (the "decode+NMS us/frame" half of the metric) and the scan kernel alone,
-        #      launched unfused with CUDA events around the scan kernel on its launching stream ----
-        fused = pipe.fused
-        for i in range(W):
-            fused.enqueue(BATCH, head_sets[i % R])
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(K):
-            fused.enqueue(BATCH, head_sets[(W + i) % R])
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms_decnms = e0.elapsed_time(e1) / K
-
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for i in range(K):
-            h = head_sets[(W + i) % R]
-            ev[i][0].record(stream)
-            fused.enqueue_scan(BATCH, h)
-            ev[i][1].record(stream)
-            fused.enqueue_nms(BATCH, h)
-        torch.cuda.synchronize(dev)
-        scan_ms = [a.elapsed_time(b) for a, b in ev]
-        scan_ms_avg = sum(scan_ms) / len(scan_ms)
-        # back-to-back scan launches between two events (amortises the event overhead)
-        e0.record(stream)
-        for i in range(K):
-            fused.enqueue_scan(BATCH, head_sets[(W + i) % R])
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        scan_ms_b2b = e0.elapsed_time(e1) / K
+        # ---- kernels in isolation, on the timed stream, rotating input sets (CUDA events around n launches) ----
+        fused, n_iso = pipe.fused, max(K, 100)
+        ms_decnms = time_kernel_loop(lambda i: fused.enqueue(BATCH, head_sets[i % R]), n_iso, stream, dev)
+        scan_ms_b2b = time_kernel_loop(lambda i: fused.enqueue_scan(BATCH, head_sets[i % R]), n_iso, stream, dev)
+        fused.enqueue_scan(BATCH, head_sets[0])
+        nms_ms = time_kernel_loop(lambda i: fused.enqueue_nms(BATCH, head_sets[0]), n_iso, stream, dev)
+        lb_ms = time_kernel_loop(lambda i: pipes_dev[i % R].pre.enqueue(), n_iso, stream, dev)
+        # the same scan launches inside ONE CUDA graph (how the step runs them): launch gaps are the graph's, not Python's
+        g_scan = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_scan):
+            for i in range(20):
+                fused.enqueue_scan(BATCH, head_sets[i % R])
+        scan_ms_graph = time_kernel_loop(lambda i: g_scan.replay(), 10, stream, dev) / 20
         if rank == 0:
             sampler.stop()
 
     def leave():
-        """N > 1: the step graphs hold captured NCCL kernels, and destroying the communicator under them can block;
-        drop the graphs, meet the other ranks once more, flush and leave without the interpreter's teardown."""
         if world == 1:
             return
         sys.stdout.flush()
@@ -416,59 +653,212 @@ def main():
         leave()
         return
 
-    peaks, peak_src = None, "fallback"
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        peak = 6650.0  # B200_PROFILING.md fallback
-    algo = head_bytes  # bytes one scan launch must read (all class + box rows of 32 images)
-    # average launch duration of the scan kernel: K launches on the timed stream between two CUDA events
-    achieved = algo / (scan_ms_b2b * 1e-3) / 1e9
+    peak, peak_src = peak_hbm()
+    algo = head_bytes
+    scan_ms = min(scan_ms_b2b, scan_ms_graph)
+    achieved = algo / (scan_ms * 1e-3) / 1e9
     fps = world * BATCH * K / (ms_dev * 1e-3)
     fps_e2e = world * BATCH * K / (ms_e2e * 1e-3)
+    traffic = scan_traffic() if (BATCH == 32 and head_dtype == L.F32) else None
+    lb_bytes = BATCH * LETTERBOX_BYTES_PER_IMAGE
     out = {
-        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if head_dtype == L.F32 else "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "net": [NET, NET],
-                   "num_classes": NC, "max_out": MAX_OUT, "conf_thresh": CONF, "nms_thresh": IOU,
-                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-gather of [32,1+1000*7] fp32 per step, overlapped with the next step: {gather_mode})" if world > 1 else "single GPU",
-                   "l2": f"inputs rotate over {R} distinct sets ({R * head_bytes / 1e6:.0f} MB of head tensors + "
-                         f"{R * BATCH * NET * NET * 3 / 1e6:.0f} MB of frames > 126 MB L2)",
-                   "cuda_graphs": not args.no_graph,
-                   "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
-        "clocks": sampler.summary([win_dev, win_e2e]),
+        "config": config_dict("v8n_b32", world),
+        "run": {"parallelism": f"dp{world}: batch-sharded, gather = {gather_mode}" if world > 1 else "single GPU",
+                "l2": f"inputs rotate over {R} distinct sets ({R * head_bytes / 1e6:.0f} MB of head tensors + "
+                      f"{R * BATCH * NET * NET * 3 / 1e6:.0f} MB of frames > 126 MB L2)",
+                "cuda_graphs": not args.no_graph, "overlap": "letterbox || (scan -> NMS) as parallel graph branches" if not args.no_overlap else "serial",
+                "timed_blocks": {"device": nb_dev, "e2e": nb_e2e, "steps_per_block": K, "min_timed_s": MIN_TIMED_S},
+                "gather_timeouts": gather_err,
+                "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
+        "clocks": sampler.summary(win_dev + win_e2e),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                 "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / K,
                 "note": "DetectionPipeline.submit(): frames from pinned host memory (H2D on a copy stream, double-buffered) + "
                         "compact detections back to pinned host (D2H) every step; PCIe-bound",
                 "h2d_gbps": pipe.h2d_bytes * K / (ms_e2e * 1e-3) / 1e9},
-        "gpu_launches": 3 * K,  # letterbox_kernel + yolo_v8_scan_kernel + nms_kernel per step
+        "gpu_launches": (3 + (1 if peer is not None else 0)) * K,  # letterbox + scan + nms (+ gather_wait) per step
         "decode_nms_us_per_frame": ms_decnms * 1e3 / BATCH,
         "decode_nms_ms_per_batch": ms_decnms,
+        "kernels_us": {"letterbox": lb_ms * 1e3, "scan": scan_ms_b2b * 1e3, "scan_in_graph": scan_ms_graph * 1e3, "nms": nms_ms * 1e3,
+                       "sum": (lb_ms + scan_ms_b2b + nms_ms) * 1e3, "step": ms_dev / K * 1e3},
         "roofline": {"bound": "hbm", "kernel": "yolo_v8_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
-                     "traffic": NCU_SCAN_DRAM_BYTES_B32 if BATCH == 32 and head_dtype == L.F32 else None,
-                     "algorithmic_bytes_per_launch": algo, "kernel_us": scan_ms_b2b * 1e3,
-                     "kernel_us_event_pair_per_launch": scan_ms_avg * 1e3,
-                     "achieved_event_pair_per_launch": algo / (scan_ms_avg * 1e-3) / 1e9,
-                     "copy_engine_ceiling_gbps": 5340.0,
-                     "how": "K scan launches (rotating input sets) on the timed stream between two CUDA events / K; "
-                            "kernel_us_event_pair_per_launch brackets every launch inside the unfused step loop with its own "
-                            "event pair (adds ~3 us of event latency per launch); copy_engine_ceiling = tools/tma_bench.cu, "
-                            "the same [32,84,g] fp32 tiles streamed by TMA with no compute (profiles/r01f_reg_probe.log)"},
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_source": traffic["capture"] if traffic else "no ncu capture of this kernel source committed (profiles/scan_traffic.json)",
+                     "algorithmic_bytes_per_launch": algo, "kernel_us": scan_ms * 1e3,
+                     "how": "n scan launches (rotating input sets) on the timed stream between two CUDA events / n; the smaller of "
+                            "stream launches and the same launches inside one CUDA graph (both in kernels_us)"},
+        "roofline_letterbox": {"bound": "hbm", "kernel": "letterbox_unit_kernel", "achieved": lb_bytes / (lb_ms * 1e-3) / 1e9, "peak": peak,
+                               "unit": "GB/s", "frac": lb_bytes / (lb_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": lb_bytes,
+                               "kernel_us": lb_ms * 1e3},
     }
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only (bounded sample of the same workload)
         cores = host_cores()
-        total = 128 * cores  # ~0.5 s of CPU work per core: bounded sample
-        cfps, _ = cpu_decode_nms_fps(heads_np0, total, cores)
-        c1fps, _ = cpu_decode_nms_fps(heads_np0, 64, 1)
-        out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
-                               "sample": f"{total} frames (the b32 set cycled), decode+nms oracle, {cores} threads",
-                               "single_thread_fps": c1fps, "us_per_frame_single_thread": 1e6 / c1fps}
+        cp = CpuPath("v8n_b32")
+        cfps, _ = cpu_full_path(cp, heads_np0, frames_np0, 32 * cores, cores)
+        out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores,
+                               "kind": "port" if cp.nms_kind == "port" else "reference (nms + pre-process) + port (decode)",
+                               "sample": f"{32 * cores} frames (the b32 set cycled) through cv2 letterbox + restated decode + nms(), {cores} threads",
+                               "rows": cpu_rows(cp, heads_np0, frames_np0, cores)}
     print(json.dumps(out), flush=True)
     leave()
+
+
+def run_other(args, local_rank):
+    """v5s_b1 / retina_b16 / rcnn_b8 on one GPU: same JSON shape, device-resident value + host-buffer e2e + CPU rows."""
+    import torch
+
+    from tensorrtx_b200 import plugins as P
+    from tensorrtx_b200 import synth
+    from tensorrtx_b200.pipeline import DetectionPipeline, RcnnHeadChain, RetinaPipeline
+
+    name = args.config
+    cfg = CONFIGS[name]
+    B = cfg["batch"]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(dev)
+    R = 4 if name != "v5s_b1" else 24   # input sets rotated so that consecutive steps read different HBM lines (v5s b1: 8.6 MB / set)
+    K, W = args.steps, args.warmup
+    peak, peak_src = peak_hbm()
+    roof = None
+    with torch.cuda.stream(stream):
+        if name == "rcnn_b8":
+            anchors = synth.rcnn_anchors()
+            sets = []
+            for i in range(R):
+                s, d = synth.rpn_inputs(B, seed=i)
+                cs, bd, _ = synth.predictor_inputs(B, seed=100 + i)
+                host = [torch.from_numpy(x).pin_memory() for x in (s, d, cs, bd)]
+                sets.append((host, [x.to(dev) for x in host]))
+            chain = RcnnHeadChain(B, anchors, dev)
+            graphs = [chain.capture(lambda t=t: chain.run_device(*t[1])) for t in sets]
+            step_dev = lambda i: graphs[i % R].replay()  # noqa: E731
+            stage = [torch.empty_like(x) for x in sets[0][1]]
+
+            def step_e2e(i):
+                for dst, src in zip(stage, sets[i % R][0]):
+                    dst.copy_(src, non_blocking=True)
+                fs, fb, fc = chain.run_device(*stage)
+                chain.out_host[:, :, 0].copy_(fs, non_blocking=True)
+                chain.out_host[:, :, 1:5].copy_(fb, non_blocking=True)
+                chain.out_host[:, :, 5].copy_(fc, non_blocking=True)
+            h2d = sum(x.numel() * 4 for x in sets[0][0])
+            d2h = chain.d2h_bytes
+            parts = {}
+            t = sets[0][1]
+            parts["rpn_decode"] = time_kernel_loop(lambda i: chain.p_dec.enqueue(B, [t[0], t[1]], [chain.s6, chain.b6], chain.ws), 50, stream, dev)
+            parts["rpn_nms"] = time_kernel_loop(lambda i: chain.p_nms.enqueue(B, [chain.s6, chain.b6], [chain.props], chain.ws), 50, stream, dev)
+            parts["predictor_decode"] = time_kernel_loop(lambda i: chain.p_pred.enqueue(B, [t[2], t[3], chain.props], [chain.ps, chain.pb, chain.pc], chain.ws), 50, stream, dev)
+            parts["batched_nms"] = time_kernel_loop(lambda i: chain.p_bnms.enqueue(B, [chain.ps, chain.pb, chain.pc], [chain.fs, chain.fb, chain.fc], chain.ws), 50, stream, dev)
+            kernels_us = {k: v * 1e3 for k, v in parts.items()}
+            launches = 4
+        else:
+            if name == "v5s_b1":
+                kern = [P.YoloKernel(NET // s, NET // s, a) for s, a in zip(STRIDES, synth.V5_ANCHORS)]
+                mk = lambda: DetectionPipeline(B, NET, NET, NET, NET, NC, STRIDES, MAX_OUT, cfg["conf"], cfg["iou"], dev,  # noqa: E731
+                                               plugin=P.YoloLayerPluginV5(NC, NET, NET, MAX_OUT, False, kern))
+                heads_of = lambda i: synth.yolov5_heads(B, seed=i)  # noqa: E731
+                algo_per_img = 3 * (5 + NC) * 8400 * 4
+            else:
+                mk = lambda: RetinaPipeline(B, NET, NET, 2048, dev)  # noqa: E731
+                heads_of = lambda i: synth.retina_heads(B, seed=i)  # noqa: E731
+                algo_per_img = 32 * 8400 * 4
+            pipes, head_sets, frame_host = [], [], []
+            for i in range(R):
+                p = mk()
+                f = torch.from_numpy(synth.frames(B, seed=77 + i)).pin_memory()
+                p.frames_dev.copy_(f)
+                pipes.append(p)
+                frame_host.append(f)
+                head_sets.append([torch.from_numpy(h).to(dev) for h in heads_of(i)])
+            graphs = [p.capture(lambda p=p, h=h: p.run_device(h)) for p, h in zip(pipes, head_sets)]
+            step_dev = lambda i: graphs[i % R].replay()  # noqa: E731
+            p0 = pipes[0]
+            if name == "v5s_b1":
+                step_e2e = lambda i: p0.submit(frame_host[i % R], head_sets[i % R])  # noqa: E731
+                dn = time_kernel_loop(lambda i: p0.fused.enqueue(B, head_sets[i % R]), 100, stream, dev)
+                sc = time_kernel_loop(lambda i: p0.fused.enqueue_scan(B, head_sets[i % R]), 100, stream, dev)
+                kernels_us = {"decode_nms": dn * 1e3, "scan": sc * 1e3}
+                roof_kernel = "yolo_v5_scan_kernel"
+            else:
+                step_e2e = lambda i: p0.run(frame_host[i % R], head_sets[i % R])  # noqa: E731
+                dn = time_kernel_loop(lambda i: p0.decode_nms(head_sets[i % R]), 100, stream, dev)
+                sc = time_kernel_loop(lambda i: p0.plugin.enqueue(B, head_sets[i % R], [p0.rows], p0.ws), 100, stream, dev)
+                kernels_us = {"decode_nms": dn * 1e3, "decode (scan + pack)": sc * 1e3}
+                roof_kernel = "retina_scan_kernel (+ retina_pack_kernel)"
+            lb = time_kernel_loop(lambda i: pipes[i % R].pre.enqueue(), 100, stream, dev)
+            kernels_us["letterbox"] = lb * 1e3
+            h2d, d2h = p0.h2d_bytes, p0.d2h_bytes
+            ach = B * algo_per_img / (sc * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": roof_kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": B * algo_per_img, "kernel_us": sc * 1e3,
+                    "note": "nominal bytes of SURVEY 8d: the kernel streams only the gate rows (objectness / cls) of every cell and "
+                            "touches the other rows for passing anchors, so `achieved` can exceed the peak at small batch (launch-bound)"}
+            launches = 3 if name == "v5s_b1" else 4
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.25)
+        ms_dev, win_dev, nb = timed_blocks(step_dev, K, W, stream, dev, 1, None)
+        ms_e2e, win_e2e, nb2 = timed_blocks(step_e2e, K, W, stream, dev, 1, None)
+        sampler.stop()
+    fps, fps_e2e = B * K / (ms_dev * 1e-3), B * K / (ms_e2e * 1e-3)
+    out = {"metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_dict(name, 1), "us_per_frame": ms_dev / K * 1e3 / B,
+           "run": {"cuda_graphs": True, "input_sets": R, "timed_blocks": {"device": nb, "e2e": nb2, "steps_per_block": K}},
+           "clocks": sampler.summary(win_dev + win_e2e),
+           "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                   "note": "frames (rcnn: the plugin input tensors) from pinned host memory + results back to pinned host every step"},
+           "gpu_launches": launches * K, "kernels_us": kernels_us, "roofline": roof}
+    if not args.no_cpu_baseline:
+        cores = host_cores()
+        if name == "rcnn_b8":
+            c = rcnn_cpu(2)
+            out["cpu_baseline"] = {"value": c, "unit": "frames/s", "cores": 1, "kind": "port",
+                                   "sample": "2 batches of 8 through the oracle's restatement of the four plugins, single thread"}
+        else:
+            cp = CpuPath(name)
+            heads, frames = cpu_inputs(name)
+            cf, _ = cpu_full_path(cp, heads, frames, max(B, 16) * cores // (8 if name == "retina_b16" else 1), cores)
+            out["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": cores,
+                                   "kind": "port" if cp.nms_kind == "port" else "reference (nms + pre-process) + port (decode)",
+                                   "sample": "bounded sample of the same synthetic set through cv2 letterbox + restated decode + nms()",
+                                   "rows": cpu_rows(cp, heads, frames, cores)}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--config", default="v8n_b32", choices=sorted(CONFIGS))
+    ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated to defeat the 126 MB L2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of CUDA graphs")
+    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--no-overlap", action="store_true", help="letterbox, scan and NMS strictly one after another")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather instead of the gather fused into nms_kernel")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local_rank = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    if args.config == "v8n_b32":
+        run_v8(args, rank, world, local_rank)
+    elif rank == 0:
+        run_other(args, local_rank)
 
 
 if __name__ == "__main__":

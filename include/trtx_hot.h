@@ -202,6 +202,38 @@ TRTX_API int trtx_yolo_nms_after_scan_enqueue(const trtx_yolo_params* p, const t
                                               int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
                                               trtx_stream_t stream);
 
+/* Multi-GPU gather fused into the NMS kernel (images shard by batch, the only exchange is the gather of the
+ * compact detections).  One process per GPU on one NVSwitch node; every rank owns
+ *   out   : [slots][world*batch][1 + max_det*R] fp32  -- the gathered detections (rank r's images at [r*batch, (r+1)*batch))
+ *   flags : [world][slots] uint32, zero-initialised
+ *   ctrl  : [4] uint32, zero-initialised, local only: step counter, CTAs done, error (1 = a wait timed out), spare
+ * allocated with trtx_peer_alloc (cudaMalloc + CUDA IPC handle) and mapped into the other ranks with trtx_peer_open, so
+ * that out_dev[] / flags_dev[] hold, on every rank, the addresses of all ranks' buffers ([rank] = its own).
+ * trtx_yolo_decode_nms_gather_enqueue = trtx_yolo_decode_nms_enqueue whose NMS kernel additionally stores every emitted
+ * row and the per-image count into slot (step % slots) of EVERY rank's `out` over NVLink (no collective kernel, no extra
+ * launch, no SMs beyond the NMS CTAs), then publishes flag[rank][slot] = step + 1 on every rank with system-scope release.
+ * Rows past `count` are not cleared in the gathered buffer.  trtx_gather_wait_enqueue (one warp) completes the step on
+ * the stream: it waits until all `world` flags of the slot carry the step, then advances the local step counter; work
+ * enqueued after it may read slot (step % slots) of the local `out`.  A slot is rewritten `slots` steps later (slots >= 2:
+ * a peer can only be that far ahead after this rank finished the step in between).  Every rank must enqueue the same
+ * sequence of steps.  world <= 8. */
+typedef struct trtx_gather {
+    int32_t world, rank, slots, reserved;
+    float* out_dev[8];
+    uint32_t* flags_dev[8];
+    uint32_t* ctrl_dev;
+} trtx_gather;
+TRTX_API int trtx_yolo_decode_nms_gather_enqueue(const trtx_yolo_params* p, const trtx_nms_params* q, int batch,
+                                                 const void* const* inputs_dev, float* compact_out_dev,
+                                                 int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
+                                                 const trtx_gather* gather, trtx_stream_t stream);
+TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream);
+/* Peer-mappable device memory (zero-initialised) + its 64-byte CUDA IPC handle; open / close a peer's handle; free. */
+TRTX_API int trtx_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
+TRTX_API int trtx_peer_open(const unsigned char handle[64], void** dev_ptr);
+TRTX_API int trtx_peer_close(void* dev_ptr);
+TRTX_API int trtx_peer_free(void* dev_ptr);
+
 /* =====================================================================================
  * 3. Decode_TRT (RetinaFace) -- replaces retinaface/decode.cu:110-199
  *    inputs_dev[l] : [batch, 32, (in_h/s)*(in_w/s)] fp32, s = 8,16,32, channels [bbox 2x4 | cls 2x2 | lmk 2x10]

@@ -68,6 +68,11 @@ class NmsParams(C.Structure):
     ]
 
 
+class Gather(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("slots", C.c_int32), ("reserved", C.c_int32),
+                ("out_dev", C.c_void_p * 8), ("flags_dev", C.c_void_p * 8), ("ctrl_dev", C.c_void_p)]
+
+
 class RetinaParams(C.Structure):
     _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32), ("gate", C.c_float), ("variant", C.c_int32)]
 
@@ -118,6 +123,13 @@ SYMBOLS = {
     "trtx_process_mask_enqueue": (_i, [C.POINTER(MaskParams), _i, _vp, _vp, _i, _vp, _vp]),
     "trtx_letterbox_matrix": (None, [_i, _i, _i, _i, C.POINTER(C.c_float)]),
     "trtx_abi_sizeof": (_sz, [_i]),
+    "trtx_yolo_decode_nms_gather_enqueue": (_i, [C.POINTER(YoloParams), C.POINTER(NmsParams), _i, _pp, _vp, _vp, _vp, _sz,
+                                                 C.POINTER(Gather), _vp]),
+    "trtx_gather_wait_enqueue": (_i, [C.POINTER(Gather), _vp]),
+    "trtx_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "trtx_peer_open": (_i, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "trtx_peer_close": (_i, [_vp]),
+    "trtx_peer_free": (_i, [_vp]),
 }
 
 _lib = None

@@ -25,6 +25,8 @@
 //
 // IoU arithmetic mirrors the reference's CPU functions operation by operation with round-to-nearest
 // intrinsics (no FMA contraction), so kept sets agree with the host code bit for bit.
+#include <string.h>
+
 #include "yolo_layout.cuh"
 
 namespace trtx {
@@ -71,7 +73,24 @@ struct NmsArgs {
 #endif
     float* out;           // [B, 1 + max_det*(7+extra)]
     int32_t* keep_index;  // [B, max_det] or null
+    // multi-GPU: phase F also stores every emitted row (and the count) into the gathered buffer of EVERY rank over
+    // NVLink peer memory, then the last CTA of the launch publishes a per-(rank, slot) flag (trtx_gather, trtx_hot.h)
+    struct Gather {
+        float* out[8];
+        unsigned* flags[8];
+        unsigned* ctrl;  // local: [0] step counter, [1] CTAs done, [2] error
+        int world, rank, slots;
+    } g;
 };
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ---- IoU variants -------------------------------------------------------------------------
 // Host IoUs restated by to_corners / box_area / overlaps below:
@@ -619,6 +638,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     const int R = 7 + a.extra_floats;
     float* o = a.out + (size_t)b * (1 + (size_t)a.max_det * R);
     int32_t* oidx = a.keep_index ? a.keep_index + (size_t)b * a.max_det : nullptr;
+    // gathered buffers: [slots][world*B][1 + max_det*R]; this image's block on every rank
+    const int gworld = a.g.world;
+    const unsigned gstep = gworld ? *reinterpret_cast<volatile unsigned*>(a.g.ctrl) : 0u;
+    const size_t goff = gworld ? ((size_t)(gstep % (unsigned)a.g.slots) * gworld * gridDim.x + (size_t)a.g.rank * gridDim.x + b) *
+                                         (1 + (size_t)a.max_det * R)
+                               : 0;
 
     if (greedy) {
         // ---------------- E: class segments ----------------
@@ -825,12 +850,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             row[4] = s_conf[i];
             row[5] = (float)s_cls[i];
             row[6] = s_keep[i] ? 1.0f : 0.0f;
+            for (int p = 0; p < gworld; ++p) {  // the same 28 bytes to every rank's gathered buffer (NVLink stores)
+                float* pr = a.g.out[p] + goff + 1 + (size_t)k * R;
+                pr[0] = bx.x;
+                pr[1] = bx.y;
+                pr[2] = bx.z;
+                pr[3] = bx.w;
+                pr[4] = row[4];
+                pr[5] = row[5];
+                pr[6] = row[6];
+            }
             if (oidx) oidx[k] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[i]) + 1].z)
                                              : (int)s_id[i];
             if (a.extra_floats && !a.from_tiles) {
                 const float* src = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 +
                                    (size_t)s_id[i] * a.det_floats + a.extra_offset;
                 for (int e = 0; e < a.extra_floats; ++e) row[7 + e] = src[e];
+                for (int p = 0; p < gworld; ++p)
+                    for (int e = 0; e < a.extra_floats; ++e) a.g.out[p][goff + 1 + (size_t)k * R + 7 + e] = src[e];
             }
         }
         carry += s_nkept;
@@ -842,7 +879,44 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     for (int i = n_rows_out * R + tid; i < a.max_det * R; i += kNmsThreads) o[1 + i] = 0.0f;
     if (oidx)
         for (int i = n_rows_out + tid; i < a.max_det; i += kNmsThreads) oidx[i] = -1;
+    if (gworld) {
+        // count last; rows past it are NOT cleared on the peers (consumers read `count` rows)
+        if (tid < gworld) a.g.out[tid][goff] = (float)n_rows_out;
+        __threadfence_system();  // this CTA's peer stores are visible system-wide before it counts itself done
+        __syncthreads();
+        if (tid == 0 && atomicAdd(&a.g.ctrl[1], 1u) == gridDim.x - 1) {  // last CTA of the launch: publish
+            a.g.ctrl[1] = 0u;
+            __threadfence_system();
+            for (int p = 0; p < gworld; ++p)
+                st_release_sys(a.g.flags[p] + (size_t)a.g.rank * a.g.slots + gstep % (unsigned)a.g.slots, gstep + 1u);
+        }
+    }
     TRTX_STAMP(6);
+}
+
+// Completes a gather step: spins (acquire, system scope) until every rank's flag for the current slot carries this step,
+// then advances the local step counter.  One warp; gives up after ~2 s of SM clocks (ctrl[2] = 1) instead of hanging the GPU.
+__global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
+    const unsigned s = g.ctrl[0], slot = s % (unsigned)g.slots;
+    const int lane = threadIdx.x;
+    bool ok = true;
+    if (lane < g.world) {
+        const unsigned* f = g.flags[g.rank] + (size_t)lane * g.slots + slot;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) != s + 1u) {
+            __nanosleep(100);
+            if (clock64() - t0 > 4000000000ll) {
+                ok = false;
+                break;
+            }
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    if (lane == 0) {
+        if (!ok) g.ctrl[2] = 1u;
+        g.ctrl[0] = s + 1u;
+    }
 }
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
@@ -926,9 +1000,25 @@ TRTX_API int trtx_nms_enqueue(const trtx_nms_params* p, int batch, const float* 
 }
 
 // shared by the fused call and its split form
+static int fill_gather(const trtx_gather* g, NmsArgs::Gather* o) {
+    memset(o, 0, sizeof(*o));
+    if (!g) return TRTX_OK;
+    if (g->world < 1 || g->world > 8 || g->rank < 0 || g->rank >= g->world || g->slots < 2 || !g->ctrl_dev) return TRTX_ERR_INVALID;
+    for (int r = 0; r < g->world; ++r) {
+        if (!g->out_dev[r] || !g->flags_dev[r]) return TRTX_ERR_INVALID;
+        o->out[r] = g->out_dev[r];
+        o->flags[r] = g->flags_dev[r];
+    }
+    o->ctrl = g->ctrl_dev;
+    o->world = g->world;
+    o->rank = g->rank;
+    o->slots = g->slots;
+    return TRTX_OK;
+}
+
 static int yolo_nms_tiles(const trtx_yolo_params* p, const trtx_nms_params* q, int batch, const YoloArgs& ya,
                           const YoloLayout& L, float* compact_out_dev, int32_t* keep_index_dev, void* workspace_dev,
-                          cudaStream_t st) {
+                          cudaStream_t st, const trtx_gather* gather = nullptr) {
     if (q->box_format == TRTX_BOX_OBB) return TRTX_ERR_UNSUPPORTED;  // the tile records carry no angle: use the plugin-row source
     NmsArgs a{};
     a.from_tiles = 1;
@@ -954,6 +1044,8 @@ static int yolo_nms_tiles(const trtx_yolo_params* p, const trtx_nms_params* q, i
     a.max_det = q->max_det;
     a.out = compact_out_dev;
     a.keep_index = keep_index_dev;
+    const int rc = fill_gather(gather, &a.g);
+    if (rc) return rc;
     return nms_launch(a, batch, st);
 }
 
@@ -975,6 +1067,65 @@ TRTX_API int trtx_yolo_decode_nms_enqueue(const trtx_yolo_params* p, const trtx_
     if (rc) return rc;
     return yolo_nms_tiles(p, q, batch, ya, L, compact_out_dev, keep_index_dev, workspace_dev, st);
 }
+
+TRTX_API int trtx_yolo_decode_nms_gather_enqueue(const trtx_yolo_params* p, const trtx_nms_params* q, int batch,
+                                                 const void* const* inputs_dev, float* compact_out_dev, int32_t* keep_index_dev,
+                                                 void* workspace_dev, size_t workspace_bytes, const trtx_gather* gather,
+                                                 trtx_stream_t stream) {
+    int rc = nms_validate(q);
+    if (rc) return rc;
+    if (!compact_out_dev || !gather) return TRTX_ERR_INVALID;
+    if (q->extra_floats) return TRTX_ERR_UNSUPPORTED;
+    YoloArgs ya;
+    YoloLayout L;
+    rc = yolo_fill_args(p, batch, inputs_dev, workspace_dev, workspace_bytes, &ya, &L);
+    if (rc) return rc;
+    if (p->max_out > kMaxSort) return TRTX_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = yolo_scan_launch(ya, L, p->in_dtype, batch, st);
+    if (rc) return rc;
+    return yolo_nms_tiles(p, q, batch, ya, L, compact_out_dev, keep_index_dev, workspace_dev, st, gather);
+}
+
+TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream) {
+    NmsArgs::Gather g;
+    int rc = fill_gather(gather, &g);
+    if (rc || !gather) return rc ? rc : TRTX_ERR_INVALID;
+    gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g);
+    return check_launch();
+}
+
+// ---- peer memory for the gather: cudaMalloc + CUDA IPC (one process per GPU on one NVSwitch node) ----
+TRTX_API int trtx_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]) {
+    if (!bytes || !dev_ptr || !handle) return TRTX_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        if (p) cudaFree(p);
+        return TRTX_ERR_CUDA;
+    }
+    memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return TRTX_OK;
+}
+TRTX_API int trtx_peer_open(const unsigned char handle[64], void** dev_ptr) {
+    if (!handle || !dev_ptr) return TRTX_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return TRTX_ERR_CUDA;
+    }
+    return TRTX_OK;
+}
+TRTX_API int trtx_peer_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? TRTX_OK : TRTX_ERR_CUDA; }
+TRTX_API int trtx_peer_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? TRTX_OK : TRTX_ERR_CUDA; }
 
 TRTX_API int trtx_yolo_scan_enqueue(const trtx_yolo_params* p, int batch, const void* const* inputs_dev,
                                     void* workspace_dev, size_t workspace_bytes, trtx_stream_t stream) {

@@ -22,12 +22,13 @@ class DetectionPipeline:
                  num_classes: int = 80, strides: Sequence[int] = (8, 16, 32), max_out: int = 1000,
                  conf_thresh: float = 0.5, nms_thresh: float = 0.45, device: str | torch.device = "cuda",
                  input_dtype: torch.dtype = torch.float32, head_dtype: int = L.F32,
-                 backbone: Callable[[torch.Tensor], Sequence[torch.Tensor]] | None = None):
+                 backbone: Callable[[torch.Tensor], Sequence[torch.Tensor]] | None = None, plugin=None):
+        """plugin: any YoloLayer plugin mirror (YoloLayerPluginV5 / V7 / ...); default = the yolov8 one."""
         self.batch, self.src_h, self.src_w, self.net_h, self.net_w = batch, src_h, src_w, net_h, net_w
         self.device = torch.device(device)
         self.backbone = backbone
-        self.plugin = YoloLayerPlugin(num_classes, 17, 0.0, net_w, net_h, max_out, False, False, False, strides,
-                                      in_dtype=head_dtype)
+        self.plugin = plugin if plugin is not None else YoloLayerPlugin(num_classes, 17, 0.0, net_w, net_h, max_out, False, False,
+                                                                        False, strides, in_dtype=head_dtype)
         self.fused = FusedYoloDecodeNms(self.plugin, batch, conf_thresh, nms_thresh, max_det=max_out,
                                         device=self.device, return_index=False)
         self.frames_dev = torch.empty((batch, src_h, src_w, 3), dtype=torch.uint8, device=self.device)
@@ -51,7 +52,8 @@ class DetectionPipeline:
         self.out_host.copy_(out, non_blocking=True)
         return self.out_host
 
-    def run_device(self, heads: Sequence[torch.Tensor], stream=None, overlap: bool = True) -> torch.Tensor:
+    def run_device(self, heads: Sequence[torch.Tensor], stream=None, overlap: bool = True,
+                   peer_gather: "PeerGather | None" = None) -> torch.Tensor:
         """Device-resident step: pre-process the frames already in HBM + decode + NMS (no host copies).
 
         The letterbox of this batch does not depend on the decode/NMS of the head tensors (with a real backbone the heads
@@ -60,14 +62,19 @@ class DetectionPipeline:
         the current stream, joined at the end.  Captured into a CUDA graph this becomes two concurrent branches; the
         latency-bound NMS (one CTA per image, 32 of 148 SMs) then runs underneath the HBM-bound letterbox instead of
         after it."""
+        gdesc = peer_gather.desc if peer_gather is not None else None
         if not overlap or self._side is None or stream is not None:
             self.pre.enqueue(stream)
-            out, _ = self.fused.enqueue(self.batch, heads, stream)
+            out, _ = self.fused.enqueue(self.batch, heads, stream, gather=gdesc)
+            if peer_gather is not None:
+                peer_gather.wait(stream)
             return out
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)                  # fork
         with torch.cuda.stream(self._side):
-            out, _ = self.fused.enqueue(self.batch, heads)
+            out, _ = self.fused.enqueue(self.batch, heads, gather=gdesc)
+            if peer_gather is not None:
+                peer_gather.wait()                   # one warp: the peers' rows of this step have landed
         self.pre.enqueue()
         cur.wait_stream(self._side)                  # join
         return out
@@ -87,7 +94,8 @@ class DetectionPipeline:
         self._copy_stream = torch.cuda.Stream(self.device)
         self._next = 0
 
-    def submit(self, frames_host: torch.Tensor, heads: Sequence[torch.Tensor] | None = None, slots: int = 2):
+    def submit(self, frames_host: torch.Tensor, heads: Sequence[torch.Tensor] | None = None, slots: int = 2,
+               peer_gather: "PeerGather | None" = None):
         """Asynchronous step with double buffering: returns (pinned host result, event); the result is valid
         once the event has completed.  The H2D copy is issued on a dedicated copy stream so that it overlaps
         the kernels of the previous submit() (the reference serialises memcpy -> H2D -> kernel -> sync per
@@ -105,7 +113,9 @@ class DetectionPipeline:
         sl["pre"].enqueue()
         if self.backbone is not None:
             heads = self.backbone(self.net_input)
-        out, _ = self.fused.enqueue(self.batch, heads)
+        out, _ = self.fused.enqueue(self.batch, heads, gather=peer_gather.desc if peer_gather is not None else None)
+        if peer_gather is not None:
+            peer_gather.wait()
         sl["out_host"].copy_(out, non_blocking=True)
         sl["done"].record(compute)
         return sl["out_host"], sl["done"]
@@ -122,6 +132,177 @@ class DetectionPipeline:
         with torch.cuda.graph(g, capture_error_mode=capture_error_mode):
             fn()
         return g
+
+
+class RetinaPipeline:
+    """retina_r50.cpp's per-batch loop on the device: letterbox of the frames, Decode_TRT over the three head tensors,
+    nms() with landmarks (retinaface/retina_r50.cpp:320-360, common.hpp:110-130).  Same structure as DetectionPipeline:
+    decode + NMS on a high-priority side stream next to the letterbox."""
+
+    def __init__(self, batch: int, in_h: int = 640, in_w: int = 640, max_det: int = 2048, device="cuda"):
+        from .plugins import DecodePlugin, float_le_threshold, nms_params
+
+        self.batch, self.device = batch, torch.device(device)
+        self.plugin = DecodePlugin(in_h, in_w)
+        self._lib = L.load()
+        self.frames_dev = torch.empty((batch, in_h, in_w, 3), dtype=torch.uint8, device=self.device)
+        self.net_input = torch.empty((batch, 3, in_h, in_w), dtype=torch.float32, device=self.device)
+        self.pre = PreprocessPlan(list(self.frames_dev.unbind(0)), self.net_input, in_w, in_h)
+        self.rows = torch.empty((batch, self.plugin.output_elems()), dtype=torch.float32, device=self.device)
+        self.ws = torch.empty(max(self.plugin.getWorkspaceSize(batch), 256), dtype=torch.uint8, device=self.device)
+        self.q = nms_params(L.BOX_RETINA, L.NMS_GREEDY, float_le_threshold(0.1), 0.4, max_det, False, extra_floats=10, extra_offset=5)
+        self.max_rows = self.plugin.total_priors
+        self.out = torch.empty((batch, 1 + max_det * 17), dtype=torch.float32, device=self.device)
+        import ctypes as C
+        self.nms_ws_bytes = int(self._lib.trtx_nms_workspace_size(C.byref(self.q), batch, self.max_rows))
+        self.nms_ws = torch.empty(max(self.nms_ws_bytes, 256), dtype=torch.uint8, device=self.device)
+        self.out_host = torch.empty_like(self.out, device="cpu").pin_memory()
+        self._side = torch.cuda.Stream(self.device, priority=-1)
+        self.h2d_bytes, self.d2h_bytes = self.frames_dev.numel(), self.out.numel() * 4
+
+    def decode_nms(self, heads) -> torch.Tensor:
+        import ctypes as C
+
+        from .plugins import _ptr, _stream
+        rc = self.plugin.enqueue(self.batch, heads, [self.rows], self.ws)
+        if rc:
+            L.check(rc, "trtx_retina_decode_enqueue")
+        L.check(self._lib.trtx_nms_enqueue(C.byref(self.q), self.batch, _ptr(self.rows), self.max_rows, 15, _ptr(self.out), None,
+                                           _ptr(self.nms_ws), self.nms_ws_bytes, _stream(None)), "trtx_nms_enqueue")
+        return self.out
+
+    def run_device(self, heads, overlap: bool = True) -> torch.Tensor:
+        cur = torch.cuda.current_stream(self.device)
+        if not overlap:
+            self.pre.enqueue()
+            return self.decode_nms(heads)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self.decode_nms(heads)
+        self.pre.enqueue()
+        cur.wait_stream(self._side)
+        return self.out
+
+    def run(self, frames_host: torch.Tensor, heads) -> torch.Tensor:
+        self.frames_dev.copy_(frames_host, non_blocking=True)
+        self.run_device(heads)
+        self.out_host.copy_(self.out, non_blocking=True)
+        return self.out_host
+
+    capture = DetectionPipeline.capture
+
+
+class RcnnHeadChain:
+    """The four Faster R-CNN plugins chained on one stream exactly as rcnn.cpp wires them (rcnn/rcnn.cpp:134-195):
+    RpnDecode -> RpnNms -> [RoIAlign + box head: TensorRT, not on this path; its outputs are inputs here] ->
+    PredictorDecode -> BatchedNms.  All images of the batch per launch."""
+
+    def __init__(self, batch: int, anchors, device="cuda", H: int = 50, W: int = 67, image_h: int = 800, image_w: int = 1067,
+                 pre: int = 6000, post: int = 1000, classes: int = 80, dets: int = 100, nms_method: int = 1):
+        from .plugins import BatchedNmsPlugin, PredictorDecodePlugin, RpnDecodePlugin, RpnNmsPlugin
+
+        dev = torch.device(device)
+        self.batch, self.device = batch, dev
+        self.p_dec = RpnDecodePlugin(pre, anchors, 16.0, image_h, image_w, H, W)
+        self.p_nms = RpnNmsPlugin(0.7, post, pre)
+        self.p_pred = PredictorDecodePlugin(post, image_h, image_w, (10.0, 10.0, 5.0, 5.0), classes)
+        self.p_bnms = BatchedNmsPlugin(nms_method, 0.5, dets, post)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        self.s6, self.b6, self.props = z(batch, pre), z(batch, pre, 4), z(batch, post, 4)
+        self.ps, self.pb, self.pc = z(batch, post), z(batch, post, 4), z(batch, post)
+        self.fs, self.fb, self.fc = z(batch, dets), z(batch, dets, 4), z(batch, dets)
+        self.ws = torch.empty(max(self.p_dec.getWorkspaceSize(batch), 4096), dtype=torch.uint8, device=dev)
+        self.out_host = torch.empty((batch, dets, 6), dtype=torch.float32).pin_memory()
+        self.d2h_bytes = self.out_host.numel() * 4
+
+    def run_device(self, rpn_scores, rpn_deltas, cls_scores, box_deltas):
+        for rc in (self.p_dec.enqueue(self.batch, [rpn_scores, rpn_deltas], [self.s6, self.b6], self.ws),
+                   self.p_nms.enqueue(self.batch, [self.s6, self.b6], [self.props], self.ws),
+                   self.p_pred.enqueue(self.batch, [cls_scores, box_deltas, self.props], [self.ps, self.pb, self.pc], self.ws),
+                   self.p_bnms.enqueue(self.batch, [self.ps, self.pb, self.pc], [self.fs, self.fb, self.fc], self.ws)):
+            if rc:
+                raise L.TrtxError(f"rcnn plugin enqueue failed: {rc}")
+        return self.fs, self.fb, self.fc
+
+    capture = DetectionPipeline.capture
+
+
+class _RawCuda:
+    """A raw device pointer as something torch.as_tensor can wrap (no copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2}
+
+
+class PeerGather:
+    """The gather of the compact detections FUSED into the NMS kernel (trtx_gather, include/trtx_hot.h): every rank's
+    nms_kernel stores its kept rows straight into the gathered buffer of every rank over NVLink peer memory and raises a
+    flag; `wait()` enqueues the one-warp kernel that completes the step.  No NCCL kernel competes with the step for SMs
+    (the NCCL all-gather of round 1 stretched the step by 8-20 %).
+
+    Buffers are cudaMalloc'ed by the library and exchanged between the processes of the node as CUDA IPC handles through
+    torch.distributed (object all-gather); torch is plumbing only.  `result(slot)` views this rank's gathered buffer
+    [world*batch, 1 + max_det*7]; rows past each image's count are stale."""
+
+    def __init__(self, world: int, rank: int, batch: int, cols: int, device, slots: int = 4):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        self._lib = L.load()
+        self.world, self.rank, self.batch, self.cols, self.slots = world, rank, batch, cols, slots
+        self.device = torch.device(device)
+        out_bytes = slots * world * batch * cols * 4
+        flag_bytes = world * slots * 4
+        self._own, handles = [], []
+        for nbytes in (out_bytes, flag_bytes, 16):
+            ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+            L.check(self._lib.trtx_peer_alloc(nbytes, C.byref(ptr), h), "trtx_peer_alloc")
+            self._own.append(ptr.value)
+            handles.append(bytes(h))
+        every = [None] * world
+        dist.all_gather_object(every, (rank, handles[0], handles[1]))
+        g = L.Gather()
+        g.world, g.rank, g.slots = world, rank, slots
+        self._opened = []
+        for r, h_out, h_flags in every:
+            if r == rank:
+                g.out_dev[r], g.flags_dev[r] = self._own[0], self._own[1]
+                continue
+            for k, h in ((0, h_out), (1, h_flags)):
+                ptr = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                L.check(self._lib.trtx_peer_open(buf, C.byref(ptr)), "trtx_peer_open")
+                self._opened.append(ptr.value)
+                (g.out_dev if k == 0 else g.flags_dev)[r] = ptr.value
+        g.ctrl_dev = self._own[2]
+        self.desc = g
+        self._out = torch.as_tensor(_RawCuda(self._own[0], (slots, world * batch, cols), "<f4"), device=self.device)
+        self._ctrl = torch.as_tensor(_RawCuda(self._own[2], (4,), "<u4"), device=self.device)
+        dist.barrier()  # every rank has mapped every buffer before anyone stores into them
+
+    def result(self, slot: int) -> torch.Tensor:
+        return self._out[slot]
+
+    def step_counter(self) -> int:
+        return int(self._ctrl[0].item())
+
+    def error(self) -> int:
+        return int(self._ctrl[2].item())
+
+    def wait(self, stream=None) -> None:
+        import ctypes as C
+
+        from .plugins import _stream
+        L.check(self._lib.trtx_gather_wait_enqueue(C.byref(self.desc), _stream(stream)), "trtx_gather_wait_enqueue")
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._lib.trtx_peer_close(p)
+        self._opened = []
+        for p in self._own:
+            self._lib.trtx_peer_free(p)
+        self._own = []
 
 
 def gather(local: torch.Tensor, world_size: int) -> torch.Tensor:

@@ -611,10 +611,18 @@ class FusedYoloDecodeNms:
         self.out = torch.empty((max_batch, 1 + self.max_det * 7), dtype=torch.float32, device=device)
         self.idx = torch.empty((max_batch, self.max_det), dtype=torch.int32, device=device) if return_index else None
 
-    def enqueue(self, batch: int, inputs, stream=None, out=None, idx=None):
+    def enqueue(self, batch: int, inputs, stream=None, out=None, idx=None, gather=None):
+        """gather: an L.Gather descriptor (pipeline.PeerGather.desc) -> the NMS kernel also stores its rows into every
+        rank's gathered buffer (trtx_yolo_decode_nms_gather_enqueue)."""
         ptrs = L.ptr_array([_ptr(t) for t in inputs])
         out = self.out if out is None else out
         idx = self.idx if idx is None else idx
+        if gather is not None:
+            L.check(self._lib.trtx_yolo_decode_nms_gather_enqueue(C.byref(self.plugin.params), C.byref(self.q), int(batch), ptrs,
+                                                                  _ptr(out), _ptr(idx) if idx is not None else None, _ptr(self.ws),
+                                                                  self.ws_bytes, C.byref(gather), _stream(stream)),
+                    "trtx_yolo_decode_nms_gather_enqueue")
+            return out[:batch], (idx[:batch] if idx is not None else None)
         L.check(self._lib.trtx_yolo_decode_nms_enqueue(C.byref(self.plugin.params), C.byref(self.q), int(batch), ptrs,
                                                        _ptr(out), _ptr(idx) if idx is not None else None,
                                                        _ptr(self.ws), self.ws_bytes, _stream(stream)),

@@ -1,0 +1,71 @@
+"""The gather fused into nms_kernel (trtx_gather): protocol test on ONE GPU.  Two logical ranks share the device -- each
+owns a gathered buffer, a flag array and a control block (plain device memory here; CUDA IPC mappings in production) and
+the two ranks' steps are enqueued alternately on two streams.  After every step both gathered buffers must hold both ranks'
+detections (count + kept rows) in the slot of that step, and the step counters must advance."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tensorrtx_b200 import _lib as L
+from tensorrtx_b200 import plugins as P
+from tensorrtx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fused_peer_gather_protocol_two_logical_ranks(oracle, dev):
+    lib = L.load()
+    W, B, K, SLOTS = 2, 3, 1000, 3
+    cols = 1 + K * 7
+    outs = [torch.full((SLOTS, W * B, cols), -9.0, dtype=torch.float32, device=dev) for _ in range(W)]
+    flags = [torch.zeros((W, SLOTS), dtype=torch.int32, device=dev) for _ in range(W)]
+    ctrls = [torch.zeros(4, dtype=torch.int32, device=dev) for _ in range(W)]
+    descs = []
+    for r in range(W):
+        g = L.Gather()
+        g.world, g.rank, g.slots = W, r, SLOTS
+        for p in range(W):
+            g.out_dev[p], g.flags_dev[p] = outs[p].data_ptr(), flags[p].data_ptr()
+        g.ctrl_dev = ctrls[r].data_ptr()
+        descs.append(g)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, K, False, False, False, (8, 16, 32))
+    fused = [P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev) for _ in range(W)]
+    streams = [torch.cuda.Stream(dev) for _ in range(W)]
+    n_steps = 5                                             # wraps the 3 slots
+    for step in range(n_steps):
+        heads = [synth.yolov8_heads(B, seed=900 + 10 * step + r, n_obj=12) for r in range(W)]
+        local = []
+        for r in range(W):
+            with torch.cuda.stream(streams[r]):
+                hd = [torch.from_numpy(h).to(dev) for h in heads[r]]
+                out, _ = fused[r].enqueue(B, hd, gather=descs[r])
+                L.check(lib.trtx_gather_wait_enqueue(C.byref(descs[r]), streams[r].cuda_stream), "wait")
+                local.append(out)
+        torch.cuda.synchronize()
+        slot = step % SLOTS
+        for r in range(W):
+            assert ctrls[r].cpu().tolist()[:3] == [step + 1, 0, 0]        # step advanced, CTA counter reset, no timeout
+            assert flags[r][:, slot].cpu().tolist() == [step + 1] * W
+        for r in range(W):                                                # rank r's images, as seen by every rank p
+            loc = local[r].cpu().numpy()
+            ref, _ = oracle.yolov8_decode(heads[r])
+            for p in range(W):
+                got = outs[p][slot, r * B:(r + 1) * B].cpu().numpy()
+                for b in range(B):
+                    n = int(loc[b, 0])
+                    res, _ = oracle.nms(0, ref[b], K, 90, 0.5, 0.45)
+                    assert n == len(res) and n > 3 and got[b, 0] == n
+                    assert np.array_equal(got[b, 1:1 + n * 7], loc[b, 1:1 + n * 7])   # same bytes as the local output
+    # a rank whose peers never publish gives up instead of hanging the GPU: error flag set, step still advances
+    lone = L.Gather()
+    lone.world, lone.rank, lone.slots = 2, 0, SLOTS
+    f2 = torch.zeros((2, SLOTS), dtype=torch.int32, device=dev)
+    c2 = torch.zeros(4, dtype=torch.int32, device=dev)
+    for p in range(2):
+        lone.out_dev[p], lone.flags_dev[p] = outs[0].data_ptr(), f2.data_ptr()
+    lone.ctrl_dev = c2.data_ptr()
+    L.check(lib.trtx_gather_wait_enqueue(C.byref(lone), None), "wait")
+    torch.cuda.synchronize()
+    assert c2.cpu().tolist()[:3] == [1, 0, 1]
