@@ -114,7 +114,13 @@ class Mat {
     T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <typename T>
     const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
-    Mat operator()(const Rect&) const { shim_abort("Mat::operator()(Rect)"); }
+    // scale_mask (yolov8/src/postprocess.cpp:207-226) crops then resizes: the shim only RECORDS the crop rectangle and the
+    // target size (ref_v8_scale_mask_rect reads them back); pixel work stays out of the shim
+    Mat operator()(const Rect& r) const {
+        shim_last_crop()[0] = r.x; shim_last_crop()[1] = r.y; shim_last_crop()[2] = r.width; shim_last_crop()[3] = r.height;
+        return Mat(r.height > 0 ? r.height : 0, r.width > 0 ? r.width : 0, type_, data);
+    }
+    static int* shim_last_crop() { static thread_local int v[6] = {0, 0, 0, 0, 0, 0}; return v; }
     Mat clone() const { shim_abort("Mat::clone"); }
     bool empty() const { return data == nullptr; }
     Size size() const { return Size(cols, rows); }
@@ -134,7 +140,13 @@ inline void putText(Mat&, const std::string&, Point, int, double, const Scalar&,
     shim_abort("putText");
 }
 inline Size getTextSize(const std::string&, int, double, int, int*) { shim_abort("getTextSize"); }
-inline void resize(const Mat&, Mat&, Size, double = 0, double = 0, int = 1) { shim_abort("resize"); }
+inline void resize(const Mat&, Mat& dst, Size s, double = 0, double = 0, int = 1) {
+    Mat::shim_last_crop()[4] = s.width;
+    Mat::shim_last_crop()[5] = s.height;
+    dst = Mat(0, 0, 0, nullptr);
+    dst.cols = s.width;
+    dst.rows = s.height;
+}
 inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) { shim_abort("line"); }
 inline void circle(Mat&, Point, int, const Scalar&, int = 1, int = 8, int = 0) { shim_abort("circle"); }
 inline void polylines(Mat&, const std::vector<std::vector<Point>>&, bool, const Scalar&, int = 1, int = 8, int = 0) {

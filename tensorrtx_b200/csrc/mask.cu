@@ -161,6 +161,46 @@ __global__ void __launch_bounds__(256) process_mask_kernel(const __grid_constant
     }
 }
 
+// scale_mask (yolov8/src/postprocess.cpp:207-226): cv::resize(mask(r), img.size()) for n masks in one launch.  A thread
+// produces 4 adjacent output pixels (one 16-byte store); OpenCV's float bilinear kernel as above (HResize then VResize).
+struct ScaleMaskArgs {
+    const float* in;  // [n, net_h, net_w]
+    float* out;       // [n, img_h, img_w]
+    int net_w, net_h, img_w, img_h;
+    int rx, ry, rw, rh;
+};
+__global__ void __launch_bounds__(256) scale_mask_kernel(const __grid_constant__ ScaleMaskArgs a) {
+    const int ox0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ox0 >= a.img_w || oy >= a.img_h) return;
+    const double scale_x = (double)a.rw / (double)a.img_w, scale_y = (double)a.rh / (double)a.img_h;
+    const float* src = a.in + (size_t)blockIdx.z * a.net_h * a.net_w + (size_t)a.ry * a.net_w + a.rx;
+    int sy;
+    float fy;
+    resize_tap(oy, scale_y, a.rh, sy, fy);
+    const float* r0 = src + (size_t)sy * a.net_w;
+    const float* r1 = src + (size_t)min(sy + 1, a.rh - 1) * a.net_w;
+    const float b0 = 1.0f - fy, b1 = fy;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int sx;
+        float fx;
+        resize_tap(min(ox0 + k, a.img_w - 1), scale_x, a.rw, sx, fx);
+        const int sx1 = min(sx + 1, a.rw - 1);
+        const float a0 = 1.0f - fx, a1 = fx;
+        const float h0 = __fadd_rn(__fmul_rn(__ldg(r0 + sx), a0), __fmul_rn(__ldg(r0 + sx1), a1));
+        const float h1 = __fadd_rn(__fmul_rn(__ldg(r1 + sx), a0), __fmul_rn(__ldg(r1 + sx1), a1));
+        o[k] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    }
+    float* dst = a.out + (size_t)blockIdx.z * a.img_h * a.img_w + (size_t)oy * a.img_w + ox0;
+    if (ox0 + 3 < a.img_w && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int k = 0; k < 4 && ox0 + k < a.img_w; ++k) dst[k] = o[k];
+    }
+}
+
 }  // namespace trtx
 
 using namespace trtx;
@@ -193,6 +233,44 @@ TRTX_API int trtx_process_mask_enqueue(const trtx_mask_params* p, int batch, con
     a.max_masks = p->max_masks;
     dim3 grid((p->mask_w + kMaskTile - 1) / kMaskTile, (p->mask_h + kMaskTile - 1) / kMaskTile, batch * p->max_masks);
     process_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch();
+}
+
+// the crop of scale_mask, yolov8/src/postprocess.cpp:208-222: `h = r_w * img.rows` truncates float -> int, `(kInputH - h) / 2`
+// is an integer division
+TRTX_API int trtx_scale_mask_rect(int net_w, int net_h, int img_w, int img_h, int rect[4]) {
+    if (!rect || net_w <= 0 || net_h <= 0 || img_w <= 0 || img_h <= 0) return TRTX_ERR_INVALID;
+    int x, y, w, h;
+    const float r_w = (float)(net_w / (img_w * 1.0));
+    const float r_h = (float)(net_h / (img_h * 1.0));
+    if (r_h > r_w) {
+        w = net_w;
+        h = (int)(r_w * img_h);
+        x = 0;
+        y = (net_h - h) / 2;
+    } else {
+        w = (int)(r_h * img_w);
+        h = net_h;
+        x = (net_w - w) / 2;
+        y = 0;
+    }
+    rect[0] = x;
+    rect[1] = y;
+    rect[2] = w;
+    rect[3] = h;
+    return TRTX_OK;
+}
+
+TRTX_API int trtx_scale_mask_enqueue(const float* masks_dev, int n, int net_w, int net_h, int img_w, int img_h, float* out_dev,
+                                     trtx_stream_t stream) {
+    if (!masks_dev || !out_dev || n <= 0 || n > 65535) return TRTX_ERR_INVALID;
+    int r[4];
+    const int rc = trtx_scale_mask_rect(net_w, net_h, img_w, img_h, r);
+    if (rc) return rc;
+    if (r[2] <= 0 || r[3] <= 0 || r[0] < 0 || r[1] < 0 || r[0] + r[2] > net_w || r[1] + r[3] > net_h) return TRTX_ERR_UNSUPPORTED;
+    ScaleMaskArgs a{masks_dev, out_dev, net_w, net_h, img_w, img_h, r[0], r[1], r[2], r[3]};
+    dim3 grid((img_w + 255) / 256, (img_h + 3) / 4, n);
+    scale_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch();
 }
 

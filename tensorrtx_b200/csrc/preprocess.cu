@@ -476,6 +476,60 @@ TRTX_API int trtx_get_rect(int variant, int net_w, int net_h, int img_w, int img
     return TRTX_OK;
 }
 
+// get_rect_adapt_landmark, yolov8/src/postprocess.cpp:38-69, statement by statement (ratios: double division stored to float;
+// `(kInputH - r_w * img.rows) / 2`: int - float*int in float, then / 2).
+TRTX_API int trtx_get_rect_adapt_landmark(int net_w, int net_h, int img_w, int img_h, const float bbox[4], float* lmk,
+                                          int num_kpts, int rect[4]) {
+    if (!bbox || !rect || (num_kpts > 0 && !lmk) || num_kpts < 0 || net_w <= 0 || net_h <= 0 || img_w <= 0 || img_h <= 0)
+        return TRTX_ERR_INVALID;
+    float l, r, t, b;
+    const float r_w = (float)(net_w / (img_w * 1.0));
+    const float r_h = (float)(net_h / (img_h * 1.0));
+    if (r_h > r_w) {
+        l = bbox[0] / r_w;
+        r = bbox[2] / r_w;
+        t = (bbox[1] - (net_h - r_w * img_h) / 2) / r_w;
+        b = (bbox[3] - (net_h - r_w * img_h) / 2) / r_w;
+        for (int i = 0; i < num_kpts * 3; i += 3) {
+            lmk[i] /= r_w;
+            lmk[i + 1] = (lmk[i + 1] - (net_h - r_w * img_h) / 2) / r_w;
+        }
+    } else {
+        l = (bbox[0] - (net_w - r_h * img_w) / 2) / r_h;
+        r = (bbox[2] - (net_w - r_h * img_w) / 2) / r_h;
+        t = bbox[1] / r_h;
+        b = bbox[3] / r_h;
+        for (int i = 0; i < num_kpts * 3; i += 3) {
+            lmk[i] = (lmk[i] - (net_w - r_h * img_w) / 2) / r_h;
+            lmk[i + 1] /= r_h;
+        }
+    }
+    l = 0.0f > l ? 0.0f : l;
+    t = 0.0f > t ? 0.0f : t;
+    const int rw = (int)round((double)(r - l)), rl = (int)round((double)l);
+    const int rh = (int)round((double)(b - t)), rt = (int)round((double)t);
+    const int width = rw < img_w - rl ? rw : img_w - rl, height = rh < img_h - rt ? rh : img_h - rt;
+    rect[0] = rl;
+    rect[1] = rt;
+    rect[2] = width > 0 ? width : 0;
+    rect[3] = height > 0 ? height : 0;
+    return TRTX_OK;
+}
+
+// process_decode_ptr_host, yolov8/src/postprocess.cpp:131-147
+TRTX_API int trtx_process_decode_ptr_host(const float* decode_ptr_host, int bbox_element, int count, float* rows_out) {
+    if (!decode_ptr_host || !rows_out || bbox_element < 7 || count < 0) return -TRTX_ERR_INVALID;
+    int n = 0;
+    for (int i = 0; i < count; ++i) {
+        const float* p = decode_ptr_host + 1 + (size_t)i * bbox_element;
+        if ((int)p[6] == 1) {  // `int keep_flag = decode_ptr_host[basic_pos + 6]`
+            for (int k = 0; k < 6; ++k) rows_out[(size_t)n * 6 + k] = p[k];
+            ++n;
+        }
+    }
+    return n;
+}
+
 TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, int batch, void* dst_dev, int dst_w,
                                            int dst_h, int out_dtype, trtx_stream_t stream) {
     if (!images_host || batch <= 0 || !dst_dev || dst_w <= 0 || dst_h <= 0) return TRTX_ERR_INVALID;

@@ -932,6 +932,27 @@ def get_rect(img_w: int, img_h: int, bbox, net_w: int = 640, net_h: int = 640, v
     return tuple(r)
 
 
+def get_rect_adapt_landmark(img_w: int, img_h: int, bbox, lmk, net_w: int = 640, net_h: int = 640):
+    """get_rect_adapt_landmark(img, bbox, lmk) of yolov8/src/postprocess.cpp:38-69 -> ((x, y, w, h), mapped keypoints)."""
+    lib = L.load()
+    b = (C.c_float * 4)(*[float(v) for v in bbox])
+    k = (C.c_float * len(lmk))(*[float(v) for v in lmk])
+    r = (C.c_int * 4)()
+    L.check(lib.trtx_get_rect_adapt_landmark(net_w, net_h, img_w, img_h, b, k, len(lmk) // 3, r), "trtx_get_rect_adapt_landmark")
+    return tuple(r), list(k)
+
+
+def scale_mask(masks: torch.Tensor, img_w: int, img_h: int, out=None, stream=None) -> torch.Tensor:
+    """scale_mask(mask, img) of yolov8/src/postprocess.cpp:207-226 for a stack of device masks [n, net_h, net_w] fp32 ->
+    [n, img_h, img_w]: the letterboxed region, bilinearly resized (cv::resize) to the original image."""
+    lib = L.load()
+    n, nh, nw = masks.shape
+    if out is None:
+        out = torch.empty((n, img_h, img_w), dtype=torch.float32, device=masks.device)
+    L.check(lib.trtx_scale_mask_enqueue(_ptr(masks), n, nw, nh, img_w, img_h, _ptr(out), _stream(stream)), "trtx_scale_mask_enqueue")
+    return out
+
+
 def letterbox_matrix(src_w: int, src_h: int, dst_w: int, dst_h: int):
     m = (C.c_float * 6)()
     L.load().trtx_letterbox_matrix(src_w, src_h, dst_w, dst_h, m)

@@ -313,3 +313,24 @@ def test_anticov_decode_oracle_vs_numpy(oracle):
         e = np.asarray(exp, np.float64)
         assert np.array_equal(idx[b, :n], e[:, 0].astype(np.int32))
         np.testing.assert_allclose(out[b, 1:1 + n * 16].reshape(n, 16), e[:, 1:], rtol=1e-5, atol=1e-3)
+
+
+def test_resize_of_a_crop_matches_cv2(oracle):
+    """scale_mask = cv::resize(mask(r), img.size()): the oracle's bilinear restatement on a cropped, strided view against
+    cv2.resize (INTER_LINEAR) for up- and down-scaling targets."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    mask = rng.uniform(0, 1, (640, 640)).astype(np.float32)
+    for (x, y, w, h, W, H) in ((0, 140, 640, 360, 1920, 1080), (140, 0, 360, 640, 1080, 1920), (0, 0, 640, 640, 333, 333), (0, 80, 640, 480, 500, 375)):
+        crop = np.ascontiguousarray(mask[y:y + h, x:x + w])
+        got = oracle.resize_bilinear(crop, H, W)
+        # OpenCV's own C++ kernel (what the restatement follows): within 1 ulp (its SIMD path contracts to FMA).  With the
+        # optional IPP accelerator (on in this cv2 build) the coefficients are computed differently: <= 3e-5 at these sizes,
+        # inside the 1e-4 tolerance of the north star -- the reference's own result depends on its OpenCV build there.
+        ipp = cv2.ipp.useIPP()
+        try:
+            cv2.ipp.setUseIPP(False)
+            np.testing.assert_allclose(got, cv2.resize(crop, (W, H), interpolation=cv2.INTER_LINEAR), atol=2e-7, rtol=0)
+        finally:
+            cv2.ipp.setUseIPP(ipp)
+        np.testing.assert_allclose(got, cv2.resize(crop, (W, H), interpolation=cv2.INTER_LINEAR), atol=1e-4, rtol=0)

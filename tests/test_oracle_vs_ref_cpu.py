@@ -145,3 +145,52 @@ def test_get_rect_equals_reference(oracle, variant, libname, fn):
             assert np.array_equal(oracle.get_rect(variant, w, h, bb), ref)
             assert P.get_rect(w, h, bb, variant=variant) == tuple(int(v) for v in ref)
 
+
+
+SIZES = ((1920, 1080), (1080, 1920), (640, 640), (1280, 720), (333, 777), (4000, 3000), (641, 640), (50, 60))
+
+
+def test_get_rect_adapt_landmark_equals_reference():
+    """get_rect_adapt_landmark (yolov8/src/postprocess.cpp:38-69, pose models): box AND the 17 keypoints mapped back to the
+    original image -- the library's host function against the reference's compiled code, identical integers and identical
+    keypoint bits on 300 boxes x 8 image sizes."""
+    from tensorrtx_b200 import plugins as P
+    lib = _load("libref_yolov8_host.so")
+    rng = np.random.default_rng(70)
+    for (w, h) in SIZES:
+        for _ in range(300):
+            x1, y1 = rng.uniform(-30, 650, 2)
+            bb = np.array([x1, y1, x1 + rng.uniform(-5, 400), y1 + rng.uniform(-5, 400)], np.float32)
+            lmk = rng.uniform(-20, 660, 51).astype(np.float32)
+            lmk[2::3] = rng.uniform(0, 1, 17).astype(np.float32)
+            ref_l, ref_r = lmk.copy(), np.zeros(4, np.int32)
+            lib.ref_v8_get_rect_adapt_landmark(w, h, bb.copy().ctypes.data_as(C.c_void_p), ref_l.ctypes.data_as(C.c_void_p),
+                                               ref_r.ctypes.data_as(C.c_void_p))
+            rect, mapped = P.get_rect_adapt_landmark(w, h, bb, lmk)
+            assert rect == tuple(int(v) for v in ref_r)
+            assert np.array_equal(np.asarray(mapped, np.float32), ref_l)
+
+
+def test_scale_mask_rect_and_process_decode_rows_equal_reference():
+    """scale_mask's crop of the 640x640 mask and its target size (postprocess.cpp:207-226; read back from the OpenCV shim) and
+    process_decode_ptr_host (:131-147) -- the library's host functions against the reference's compiled code."""
+    from tensorrtx_b200 import _lib as L
+    ref = _load("libref_yolov8_host.so")
+    lib = L.load()
+    for w in list(range(37, 2000, 97)) + [640, 641, 1920, 1080]:
+        for h in (48, 479, 480, 640, 1080, 1920, 3000):
+            r6, mine = np.zeros(6, np.int32), (C.c_int * 4)()
+            ref.ref_v8_scale_mask_rect(w, h, r6.ctypes.data_as(C.c_void_p))
+            assert lib.trtx_scale_mask_rect(640, 640, w, h, mine) == 0
+            assert list(mine) == r6[:4].tolist() and r6[4:].tolist() == [w, h]
+    rng = np.random.default_rng(71)
+    K = 200
+    buf = np.zeros(1 + K * 7, np.float32)
+    buf[0] = K
+    rows = buf[1:].reshape(K, 7)
+    rows[:, :6] = rng.uniform(0, 640, (K, 6)).astype(np.float32)
+    rows[:, 6] = rng.integers(0, 2, K)
+    out_ref, out_mine = np.zeros((K, 6), np.float32), np.zeros((K, 6), np.float32)
+    n_ref = ref.ref_v8_process_decode_ptr_host(buf.ctypes.data_as(C.c_void_p), 7, K, out_ref.ctypes.data_as(C.c_void_p))
+    n = lib.trtx_process_decode_ptr_host(buf.ctypes.data_as(C.POINTER(C.c_float)), 7, K, out_mine.ctypes.data_as(C.POINTER(C.c_float)))
+    assert n == n_ref == int(rows[:, 6].sum()) and np.array_equal(out_mine, out_ref)

@@ -287,3 +287,22 @@ def test_process_mask_matches_oracle(oracle, dev, variant):
             assert (got[b, i] > 0).sum() == (ref > 0).sum()
         assert np.all(got[b, n:] == sentinel)              # slots past the image's detections are not written
 
+
+
+@pytest.mark.parametrize("img_w,img_h", [(1920, 1080), (1080, 1920), (640, 640), (500, 375), (333, 1001)])
+def test_scale_mask_matches_oracle(oracle, dev, img_w, img_h):
+    """scale_mask (yolov8/src/postprocess.cpp:207-226) for a stack of device masks: crop rectangle pinned to the reference's
+    compiled code (tests/test_oracle_vs_ref_cpu.py), resize = OpenCV's float bilinear kernel (pinned to cv2 on the CPU)."""
+    import ctypes as C
+    rng = np.random.default_rng(img_w + img_h)
+    n = 3
+    masks = rng.uniform(0, 1, (n, 640, 640)).astype(np.float32)
+    out = P.scale_mask(torch.from_numpy(masks).to(dev), img_w, img_h)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    r = (C.c_int * 4)()
+    assert L.load().trtx_scale_mask_rect(640, 640, img_w, img_h, r) == 0
+    x, y, w, h = list(r)
+    for i in range(n):
+        ref = oracle.resize_bilinear(np.ascontiguousarray(masks[i, y:y + h, x:x + w]), img_h, img_w)
+        assert np.array_equal(got[i], ref)      # same operations in the same order, every product and sum rounded: bit-exact
