@@ -200,7 +200,23 @@ def test_bench_reference_arm_prints_contract_json():
 
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"].split()[0] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
+    # both arms print the same config dict (the driver's same_config check)
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert line["config"] == bench.config_dict("v8n_b32", 1)
+    assert line["config"]["stages"] == "pre-process + decode + NMS"
+
+
+@pytest.mark.parametrize("config", ["v5s_b1", "retina_b16", "rcnn_b8"])
+def test_bench_reference_arm_other_configs(config):
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--config", config, "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    import json
+
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["config"]["config"] == config
 
 
 def test_division_free_overlap_test_is_exact(tmp_path):
