@@ -249,26 +249,77 @@ class CpuPath:
                                            float(self.cfg["iou"]))
         return len(keep)
 
-    # ---- timed loops ----
-    def run(self, fn, total: int, threads: int) -> float:
-        """fn(frame_index, worker_state); `total` frames over `threads` Python threads (ctypes / cv2 / numpy release the
-        GIL inside the heavy calls).  Returns frames/s."""
-        gate = threading.Barrier(threads + 1)
+    # ---- one frame of each timed variant (selected by name so that worker PROCESSES can run it) ----
+    def task(self, key: str, f: int, st) -> int:
+        B = self.frames.shape[0]
+        if key == "full":          # pre-process + decode + NMS
+            self.preprocess(self.frames[f % B])
+            self.decode(self.heads, f % B, st)
+            return self.nms(st)
+        if key == "dec_nms":
+            self.decode(self.heads, f % B, st)
+            return self.nms(st)
+        if key in ("nms_O2", "nms_O0", "cv2nms"):
+            st["rows"][:] = self.decoded[f % B]
+            if key == "cv2nms":
+                return self.cv2_nms(st)
+            return self.nms(st, self.ref_O0 if key == "nms_O0" else self.ref)
+        if key == "pre":
+            self.preprocess(self.frames[f % B])
+            return 0
+        raise KeyError(key)
 
-        def worker(tid):
-            st = self.make_worker_state()
-            fn(tid, st)          # untimed: first touch of the worker's buffers, lazy symbol binding
-            gate.wait()
-            for f in range(tid, total, threads):
-                fn(f, st)
-        ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
-        for t in ts:
-            t.start()
-        gate.wait()
+    def bind(self, heads, frames) -> None:
+        """Inputs (and, for the NMS-only rows, the decoded plugin rows) the workers inherit through fork()."""
+        self.heads, self.frames = heads, frames
+        sts = [self.make_worker_state() for _ in range(frames.shape[0])]
+        for b in range(frames.shape[0]):
+            self.decode(heads, b, sts[b])
+        self.decoded = [s_["rows"].copy() for s_ in sts]
+
+
+_CP = None  # the CpuPath the forked workers use
+
+
+def _pool_task(args):
+    key, first, total, stride = args
+    st = _CP.make_worker_state()
+    kept = 0
+    for f in range(first, total, stride):
+        kept += _CP.task(key, f, st)
+    return kept
+
+
+class CpuRunner:
+    """`workers` host PROCESSES (fork; no GIL between them), one frame at a time each.  Pools persist across calls."""
+
+    def __init__(self, cp: CpuPath):
+        global _CP
+        _CP = cp
+        self.cp, self.pools = cp, {}
+
+    def run(self, key: str, total: int, workers: int):
+        """-> (frames/s, kept rows)"""
+        if workers <= 1:
+            st = self.cp.make_worker_state()
+            self.cp.task(key, 0, st)  # untimed first touch
+            t0 = time.perf_counter()
+            kept = sum(self.cp.task(key, f, st) for f in range(total))
+            return total / (time.perf_counter() - t0), kept
+        import multiprocessing as mp
+        if workers not in self.pools:
+            pool = mp.get_context("fork").Pool(workers)
+            pool.map(_pool_task, [(key, i, workers, workers) for i in range(workers)])  # untimed: page in, bind symbols
+            self.pools[workers] = pool
+        pool = self.pools[workers]
         t0 = time.perf_counter()
-        for t in ts:
-            t.join()
-        return total / (time.perf_counter() - t0)
+        kept = sum(pool.map(_pool_task, [(key, i, total, workers) for i in range(workers)], chunksize=1))
+        return total / (time.perf_counter() - t0), kept
+
+    def close(self):
+        for p_ in self.pools.values():
+            p_.terminate()
+        self.pools = {}
 
 
 def cpu_inputs(name: str, seed: int = 0):
@@ -283,62 +334,27 @@ def cpu_inputs(name: str, seed: int = 0):
     return heads, synth.frames(B, seed=77 + seed, h=NET, w=NET)
 
 
-def cpu_full_path(cp: CpuPath, heads, frames, total: int, threads: int):
-    """pre-process + decode + NMS per frame -> (frames/s, kept rows)."""
-    B = frames.shape[0]
-    kept = [0]
-
-    def fn(f, st):
-        cp.preprocess(frames[f % B])
-        cp.decode(heads, f % B, st)
-        kept[0] += cp.nms(st)
-    if not getattr(cp, "_warm", False):  # the first multi-threaded pass of a process runs far below speed: untimed
-        cp.run(fn, max(B, threads), threads)
-        cp._warm = True
-        kept[0] = 0
-    return cp.run(fn, total, threads), kept[0]
-
-
-def cpu_rows(cp: CpuPath, heads, frames, cores: int) -> dict:
-    """B1 NMS only (-O2 / -O0, 1 and 8 threads), B2 decode + NMS, B3 cv2.dnn.NMSBoxes; us/frame."""
-    B = frames.shape[0]
+def cpu_rows(run: CpuRunner, cores: int) -> dict:
+    """B1 NMS only (-O2 / -O0, 1 and 8 workers), B2 decode + NMS, B3 cv2.dnn.NMSBoxes; us/frame."""
+    cp = run.cp
+    B = cp.frames.shape[0]
     rows = {}
-    st0 = [cp.make_worker_state() for _ in range(B)]
-    for b in range(B):
-        cp.decode(heads, b, st0[b])
-    decoded = [s["rows"].copy() for s in st0]
-
-    def nms_only(lib):
-        def fn(f, st):
-            st["rows"][:] = decoded[f % B]
-            cp.nms(st, lib)
-        return fn
-    n1, n8 = max(B, 64), max(B, 8 * 32)
-    cp.run(nms_only(cp.ref), n8, min(8, cores))  # untimed: the first multi-threaded pass of a process runs far below speed
-    for label, lib in (("O2", cp.ref), ("O0", cp.ref_O0)):
-        if lib is None and label == "O0":
+    n1, n8, w8 = max(B, 64), max(B, 8 * 32), min(8, cores)
+    for label in ("O2", "O0"):
+        if label == "O0" and cp.ref_O0 is None:
             continue
-        rows[f"B1_nms_only_{label}_1thread_us"] = 1e6 / cp.run(nms_only(lib), n1, 1)
-        rows[f"B1_nms_only_{label}_8threads_us"] = 1e6 / cp.run(nms_only(lib), n8, min(8, cores)) * 1.0
+        rows[f"B1_nms_only_{label}_1thread_us"] = 1e6 / run.run(f"nms_{label}", n1, 1)[0]
+        rows[f"B1_nms_only_{label}_8workers_us"] = 1e6 / run.run(f"nms_{label}", n8, w8)[0]
     rows["B1_kind"] = cp.nms_kind + (" (compiled from /root/reference into oracle/_ref)" if cp.ref is not None else " (oracle restatement)")
-
-    def dec_nms(f, st):
-        cp.decode(heads, f % B, st)
-        cp.nms(st)
-    rows["B2_decode_nms_1thread_us"] = 1e6 / cp.run(dec_nms, max(B, 32), 1)
-    rows["B2_decode_nms_8threads_us"] = 1e6 / cp.run(dec_nms, n8, min(8, cores))
-    rows["B2_decode_nms_all_cores_us"] = 1e6 / cp.run(dec_nms, max(n8, 16 * cores), cores)
+    rows["B2_decode_nms_1thread_us"] = 1e6 / run.run("dec_nms", max(B, 32), 1)[0]
+    rows["B2_decode_nms_8workers_us"] = 1e6 / run.run("dec_nms", n8, w8)[0]
+    rows["B2_decode_nms_all_cores_us"] = 1e6 / run.run("dec_nms", max(n8, 16 * cores), cores)[0]
     if cp.cv2 is not None:
-        def b3(f, st):
-            st["rows"][:] = decoded[f % B]
-            cp.cv2_nms(st)
-        rows["B3_cv2_dnn_NMSBoxes_1thread_us"] = 1e6 / cp.run(b3, max(B, 32), 1)
-
-        def pre(f, st):
-            cp.preprocess(frames[f % B])
-        rows["preprocess_cv2_1thread_us"] = 1e6 / cp.run(pre, max(B, 32), 1)
-    rows["note"] = ("us per frame; 8-thread / all-core rows = one frame per thread, throughput-equivalent us; decode = restated "
-                    "CalDetection (the reference decodes on the GPU only)")
+        rows["B3_cv2_dnn_NMSBoxes_1thread_us"] = 1e6 / run.run("cv2nms", max(B, 32), 1)[0]
+        rows["preprocess_cv2_1thread_us"] = 1e6 / run.run("pre", max(B, 32), 1)[0]
+        rows["preprocess_cv2_all_cores_us"] = 1e6 / run.run("pre", max(n8, 16 * cores), cores)[0]
+    rows["note"] = ("us per frame; multi-worker rows = one frame at a time per host PROCESS (fork), throughput-equivalent us; decode = "
+                    "restated CalDetection (the reference decodes on the GPU only)")
     return rows
 
 
@@ -361,6 +377,17 @@ def rcnn_cpu(total_batches: int):
     return total_batches * B / (time.perf_counter() - t0)
 
 
+def cpu_baseline_subprocess(name: str) -> dict:
+    """The CPU path in a fresh process (it forks worker processes, which must not inherit a CUDA context): the reference
+    arm of this file on a bounded sample, with the rows of BASELINE.md section 2."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--config", name, "--steps", "3", "--warmup", "1",
+                        "--rows"], capture_output=True, text=True, timeout=600)
+    try:
+        return json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception:
+        return {"value": None, "unit": "frames/s", "cores": host_cores(), "kind": "port", "sample": "failed: " + r.stderr[-300:]}
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU implementation of the same stages on the box's host cores (rank 0 only):
     pre-process (the reference's Python/cv2 letterbox) + decode (restated plugin kernel) + nms() (compiled reference code)."""
@@ -368,6 +395,7 @@ def run_reference(args, rank: int, world: int):
         return
     name, cores = args.config, host_cores()
     cfg = CONFIGS[name]
+    rows = None
     if name == "rcnn_b8":
         per_step = 1
         for _ in range(min(args.warmup, 2)):
@@ -380,28 +408,32 @@ def run_reference(args, rank: int, world: int):
         kind, cores_used, sample, kept = "port", 1, f"{per_step} batch of 8 per step x {args.steps} steps, single thread (oracle restatement)", None
     else:
         cp = CpuPath(name)
-        heads, frames = cpu_inputs(name)
-        frames_per_step = max(cfg["batch"], cfg["batch"] * max(1, cores // 8))  # bounded sample: ~0.1-0.3 s per step
+        cp.bind(*cpu_inputs(name))
+        run = CpuRunner(cp)
+        frames_per_step = max(cfg["batch"], 16 * cores)  # bounded sample: 16 frames per worker and step (~0.1-1 s per step)
         for _ in range(min(args.warmup, 3)):
-            cpu_full_path(cp, heads, frames, frames_per_step, cores)
+            run.run("full", frames_per_step, cores)
         t0 = time.perf_counter()
         kept = 0
         for _ in range(args.steps):
-            _, k = cpu_full_path(cp, heads, frames, frames_per_step, cores)
-            kept += k
+            kept += run.run("full", frames_per_step, cores)[1]
         dt = time.perf_counter() - t0
         fps = frames_per_step * args.steps / dt
         kind = "port" if cp.nms_kind == "port" else "reference (nms + pre-process) + port (decode)"
         cores_used = cores
-        sample = (f"{frames_per_step} frames/step x {args.steps} steps of the synthetic set, {cores} threads; pre-process = "
+        sample = (f"{frames_per_step} frames/step x {args.steps} steps of the synthetic set, {cores} worker processes; pre-process = "
                   f"{'cv2 letterbox of yolov8_det_trt.py' if cp.cv2 is not None else 'oracle warp-affine'}, decode = restated CalDetection, "
                   f"nms = {cp.nms_kind}")
+        if args.rows:
+            rows = cpu_rows(run, cores)
+        run.close()
     print(json.dumps({
         "impl": "reference", "metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(name, max(1, args.gpus)),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores_used, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores_used, "kind": kind, "sample": sample,
+                         **({"rows": rows} if rows else {})},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "us_per_frame": 1e6 / fps, "kept_rows": kept,
     }))
@@ -425,7 +457,7 @@ def scan_traffic():
     return None
 
 
-def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None):
+def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None, run_many=None):
     """W warm-up steps, then blocks of exactly K steps; returns (mean ms per block, [(t0, t1) wall windows], n_blocks)."""
     import torch
 
@@ -438,8 +470,11 @@ def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record(stream)
-        for i in range(K):
-            step(first + i)
+        if run_many is not None:
+            run_many(first, K)
+        else:
+            for i in range(K):
+                step(first + i)
         if flush is not None:
             flush(first + K - 1)
         e1.record(stream)
@@ -454,8 +489,11 @@ def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None):
             ms = float(t.item())
         return ms, (t0, t1)
 
-    for i in range(W):
-        step(i)
+    if run_many is not None:
+        run_many(0, W)
+    else:
+        for i in range(W):
+            step(i)
     if flush is not None:
         flush(W - 1)
     ms0, w0 = block(W)
@@ -553,7 +591,15 @@ def run_v8(args, rank, world, local_rank):
                 peer = None
         use_ring = world > 1 and peer is None
 
-        def make_step(j):
+        # ---- the device-resident step.  The letterbox of a batch and the decode + NMS of a batch's head tensors are independent
+        #      chains (the TensorRT backbone sits between them and is not on this path), so a graph holds G consecutive steps
+        #      as TWO concurrent chains: chain A = their G letterbox launches, chain B (high priority) = their G x (scan -> NMS
+        #      [-> gather wait]) launches.  Exactly one letterbox, one scan and one NMS launch per step; per-launch gaps, kernel
+        #      ramps / tails and the latency-bound NMS hide under the other chain's HBM traffic.
+        G = 1 if (use_ring or args.no_overlap) else max(1, min(args.graph_steps, R))
+        chain_b = torch.cuda.Stream(dev, priority=-1)
+
+        def make_step(j):   # single step (serial / NCCL-ring modes)
             p, h, prev = pipes_dev[j], head_sets[j], pipes_dev[(j - 1) % R]
 
             def f():
@@ -561,6 +607,20 @@ def run_v8(args, rank, world, local_rank):
                     ring.launch(prev.fused.out, (j - 1) % R)  # fork: detections of the previous step
                 p.run_device(h, overlap=not args.no_overlap, peer_gather=peer)
                 ring.join()
+            return f
+
+        def make_group(j0, n):   # steps j0 .. j0+n-1 (input sets mod R) as two chains
+            def f():
+                cur = torch.cuda.current_stream(dev)
+                chain_b.wait_stream(cur)                     # fork
+                with torch.cuda.stream(chain_b):
+                    for j in range(j0, j0 + n):
+                        pipes_dev[j % R].fused.enqueue(BATCH, head_sets[j % R], gather=peer.desc if peer is not None else None)
+                        if peer is not None:
+                            peer.wait()
+                for j in range(j0, j0 + n):
+                    pipes_dev[j % R].pre.enqueue()
+                cur.wait_stream(chain_b)                     # join
             return f
 
         if use_ring:  # NCCL communicator and buffers must exist before anything is captured
@@ -571,8 +631,16 @@ def run_v8(args, rank, world, local_rank):
         needs_flush = use_ring  # make_step() gathers the PREVIOUS step's detections
         if world > 1:
             dist.barrier()  # ranks enter the (eager warm-up + capture) steps together: the gather's wait kernel gives up after ~2 s
+        group_replay, tail_replay = None, {}
         if args.no_graph:
             dev_steps = [make_step(j) for j in range(R)]
+        elif G > 1:
+            assert R % G == 0 or G == R
+            mode = "thread_local" if world > 1 else "global"
+            groups = [pipe.capture(make_group(j0, G), mode) for j0 in range(0, R, G)]
+            singles = [pipe.capture(make_group(j, 1), mode) for j in range(R)]
+            dev_steps = [g.replay for g in singles]
+            group_replay = [g.replay for g in groups]
         else:
             try:
                 dg = [pipe.capture(make_step(j), "thread_local" if world > 1 else "global") for j in range(R)]
@@ -597,6 +665,20 @@ def run_v8(args, rank, world, local_rank):
         def step_dev(i):
             dev_steps[i % R]()
 
+        def run_dev(first, n):
+            """steps first .. first+n-1: whole groups of G steps as one graph replay each, the remainder step by step"""
+            i = first
+            if group_replay is not None:
+                while i % G and i < first + n:
+                    step_dev(i)
+                    i += 1
+                while i + G <= first + n:
+                    group_replay[(i % R) // G]()
+                    i += G
+            while i < first + n:
+                step_dev(i)
+                i += 1
+
         def flush_dev(i_last):
             if needs_flush:
                 ring.launch(pipes_dev[i_last % R].fused.out, i_last % R)
@@ -614,7 +696,7 @@ def run_v8(args, rank, world, local_rank):
             sampler.start()
             time.sleep(0.25)
         K, W = args.steps, args.warmup
-        ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev)
+        ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev, run_many=run_dev)
         ms_e2e, win_e2e, nb_e2e = timed_blocks(step_e2e, K, W, stream, dev, world, dist, lambda i: ring.join())
         gather_err = peer.error() if peer is not None else 0
 
@@ -669,7 +751,9 @@ def run_v8(args, rank, world, local_rank):
         "run": {"parallelism": f"dp{world}: batch-sharded, gather = {gather_mode}" if world > 1 else "single GPU",
                 "l2": f"inputs rotate over {R} distinct sets ({R * head_bytes / 1e6:.0f} MB of head tensors + "
                       f"{R * BATCH * NET * NET * 3 / 1e6:.0f} MB of frames > 126 MB L2)",
-                "cuda_graphs": not args.no_graph, "overlap": "letterbox || (scan -> NMS) as parallel graph branches" if not args.no_overlap else "serial",
+                "cuda_graphs": not args.no_graph,
+                "overlap": (f"{G} steps per graph as two concurrent chains: letterbox launches || (scan -> NMS) launches" if G > 1 else
+                            ("letterbox || (scan -> NMS) as parallel graph branches" if not args.no_overlap else "serial")),
                 "timed_blocks": {"device": nb_dev, "e2e": nb_e2e, "steps_per_block": K, "min_timed_s": MIN_TIMED_S},
                 "gather_timeouts": gather_err,
                 "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
@@ -696,13 +780,7 @@ def run_v8(args, rank, world, local_rank):
                                "kernel_us": lb_ms * 1e3},
     }
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only (bounded sample of the same workload)
-        cores = host_cores()
-        cp = CpuPath("v8n_b32")
-        cfps, _ = cpu_full_path(cp, heads_np0, frames_np0, 32 * cores, cores)
-        out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores,
-                               "kind": "port" if cp.nms_kind == "port" else "reference (nms + pre-process) + port (decode)",
-                               "sample": f"{32 * cores} frames (the b32 set cycled) through cv2 letterbox + restated decode + nms(), {cores} threads",
-                               "rows": cpu_rows(cp, heads_np0, frames_np0, cores)}
+        out["cpu_baseline"] = cpu_baseline_subprocess("v8n_b32")
     print(json.dumps(out), flush=True)
     leave()
 
@@ -815,19 +893,7 @@ def run_other(args, local_rank):
                    "note": "frames (rcnn: the plugin input tensors) from pinned host memory + results back to pinned host every step"},
            "gpu_launches": launches * K, "kernels_us": kernels_us, "roofline": roof}
     if not args.no_cpu_baseline:
-        cores = host_cores()
-        if name == "rcnn_b8":
-            c = rcnn_cpu(2)
-            out["cpu_baseline"] = {"value": c, "unit": "frames/s", "cores": 1, "kind": "port",
-                                   "sample": "2 batches of 8 through the oracle's restatement of the four plugins, single thread"}
-        else:
-            cp = CpuPath(name)
-            heads, frames = cpu_inputs(name)
-            cf, _ = cpu_full_path(cp, heads, frames, max(B, 16) * cores // (8 if name == "retina_b16" else 1), cores)
-            out["cpu_baseline"] = {"value": cf, "unit": "frames/s", "cores": cores,
-                                   "kind": "port" if cp.nms_kind == "port" else "reference (nms + pre-process) + port (decode)",
-                                   "sample": "bounded sample of the same synthetic set through cv2 letterbox + restated decode + nms()",
-                                   "rows": cpu_rows(cp, heads, frames, cores)}
+        out["cpu_baseline"] = cpu_baseline_subprocess(name)
     print(json.dumps(out), flush=True)
 
 
@@ -840,9 +906,11 @@ def main():
     ap.add_argument("--config", default="v8n_b32", choices=sorted(CONFIGS))
     ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated to defeat the 126 MB L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows", action="store_true", help="--impl reference: also time the CPU rows B1 / B2 / B3 of BASELINE.md section 2")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of CUDA graphs")
     ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"])
     ap.add_argument("--no-overlap", action="store_true", help="letterbox, scan and NMS strictly one after another")
+    ap.add_argument("--graph-steps", type=int, default=4, help="consecutive steps captured into one CUDA graph (two concurrent chains)")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather instead of the gather fused into nms_kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -322,6 +322,10 @@ static bool unit_scale_image(const trtx_image_desc& d, const float m[6], UnitIma
     if (reinterpret_cast<uintptr_t>(d.data_dev) % 16 != 0 || d.pitch % 16 != 0) return false;  // TMA base / stride
     u->ox = (int)floorf(tx);
     u->oy = (int)floorf(ty);
+    // TMA fetches the box from byte column 3 * (64 * tile + ox): the start of a box must be 16-byte aligned in global memory
+    // (an unaligned start is an illegal instruction on sm_100a), so horizontal offsets that are not a multiple of 16 pixels
+    // (e.g. a 624-wide source centred in 640) take the general kernel
+    if (u->ox % 16 != 0) return false;
     u->lx = tx - floorf(tx);
     u->ly = ty - floorf(ty);
     u->sw = d.width;

@@ -182,7 +182,10 @@ def test_rcnn_full_config_b8_chain(oracle, dev):
                       _ws(p1.getWorkspaceSize(B), dev)) == 0
     r_s, r_b = oracle.rpn_decode(scores, deltas, 800, 1067, 16.0, anchors, pre)
     assert np.array_equal(d_s.cpu().numpy(), r_s)
-    np.testing.assert_allclose(d_b.cpu().numpy(), r_b, atol=ATOL, rtol=RTOL_EXP)
+    # x1 = ctr - w/2 with w = expf(..) * anchor up to ~1000 px: one ulp of CUDA-vs-glibc expf at that scale (1.2e-4) survives the
+    # cancellation into a small coordinate, so the absolute slack is 5 ulp(1024) here (vs the reference KERNEL: <= 2 ulp,
+    # tests/test_vs_reference_gpu.py::test_rcnn_vs_reference_functions)
+    np.testing.assert_allclose(d_b.cpu().numpy(), r_b, atol=6e-4, rtol=RTOL_EXP)
     props = torch.zeros((B, post, 4), device=dev)
     assert P.RpnNmsPlugin(0.7, post, pre).enqueue(B, [d_s, d_b], [props], _ws(256, dev)) == 0
     assert np.array_equal(props.cpu().numpy(), oracle.rpn_nms(d_s.cpu().numpy(), d_b.cpu().numpy(), post, 0.7))
@@ -193,7 +196,7 @@ def test_rcnn_full_config_b8_chain(oracle, dev):
         B, [torch.from_numpy(cls_scores).to(dev), torch.from_numpy(box_deltas).to(dev), props], [os_, ob, oc], _ws(256, dev)) == 0
     rs, rb, rc_ = oracle.predictor_decode(cls_scores, box_deltas, props.cpu().numpy(), 800, 1067, w)
     assert np.array_equal(os_.cpu().numpy(), rs) and np.array_equal(oc.cpu().numpy(), rc_)
-    np.testing.assert_allclose(ob.cpu().numpy(), rb, atol=ATOL, rtol=RTOL_EXP)
+    np.testing.assert_allclose(ob.cpu().numpy(), rb, atol=6e-4, rtol=RTOL_EXP)
     for method in (0, 1):
         fs, fb, fc = torch.zeros((B, 100), device=dev), torch.zeros((B, 100, 4), device=dev), torch.zeros((B, 100), device=dev)
         assert P.BatchedNmsPlugin(method, 0.5, 100, N).enqueue(B, [os_, ob, oc], [fs, fb, fc], _ws(256, dev)) == 0
