@@ -51,15 +51,27 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
                 m.z = fmaxf(m.z, v[u].z);
                 m.w = fmaxf(m.w, v[u].w);
             }
-            if ((m.x > s.bx[0]) | (m.y > s.bx[1]) | (m.z > s.bx[2]) | (m.w > s.bx[3])) {
+            // replay only the anchors whose running maximum rises (usually one of the four, around a real candidate):
+            // U sequential updates for that anchor instead of 4*U for the quad; ONE branch in the common (no hit) case
+            if (!((m.x > s.bx[0]) | (m.y > s.bx[1]) | (m.z > s.bx[2]) | (m.w > s.bx[3]))) {
+                p += (size_t)U * g;
+                continue;
+            }
+            if (m.x > s.bx[0]) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int c = cls0 + r + u;
-                    update_one<VEC>(s, 0, v[u].x, c);
-                    update_one<VEC>(s, 1, v[u].y, c);
-                    update_one<VEC>(s, 2, v[u].z, c);
-                    update_one<VEC>(s, 3, v[u].w, c);
-                }
+                for (int u = 0; u < U; ++u) update_one<VEC>(s, 0, v[u].x, cls0 + r + u);
+            }
+            if (m.y > s.bx[1]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) update_one<VEC>(s, 1, v[u].y, cls0 + r + u);
+            }
+            if (m.z > s.bx[2]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) update_one<VEC>(s, 2, v[u].z, cls0 + r + u);
+            }
+            if (m.w > s.bx[3]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) update_one<VEC>(s, 3, v[u].w, cls0 + r + u);
             }
         } else {
             float v[U];

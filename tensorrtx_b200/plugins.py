@@ -602,7 +602,7 @@ class FusedYoloDecodeNms:
                  device="cuda", return_index=True):
         self.plugin = plugin
         self.max_batch = max_batch
-        v5 = isinstance(plugin, YoloLayerPluginV5)
+        v5 = plugin.params.variant in (L.YOLO_V5, L.YOLO_V3)  # anchor-based rows are cx, cy, w, h
         self.max_det = max_det or plugin.mMaxOutObject
         self.q = nms_params(L.BOX_CXCYWH if v5 else L.BOX_LTRB, mode, conf_thresh, nms_thresh, self.max_det, True)
         self._lib = L.load()
