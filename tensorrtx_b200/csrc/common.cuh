@@ -46,6 +46,12 @@ __device__ __forceinline__ float4 ldg_stream_h4(const __half* p) {
     float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
     return make_float4(f0.x, f0.y, f1.x, f1.y);
 }
+// 8 halfs (16 bytes), raw
+__device__ __forceinline__ uint4 ldg_stream_h8(const __half* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float ldg_stream_h1(const __half* p) {
     unsigned short r;
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));

@@ -90,6 +90,67 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
 }
 
 // --------------------------------------------------------------------------------------------
+// fp16 inputs, 8 anchors per lane (one 16-byte load per lane and channel row = 512 contiguous bytes per warp-row, the same
+// request size as the fp32 path at half the requests per anchor).  The running maximum is ALSO kept as packed half2 so that
+// the hot loop is 4 HMNMX2 per row for 8 anchors with no fp16 -> fp32 conversion at all: max and `>` on halfs are exact and
+// order-preserving (hmax2 ignores NaN like fmaxf, hgt2 is false on NaN like `p > max`).  The half2 mirror of an anchor
+// that has not been raised yet is x_lo rounded DOWN to half, so the packed test can only over-report; the exact decision
+// is the per-anchor replay on the fp32 state (half -> float is exact), identical to the fp32 path from there on.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+template <int U>
+__device__ __forceinline__ void scan_classes_h8(const __half* __restrict__ row0, size_t g, int nrows, int cls0, Best<8>& s) {
+    __half2 bxh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bxh[k] = __halves2half2(__float2half_rd(s.bx[2 * k]), __float2half_rd(s.bx[2 * k + 1]));
+    const __half* p = row0;
+#pragma unroll 1
+    for (int r = 0; r < nrows; r += U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u < nrows)
+                v[u] = ldg_stream_h8(p + (size_t)u * g);
+            else
+                v[u] = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);  // -inf
+        }
+        __half2 m[4] = {u32_as_h2(v[0].x), u32_as_h2(v[0].y), u32_as_h2(v[0].z), u32_as_h2(v[0].w)};
+#pragma unroll
+        for (int u = 1; u < U; ++u) {
+            m[0] = __hmax2(m[0], u32_as_h2(v[u].x));
+            m[1] = __hmax2(m[1], u32_as_h2(v[u].y));
+            m[2] = __hmax2(m[2], u32_as_h2(v[u].z));
+            m[3] = __hmax2(m[3], u32_as_h2(v[u].w));
+        }
+        unsigned hit[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hit[k] = __hgt2_mask(m[k], bxh[k]);
+        p += (size_t)U * g;
+        if (!(hit[0] | hit[1] | hit[2] | hit[3])) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!hit[k]) continue;
+            if (hit[k] & 0xffffu) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t w = k == 0 ? v[u].x : (k == 1 ? v[u].y : (k == 2 ? v[u].z : v[u].w));
+                    update_one<8>(s, 2 * k, __low2float(u32_as_h2(w)), cls0 + r + u);
+                }
+            }
+            if (hit[k] >> 16) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t w = k == 0 ? v[u].x : (k == 1 ? v[u].y : (k == 2 ? v[u].z : v[u].w));
+                    update_one<8>(s, 2 * k + 1, __high2float(u32_as_h2(w)), cls0 + r + u);
+                }
+            }
+            bxh[k] = __halves2half2(__float2half_rd(s.bx[2 * k]), __float2half_rd(s.bx[2 * k + 1]));
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 // Anchor-free scan (yolov8 family).  grid = B * tiles_per_image CTAs of SLICES warps.
 // --------------------------------------------------------------------------------------------
 template <typename T, int VEC, int SLICES, int U>
@@ -109,7 +170,7 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
     const int warp = threadIdx.x >> 5;
     const int a0 = tile * TILE + lane * VEC;  // first cell handled by this lane
     const size_t g = (size_t)L.g;
-    const bool active = a0 < L.g;  // vector path: g % 4 == 0, so a0 < g implies the whole quad is in range
+    const bool active = a0 < L.g;  // vector paths: g % VEC == 0, so a0 < g implies the whole group is in range
     const T* base = reinterpret_cast<const T*>(L.in) + (size_t)b * a.C * g;
 
     Best<VEC> s;
@@ -133,7 +194,13 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
     auto load_box = [&]() {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if constexpr (VEC == 4) {
+            if constexpr (VEC == 8) {
+                const uint4 v = ldg_stream_h8(reinterpret_cast<const __half*>(base) + (size_t)k * g + a0);
+                const float2 f0 = __half22float2(u32_as_h2(v.x)), f1 = __half22float2(u32_as_h2(v.y));
+                const float2 f2 = __half22float2(u32_as_h2(v.z)), f3 = __half22float2(u32_as_h2(v.w));
+                d[k][0] = f0.x, d[k][1] = f0.y, d[k][2] = f1.x, d[k][3] = f1.y;
+                d[k][4] = f2.x, d[k][5] = f2.y, d[k][6] = f3.x, d[k][7] = f3.y;
+            } else if constexpr (VEC == 4) {
                 float4 v = Elem<T>::ld4(base + (size_t)k * g + a0);
                 d[k][0] = v.x;
                 d[k][1] = v.y;
@@ -152,7 +219,12 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
             for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)k * g + a0));
         }
     }
-    if (active && c1 > c0) scan_classes<T, VEC, U>(base + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
+    if (active && c1 > c0) {
+        if constexpr (VEC == 8)
+            scan_classes_h8<U>(reinterpret_cast<const __half*>(base) + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
+        else
+            scan_classes<T, VEC, U>(base + (size_t)(4 + c0) * g + a0, g, c1 - c0, c0, s);
+    }
 
     if constexpr (SLICES > 1) {
         bool mine = false;
@@ -606,6 +678,13 @@ __global__ void __launch_bounds__(256) yolo_pack_rows_kernel(const __grid_consta
 // host side
 // --------------------------------------------------------------------------------------------
 int yolo_pick_vec(const trtx_yolo_params* p, const void* const* inputs_dev) {
+    // fp16 inputs of the anchor-free layout: 8 anchors per lane (16-byte loads, packed half2 maxima) when every level allows it
+    if (p->in_dtype == TRTX_F16 && p->variant == TRTX_YOLO_V8) {
+        bool ok8 = true;
+        for (int l = 0; l < p->num_levels && ok8; ++l)
+            ok8 = (p->grid_h[l] * p->grid_w[l]) % 8 == 0 && !(inputs_dev && reinterpret_cast<uintptr_t>(inputs_dev[l]) % 16 != 0);
+        if (ok8) return 8;
+    }
     const size_t need = (p->in_dtype == TRTX_F16) ? 8 : 16;
     for (int l = 0; l < p->num_levels; ++l) {
         int g = p->grid_h[l] * p->grid_w[l];
@@ -658,7 +737,7 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
     if (p->tune_class_slices < 0 || p->tune_rows_in_flight < 0 || p->tune_tma_stages < 0 || p->tune_box_prefetch < 0 ||
         p->tune_box_prefetch > 3 || (p->tune_tma_pipeline != 0 && p->tune_tma_pipeline != 1))
         return TRTX_ERR_INVALID;
-    const bool pipe = p->tune_tma_pipeline && p->variant == TRTX_YOLO_V8 && vec == 4 && yolo_pipe_supported(p, inputs_dev);
+    const bool pipe = p->tune_tma_pipeline && p->variant == TRTX_YOLO_V8 && vec >= 4 && yolo_pipe_supported(p, inputs_dev);
     YoloLayout L = yolo_layout(p, batch, pipe ? 1 : vec);
     L.pipe = pipe ? 1 : 0;
     L.slices = p->tune_class_slices ? p->tune_class_slices : 2;
@@ -768,7 +847,8 @@ int yolo_scan_launch(const YoloArgs& a, const YoloLayout& L, int in_dtype, int b
         if (in_dtype == TRTX_F32)
             rc = L.vec == 4 ? launch_v8<float, 4>(a, L, grid, st) : launch_v8<float, 1>(a, L, grid, st);
         else
-            rc = L.vec == 4 ? launch_v8<__half, 4>(a, L, grid, st) : launch_v8<__half, 1>(a, L, grid, st);
+            rc = L.vec == 8 ? launch_v8<__half, 8>(a, L, grid, st)
+                            : (L.vec == 4 ? launch_v8<__half, 4>(a, L, grid, st) : launch_v8<__half, 1>(a, L, grid, st));
         if (rc) return rc;
     } else {
         if (in_dtype == TRTX_F32) {

@@ -131,6 +131,23 @@ def test_v8_all_register_scan_variants(oracle, dev, slices, unroll):
     _check_rows(got, ref, 2, 90, 6, 1000)
 
 
+@pytest.mark.parametrize("slices,unroll", [(1, 8), (2, 5), (2, 10), (4, 5), (4, 20), (8, 10)])
+@pytest.mark.parametrize("B,n_obj", [(2, 64), (5, 200)])
+def test_v8_fp16_eight_anchors_per_lane_scan(oracle, dev, slices, unroll, B, n_obj):
+    """fp16 inputs take the 8-anchors-per-lane scan (16-byte loads, packed half2 running maxima, exact per-anchor replay in
+    fp32): every built (slices, rows) pair on fp16-representable heads against the fp32 oracle, including dense images
+    (n_obj = 200: most groups of rows raise some anchor) and exact ties between halfs."""
+    heads = [h.astype(np.float16).astype(np.float32) for h in synth.yolov8_heads(B, seed=17 + B, n_obj=n_obj)]
+    heads[0][0, 4 + 11, 300] = 3.5
+    heads[0][0, 4 + 70, 300] = 3.5          # exact tie: the first class wins
+    heads[1][B - 1, 4 + 3, 8] = 12.0        # saturating sigmoids in fp32: collision replay
+    heads[1][B - 1, 4 + 2, 8] = 11.5
+    ref, _ = oracle.yolov8_decode(heads)
+    plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, 1000, False, False, False, (8, 16, 32), in_dtype=L.F16).tune(slices=slices, rows=unroll)
+    got = _decode_gpu(plug, _to_dev(heads, dev, torch.float16), B, dev)
+    _check_rows(got, ref, B, 90, 6, 1000)
+
+
 def test_v8_unbuilt_tuning_is_refused_and_tunings_are_per_plugin(oracle, dev):
     """trtx_yolo_params.tune_* is per-call data: a pair that is not built -> TRTX_ERR_UNSUPPORTED (no silent default),
     and two plugins with different tunings used alternately give the same (oracle) rows -- no shared state."""
