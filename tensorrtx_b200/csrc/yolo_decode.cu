@@ -53,6 +53,13 @@ __device__ __forceinline__ void scan_classes(const T* __restrict__ row0, size_t 
             }
             // replay only the anchors whose running maximum rises (usually one of the four, around a real candidate):
             // U sequential updates for that anchor instead of 4*U for the quad; ONE branch in the common (no hit) case
+#if defined(TRTX_SCAN_PROBE) && TRTX_SCAN_PROBE == 2  // experiment build: streaming + maxima only
+            if (true) {
+                s.bx[0] = fmaxf(s.bx[0], m.x), s.bx[1] = fmaxf(s.bx[1], m.y), s.bx[2] = fmaxf(s.bx[2], m.z), s.bx[3] = fmaxf(s.bx[3], m.w);
+                p += (size_t)U * g;
+                continue;
+            }
+#endif
             if (!((m.x > s.bx[0]) | (m.y > s.bx[1]) | (m.z > s.bx[2]) | (m.w > s.bx[3]))) {
                 p += (size_t)U * g;
                 continue;
@@ -271,6 +278,9 @@ __global__ void __launch_bounds__(32 * SLICES) yolo_v8_scan_kernel(const __grid_
     int total;
     int off = warp_excl_scan(__popc(flags), lane, &total);
     if (lane == 0) a.tile_count[(size_t)b * a.tiles_per_image + t] = total;
+#if defined(TRTX_SCAN_PROBE) && TRTX_SCAN_PROBE == 1  // experiment build: no box decode / record stores
+    flags = 0;
+#endif
     if (flags) {
         if (a.prefetch_box != 3) load_box();
         const size_t slot0 = (size_t)b * a.slots_per_image + L.slot_begin + (size_t)tile * TILE;
