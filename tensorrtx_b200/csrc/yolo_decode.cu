@@ -751,7 +751,7 @@ int yolo_fill_args(const trtx_yolo_params* p, int batch, const void* const* inpu
     YoloLayout L = yolo_layout(p, batch, pipe ? 1 : vec);
     L.pipe = pipe ? 1 : 0;
     L.slices = p->tune_class_slices ? p->tune_class_slices : 2;
-    L.unroll = p->tune_rows_in_flight ? p->tune_rows_in_flight : 5;
+    L.unroll = p->tune_rows_in_flight ? p->tune_rows_in_flight : (vec == 8 ? 10 : 5);  // B200 sweep, profiles/r02c_sweep_graph.log
     L.pipe_stages = p->tune_tma_stages;
     if (workspace_bytes < L.total_bytes) return TRTX_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0) return TRTX_ERR_INVALID;
