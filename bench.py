@@ -591,7 +591,7 @@ def run_v8(args, rank, world, local_rank):
         # ---- N > 1: the gather.  Preferred: fused into the NMS kernel over NVLink peer memory (no collective kernel);
         #      fallback: one NCCL all-gather per step on a side stream as a parallel graph branch (round 1).
         peer, ring, gather_mode = None, GatherRing(world, BATCH, pipe.fused.out.shape[1], dev, slots=R), "none"
-        if world > 1 and not args.nccl_gather:
+        if world > 1 and not args.nccl_gather and not args.no_gather:
             try:
                 peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=4)
                 gather_mode = "fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel"
@@ -603,7 +603,7 @@ def run_v8(args, rank, world, local_rank):
             if int(ok.item()) == 0 and peer is not None:
                 peer.close()
                 peer = None
-        use_ring = world > 1 and peer is None
+        use_ring = world > 1 and peer is None and not args.no_gather
 
         # ---- the device-resident step.  The letterbox of a batch and the decode + NMS of a batch's head tensors are independent
         #      chains (the TensorRT backbone sits between them and is not on this path), so a graph holds G consecutive steps
@@ -630,7 +630,7 @@ def run_v8(args, rank, world, local_rank):
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
                         pipes_dev[j % R].fused.enqueue(BATCH, head_sets[j % R], gather=peer.desc if peer is not None else None)
-                        if peer is not None:
+                        if peer is not None and not args.peer_nowait:
                             peer.wait()
                 for j in range(j0, j0 + n):
                     pipes_dev[j % R].pre.enqueue()
@@ -720,6 +720,13 @@ def run_v8(args, rank, world, local_rank):
         scan_ms_b2b = time_kernel_loop(lambda i: fused.enqueue_scan(BATCH, head_sets[i % R]), n_iso, stream, dev)
         fused.enqueue_scan(BATCH, head_sets[0])
         nms_ms = time_kernel_loop(lambda i: fused.enqueue_nms(BATCH, head_sets[0]), n_iso, stream, dev)
+        nms_gather_ms = None
+        if peer is not None:   # scan + NMS with the peer stores + wait, ranks in lockstep
+            dist.barrier()
+            def _sg(i):
+                fused.enqueue(BATCH, head_sets[i % R], gather=peer.desc)
+                peer.wait()
+            nms_gather_ms = time_kernel_loop(_sg, n_iso, stream, dev)
         lb_ms = time_kernel_loop(lambda i: pipes_dev[i % R].pre.enqueue(), n_iso, stream, dev)
         # the same scan launches inside ONE CUDA graph (how the step runs them): launch gaps are the graph's, not Python's
         g_scan = torch.cuda.CUDAGraph()
@@ -781,6 +788,7 @@ def run_v8(args, rank, world, local_rank):
         "decode_nms_us_per_frame": ms_decnms * 1e3 / BATCH,
         "decode_nms_ms_per_batch": ms_decnms,
         "kernels_us": {"letterbox": lb_ms * 1e3, "scan": scan_ms_b2b * 1e3, "scan_in_graph": scan_ms_graph * 1e3, "nms": nms_ms * 1e3,
+                       **({"scan+nms+gather+wait (stream)": nms_gather_ms * 1e3, "scan+nms (stream)": ms_decnms * 1e3} if nms_gather_ms else {}),
                        "sum": (lb_ms + scan_ms_b2b + nms_ms) * 1e3, "step": ms_dev / K * 1e3},
         "roofline": {"bound": "hbm", "kernel": "yolo_v8_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
@@ -926,6 +934,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="letterbox, scan and NMS strictly one after another")
     ap.add_argument("--graph-steps", type=int, default=4, help="consecutive steps captured into one CUDA graph (two concurrent chains)")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather instead of the gather fused into nms_kernel")
+    ap.add_argument("--no-gather", action="store_true", help="experiment: N > 1 without any gather (upper bound of the scaling)")
+    ap.add_argument("--peer-nowait", action="store_true", help="experiment: fused gather stores, but no gather_wait kernels in the step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
