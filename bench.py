@@ -620,7 +620,8 @@ def run_v8(args, rank, world, local_rank):
                 if use_ring:
                     ring.launch(prev.fused.out, (j - 1) % R)  # fork: detections of the previous step
                 p.run_device(h, overlap=not args.no_overlap, peer_gather=peer)
-                ring.join()
+                if use_ring:
+                    ring.join()
             return f
 
         def make_group(j0, n):   # steps j0 .. j0+n-1 (input sets mod R) as two chains
@@ -696,11 +697,13 @@ def run_v8(args, rank, world, local_rank):
         def flush_dev(i_last):
             if needs_flush:
                 ring.launch(pipes_dev[i_last % R].fused.out, i_last % R)
-            ring.join()
+            if use_ring:
+                ring.join()
 
         def step_e2e(i):
             # public API call with HOST frames: H2D (copy stream, double-buffered) + pre-process + decode + NMS + D2H
-            ring.join()
+            if use_ring:
+                ring.join()
             pipe.submit(frame_sets_host[i % R], head_sets[i % R], peer_gather=peer)
             if use_ring:
                 ring.launch(pipe.fused.out, i % R)
@@ -711,7 +714,7 @@ def run_v8(args, rank, world, local_rank):
             time.sleep(0.25)
         K, W = args.steps, args.warmup
         ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev, run_many=run_dev)
-        ms_e2e, win_e2e, nb_e2e = timed_blocks(step_e2e, K, W, stream, dev, world, dist, lambda i: ring.join())
+        ms_e2e, win_e2e, nb_e2e = timed_blocks(step_e2e, K, W, stream, dev, world, dist, (lambda i: ring.join()) if use_ring else None)
         gather_err = peer.error() if peer is not None else 0
 
         # ---- kernels in isolation, on the timed stream, rotating input sets (CUDA events around n launches) ----

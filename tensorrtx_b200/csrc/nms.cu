@@ -850,24 +850,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             row[4] = s_conf[i];
             row[5] = (float)s_cls[i];
             row[6] = s_keep[i] ? 1.0f : 0.0f;
-            for (int p = 0; p < gworld; ++p) {  // the same 28 bytes to every rank's gathered buffer (NVLink stores)
-                float* pr = a.g.out[p] + goff + 1 + (size_t)k * R;
-                pr[0] = bx.x;
-                pr[1] = bx.y;
-                pr[2] = bx.z;
-                pr[3] = bx.w;
-                pr[4] = row[4];
-                pr[5] = row[5];
-                pr[6] = row[6];
-            }
             if (oidx) oidx[k] = a.from_tiles ? __float_as_int(a.cand[2 * ((size_t)b * a.slots_per_image + s_id[i]) + 1].z)
                                              : (int)s_id[i];
             if (a.extra_floats && !a.from_tiles) {
                 const float* src = a.rows + (size_t)b * (1 + (size_t)a.max_rows * a.det_floats) + 1 +
                                    (size_t)s_id[i] * a.det_floats + a.extra_offset;
                 for (int e = 0; e < a.extra_floats; ++e) row[7 + e] = src[e];
-                for (int p = 0; p < gworld; ++p)
-                    for (int e = 0; e < a.extra_floats; ++e) a.g.out[p][goff + 1 + (size_t)k * R + 7 + e] = src[e];
             }
         }
         carry += s_nkept;
@@ -880,15 +868,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     if (oidx)
         for (int i = n_rows_out + tid; i < a.max_det; i += kNmsThreads) oidx[i] = -1;
     if (gworld) {
-        // count last; rows past it are NOT cleared on the peers (consumers read `count` rows)
-        if (tid < gworld) a.g.out[tid][goff] = (float)n_rows_out;
-        __threadfence_system();  // this CTA's peer stores are visible system-wide before it counts itself done
+        // The image's block [count, rows...] is contiguous and was just written to `o` by this CTA: copy its live part to every
+        // rank's gathered buffer with lane-consecutive stores (full 128-byte NVLink writes instead of one 4-byte packet per
+        // float; rows past `count` are NOT cleared on the peers -- consumers read `count` rows).
         __syncthreads();
-        if (tid == 0 && atomicAdd(&a.g.ctrl[1], 1u) == gridDim.x - 1) {  // last CTA of the launch: publish
-            a.g.ctrl[1] = 0u;
+        const int live = 1 + n_rows_out * R;
+        for (int p = 0; p < gworld; ++p) {
+            float* dstp = a.g.out[p] + goff;
+            for (int i = tid; i < live; i += kNmsThreads) dstp[i] = i == 0 ? (float)n_rows_out : o[i];
+        }
+        __syncthreads();  // CTA-scope order of all peer stores before thread 0's system-scope fence (cumulative)
+        if (tid == 0) {
             __threadfence_system();
-            for (int p = 0; p < gworld; ++p)
-                st_release_sys(a.g.flags[p] + (size_t)a.g.rank * a.g.slots + gstep % (unsigned)a.g.slots, gstep + 1u);
+            if (atomicAdd(&a.g.ctrl[1], 1u) == gridDim.x - 1) {  // last CTA of the launch: publish
+                a.g.ctrl[1] = 0u;
+                __threadfence_system();
+                for (int p = 0; p < gworld; ++p)
+                    st_release_sys(a.g.flags[p] + (size_t)a.g.rank * a.g.slots + gstep % (unsigned)a.g.slots, gstep + 1u);
+            }
         }
     }
     TRTX_STAMP(6);
