@@ -594,7 +594,9 @@ def run_v8(args, rank, world, local_rank):
         if world > 1 and not args.nccl_gather and not args.no_gather:
             try:
                 peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=4)
-                gather_mode = "fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel"
+                peer.fused = bool(args.fused_gather)
+                gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
+                               "gather_push_kernel after the NMS: NVLink peer stores + flags + wait in one 8-CTA launch (trtx_gather), no collective kernel")
             except Exception as e:
                 print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
                 peer = None
@@ -630,9 +632,7 @@ def run_v8(args, rank, world, local_rank):
                 chain_b.wait_stream(cur)                     # fork
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
-                        pipes_dev[j % R].fused.enqueue(BATCH, head_sets[j % R], gather=peer.desc if peer is not None else None)
-                        if peer is not None and not args.peer_nowait:
-                            peer.wait()
+                        pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer)
                 for j in range(j0, j0 + n):
                     pipes_dev[j % R].pre.enqueue()
                 cur.wait_stream(chain_b)                     # join
@@ -727,8 +727,7 @@ def run_v8(args, rank, world, local_rank):
         if peer is not None:   # scan + NMS with the peer stores + wait, ranks in lockstep
             dist.barrier()
             def _sg(i):
-                fused.enqueue(BATCH, head_sets[i % R], gather=peer.desc)
-                peer.wait()
+                pipe.decode_nms_gather(head_sets[i % R], peer)
             nms_gather_ms = time_kernel_loop(_sg, n_iso, stream, dev)
         lb_ms = time_kernel_loop(lambda i: pipes_dev[i % R].pre.enqueue(), n_iso, stream, dev)
         # the same scan launches inside ONE CUDA graph (how the step runs them): launch gaps are the graph's, not Python's
@@ -938,7 +937,7 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=4, help="consecutive steps captured into one CUDA graph (two concurrent chains)")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather instead of the gather fused into nms_kernel")
     ap.add_argument("--no-gather", action="store_true", help="experiment: N > 1 without any gather (upper bound of the scaling)")
-    ap.add_argument("--peer-nowait", action="store_true", help="experiment: fused gather stores, but no gather_wait kernels in the step")
+    ap.add_argument("--fused-gather", action="store_true", help="N > 1: gather stores from inside nms_kernel + one-warp wait kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -228,6 +228,14 @@ TRTX_API int trtx_yolo_decode_nms_gather_enqueue(const trtx_yolo_params* p, cons
                                                  int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
                                                  const trtx_gather* gather, trtx_stream_t stream);
 TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream);
+/* The same step as ONE separate small kernel after a plain trtx_yolo_decode_nms_enqueue / trtx_nms_enqueue (8 CTAs of 256
+ * threads that co-reside with the streaming kernels of the step): copies the live part [count, rows] of every image of
+ * compact_out_dev [batch, 1 + max_det*(7+extra_floats)] into slot (step % slots) of every rank, publishes the flags, waits
+ * for the peers' and advances the step counter (push + wait; do NOT also call trtx_gather_wait_enqueue).  Same buffers,
+ * same contract.  Preferred when the step is HBM-bound: the fused variant holds the NMS CTAs' 32 whole SMs during the
+ * NVLink round trips (measured in DESIGN.md section 5). */
+TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,
+                                      int extra_floats, trtx_stream_t stream);
 /* Peer-mappable device memory (zero-initialised) + its 64-byte CUDA IPC handle; open / close a peer's handle; free. */
 TRTX_API int trtx_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
 TRTX_API int trtx_peer_open(const unsigned char handle[64], void** dev_ptr);

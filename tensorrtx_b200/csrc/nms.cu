@@ -916,6 +916,49 @@ __global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
     }
 }
 
+// The same gather as a SEPARATE small kernel (a few 256-thread CTAs that co-reside with the step's streaming kernels): copies
+// the live part of every image's block of the local compact output to every rank, publishes the flags, and its last CTA
+// then waits for the peers' flags and advances the step counter -- push and wait in one launch.  Measured at N = 2
+// (profiles/r02d_*): the variant fused into nms_kernel keeps 32 whole SMs (1024 threads x 64 registers per CTA) occupied for
+// the NVLink round trips of its system-scope fence, which slows the HBM-bound kernels of the other chain; this one does not.
+__global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, const float* __restrict__ local, int batch, int cols,
+                                                          int max_det, int R) {
+    const unsigned s = *reinterpret_cast<volatile unsigned*>(g.ctrl), slot = s % (unsigned)g.slots;
+    const int tid = threadIdx.x;
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        const float* src = local + (size_t)b * cols;
+        const int n = min(max((int)src[0], 0), max_det);
+        const int live = 1 + n * R;
+        const size_t off = (((size_t)slot * g.world + g.rank) * batch + b) * cols;
+        for (int p = 0; p < g.world; ++p) {
+            float* dst = g.out[p] + off;
+            for (int i = tid; i < live; i += 256) dst[i] = src[i];
+        }
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    __threadfence_system();
+    if (atomicAdd(&g.ctrl[1], 1u) != gridDim.x - 1) return;
+    g.ctrl[1] = 0u;
+    __threadfence_system();
+    for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + (size_t)g.rank * g.slots + slot, s + 1u);
+    bool ok = true;
+    const long long t0 = clock64();
+    for (int p = 0; p < g.world && ok; ++p) {
+        const unsigned* f = g.flags[g.rank] + (size_t)p * g.slots + slot;
+        while (ld_acquire_sys(f) != s + 1u) {
+            __nanosleep(100);
+            if (clock64() - t0 > 4000000000ll) {
+                ok = false;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    if (!ok) g.ctrl[2] = 1u;
+    g.ctrl[0] = s + 1u;
+}
+
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
     const size_t S = pre_topk <= 1024 ? 1024 : kMaxSort;
     return S * (16 + 16 + 8 + 6 * 4 + 4 + 2 + 2 + 1 + 2 * (kShortSeg / 8) + 4) + 64 + sizeof(int) * (size_t)(tiles + 1);
@@ -1089,6 +1132,17 @@ TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t s
     int rc = fill_gather(gather, &g);
     if (rc || !gather) return rc ? rc : TRTX_ERR_INVALID;
     gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g);
+    return check_launch();
+}
+
+TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,
+                                      int extra_floats, trtx_stream_t stream) {
+    NmsArgs::Gather g;
+    int rc = fill_gather(gather, &g);
+    if (rc || !gather || !compact_out_dev || batch <= 0 || max_det <= 0 || extra_floats < 0) return rc ? rc : TRTX_ERR_INVALID;
+    const int R = 7 + extra_floats;
+    gather_push_kernel<<<batch < 8 ? batch : 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, compact_out_dev, batch, 1 + max_det * R,
+                                                                                          max_det, R);
     return check_launch();
 }
 

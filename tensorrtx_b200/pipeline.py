@@ -62,21 +62,29 @@ class DetectionPipeline:
         the current stream, joined at the end.  Captured into a CUDA graph this becomes two concurrent branches; the
         latency-bound NMS (one CTA per image, 32 of 148 SMs) then runs underneath the HBM-bound letterbox instead of
         after it."""
-        gdesc = peer_gather.desc if peer_gather is not None else None
         if not overlap or self._side is None or stream is not None:
             self.pre.enqueue(stream)
-            out, _ = self.fused.enqueue(self.batch, heads, stream, gather=gdesc)
-            if peer_gather is not None:
-                peer_gather.wait(stream)
+            out = self.decode_nms_gather(heads, peer_gather, stream)
             return out
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)                  # fork
         with torch.cuda.stream(self._side):
-            out, _ = self.fused.enqueue(self.batch, heads, gather=gdesc)
-            if peer_gather is not None:
-                peer_gather.wait()                   # one warp: the peers' rows of this step have landed
+            out = self.decode_nms_gather(heads, peer_gather)
         self.pre.enqueue()
         cur.wait_stream(self._side)                  # join
+        return out
+
+    def decode_nms_gather(self, heads, peer_gather: "PeerGather | None" = None, stream=None, fused_gather: bool = False) -> torch.Tensor:
+        """scan -> NMS (-> the multi-GPU gather).  Default gather = one small push + wait kernel after the NMS
+        (PeerGather.push); fused_gather=True stores from inside nms_kernel and waits with the one-warp kernel."""
+        if peer_gather is None:
+            return self.fused.enqueue(self.batch, heads, stream)[0]
+        if fused_gather or getattr(peer_gather, "fused", False):
+            out, _ = self.fused.enqueue(self.batch, heads, stream, gather=peer_gather.desc)
+            peer_gather.wait(stream)
+            return out
+        out, _ = self.fused.enqueue(self.batch, heads, stream)
+        peer_gather.push(out, self.fused.max_det, 0, stream)
         return out
 
     # ---- overlapped host pipeline: H2D of batch i+1 runs on a copy stream while batch i is decoded ----
@@ -113,9 +121,7 @@ class DetectionPipeline:
         sl["pre"].enqueue()
         if self.backbone is not None:
             heads = self.backbone(self.net_input)
-        out, _ = self.fused.enqueue(self.batch, heads, gather=peer_gather.desc if peer_gather is not None else None)
-        if peer_gather is not None:
-            peer_gather.wait()
+        out = self.decode_nms_gather(heads, peer_gather)
         sl["out_host"].copy_(out, non_blocking=True)
         sl["done"].record(compute)
         return sl["out_host"], sl["done"]
@@ -295,6 +301,14 @@ class PeerGather:
 
         from .plugins import _stream
         L.check(self._lib.trtx_gather_wait_enqueue(C.byref(self.desc), _stream(stream)), "trtx_gather_wait_enqueue")
+
+    def push(self, local_out: torch.Tensor, max_det: int, extra_floats: int = 0, stream=None) -> None:
+        """Push + wait as ONE small kernel after a plain (non-gather) decode + NMS: trtx_gather_push_enqueue."""
+        import ctypes as C
+
+        from .plugins import _ptr, _stream
+        L.check(self._lib.trtx_gather_push_enqueue(C.byref(self.desc), _ptr(local_out), int(local_out.shape[0]), int(max_det),
+                                                   int(extra_floats), _stream(stream)), "trtx_gather_push_enqueue")
 
     def close(self) -> None:
         for p in self._opened:

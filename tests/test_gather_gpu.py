@@ -40,8 +40,12 @@ def test_fused_peer_gather_protocol_two_logical_ranks(oracle, dev):
         for r in range(W):
             with torch.cuda.stream(streams[r]):
                 hd = [torch.from_numpy(h).to(dev) for h in heads[r]]
-                out, _ = fused[r].enqueue(B, hd, gather=descs[r])
-                L.check(lib.trtx_gather_wait_enqueue(C.byref(descs[r]), streams[r].cuda_stream), "wait")
+                if step % 2 == 0:   # the gather fused into nms_kernel + the one-warp wait kernel
+                    out, _ = fused[r].enqueue(B, hd, gather=descs[r])
+                    L.check(lib.trtx_gather_wait_enqueue(C.byref(descs[r]), streams[r].cuda_stream), "wait")
+                else:               # plain decode + NMS, then the push + wait kernel
+                    out, _ = fused[r].enqueue(B, hd)
+                    L.check(lib.trtx_gather_push_enqueue(C.byref(descs[r]), out.data_ptr(), B, K, 0, streams[r].cuda_stream), "push")
                 local.append(out)
         torch.cuda.synchronize()
         slot = step % SLOTS

@@ -26,8 +26,12 @@ pg = PeerGather(world, rank, B, 1 + K * 7, dev, slots=SLOTS)
 bad = 0
 for step in range(STEPS):
     heads = [torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=100 * step + rank, n_obj=20)]
-    out, _ = fused.enqueue(B, heads, gather=pg.desc)
-    pg.wait()
+    if step % 2 == 0:                     # alternate the two forms of the gather: fused into nms_kernel / push kernel
+        out, _ = fused.enqueue(B, heads, gather=pg.desc)
+        pg.wait()
+    else:
+        out, _ = fused.enqueue(B, heads)
+        pg.push(out, K)
     torch.cuda.synchronize()
     ref = torch.empty((world * B, 1 + K * 7), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(ref, out.contiguous())
