@@ -596,7 +596,7 @@ def run_v8(args, rank, world, local_rank):
                 peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=4)
                 peer.fused = bool(args.fused_gather)
                 gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
-                               "gather_push_kernel after the NMS: NVLink peer stores + flags + wait in one 8-CTA launch (trtx_gather), no collective kernel")
+                               "gather_push_kernel on a third graph chain: NVLink peer stores + flags + wait in one 8-CTA launch (trtx_gather), no collective kernel")
             except Exception as e:
                 print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
                 peer = None
@@ -614,6 +614,7 @@ def run_v8(args, rank, world, local_rank):
         #      ramps / tails and the latency-bound NMS hide under the other chain's HBM traffic.
         G = 1 if (use_ring or args.no_overlap) else max(1, min(args.graph_steps, R))
         chain_b = torch.cuda.Stream(dev, priority=-1)
+        chain_c = torch.cuda.Stream(dev)  # N > 1: the gather's push + wait kernels, off the scan -> NMS chain
 
         def make_step(j):   # single step (serial / NCCL-ring modes)
             p, h, prev = pipes_dev[j], head_sets[j], pipes_dev[(j - 1) % R]
@@ -630,12 +631,24 @@ def run_v8(args, rank, world, local_rank):
             def f():
                 cur = torch.cuda.current_stream(dev)
                 chain_b.wait_stream(cur)                     # fork
+                third = peer is not None and not peer.fused
+                if third:
+                    chain_c.wait_stream(cur)
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
-                        pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer)
+                        if third:   # NMS of step j -> event -> push + wait kernel on chain C; chain B goes straight on to step j+1
+                            out_j = pipes_dev[j % R].decode_nms_gather(head_sets[j % R], None)
+                            ev = torch.cuda.Event()
+                            ev.record(chain_b)
+                            chain_c.wait_event(ev)
+                            peer.push(out_j, MAX_OUT, 0, chain_c)
+                        else:
+                            pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer)
                 for j in range(j0, j0 + n):
                     pipes_dev[j % R].pre.enqueue()
                 cur.wait_stream(chain_b)                     # join
+                if third:
+                    cur.wait_stream(chain_c)
             return f
 
         if use_ring:  # NCCL communicator and buffers must exist before anything is captured
