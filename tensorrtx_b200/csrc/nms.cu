@@ -879,10 +879,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
         }
         __syncthreads();  // CTA-scope order of all peer stores before thread 0's system-scope fence (cumulative)
         if (tid == 0) {
-            __threadfence_system();
+            // gpu-scope fences order this CTA's stores before its count and the last CTA's view of all counts before the flag;
+            // the ONE system-scope operation is the release store of the flag (a system-scope fence under the step's HBM
+            // traffic costs several microseconds each: tools/gather_probe.py)
+            __threadfence();
             if (atomicAdd(&a.g.ctrl[1], 1u) == gridDim.x - 1) {  // last CTA of the launch: publish
                 a.g.ctrl[1] = 0u;
-                __threadfence_system();
+                __threadfence();
                 for (int p = 0; p < gworld; ++p)
                     st_release_sys(a.g.flags[p] + (size_t)a.g.rank * a.g.slots + gstep % (unsigned)a.g.slots, gstep + 1u);
             }
@@ -908,8 +911,7 @@ __global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
             }
         }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    __threadfence_system();
+    ok = __all_sync(0xffffffffu, ok);  // (the acquire loads above order the peers' rows before everything that follows)
     if (lane == 0) {
         if (!ok) g.ctrl[2] = 1u;
         g.ctrl[0] = s + 1u;
@@ -937,11 +939,11 @@ __global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, con
     }
     __syncthreads();
     if (tid != 0) return;
-    __threadfence_system();
+    __threadfence();  // gpu scope: this CTA's stores before its count (see nms_kernel's gather block)
     if (atomicAdd(&g.ctrl[1], 1u) != gridDim.x - 1) return;
     g.ctrl[1] = 0u;
-    __threadfence_system();
-    for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + (size_t)g.rank * g.slots + slot, s + 1u);
+    __threadfence();
+    for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + (size_t)g.rank * g.slots + slot, s + 1u);  // the system-scope release
     bool ok = true;
     const long long t0 = clock64();
     for (int p = 0; p < g.world && ok; ++p) {
@@ -954,7 +956,6 @@ __global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, con
             }
         }
     }
-    __threadfence_system();
     if (!ok) g.ctrl[2] = 1u;
     g.ctrl[0] = s + 1u;
 }
