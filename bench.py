@@ -596,7 +596,7 @@ def run_v8(args, rank, world, local_rank):
                 peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=4)
                 peer.fused = bool(args.fused_gather)
                 gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
-                               "gather_push_kernel on a third graph chain: NVLink peer stores + flags + wait in one 8-CTA launch (trtx_gather), no collective kernel")
+                               "gather_push_kernel (8 CTAs: NVLink peer stores + flags + wait) on a third graph chain, pipelined by one group of steps; no collective kernel")
             except Exception as e:
                 print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
                 peer = None
@@ -632,16 +632,24 @@ def run_v8(args, rank, world, local_rank):
                 cur = torch.cuda.current_stream(dev)
                 chain_b.wait_stream(cur)                     # fork
                 third = peer is not None and not peer.fused
+                evp = {}
                 if third:
+                    # chain C: the gather's push + wait kernels, software-pipelined by one group -- this graph pushes the
+                    # detections the PREVIOUS replay of the same group left in pipes_dev[j].fused.out (the first replay
+                    # pushes an unused buffer, bench's flush pushes the last group); NMS(j) below overwrites that buffer,
+                    # so it waits for push(j) -- which ran long before.  Nothing of the gather is on the scan -> NMS chain.
                     chain_c.wait_stream(cur)
+                    with torch.cuda.stream(chain_c):
+                        for j in range(j0, j0 + n):
+                            peer.push(pipes_dev[j % R].fused.out, MAX_OUT, 0)
+                            evp[j] = torch.cuda.Event()
+                            evp[j].record(chain_c)
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
-                        if third:   # NMS of step j -> event -> push + wait kernel on chain C; chain B goes straight on to step j+1
-                            out_j = pipes_dev[j % R].decode_nms_gather(head_sets[j % R], None)
-                            ev = torch.cuda.Event()
-                            ev.record(chain_b)
-                            chain_c.wait_event(ev)
-                            peer.push(out_j, MAX_OUT, 0, chain_c)
+                        if third:
+                            pipes_dev[j % R].fused.enqueue_scan(BATCH, head_sets[j % R])
+                            chain_b.wait_event(evp[j])
+                            pipes_dev[j % R].fused.enqueue_nms(BATCH, head_sets[j % R])
                         else:
                             pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer)
                 for j in range(j0, j0 + n):
@@ -712,6 +720,10 @@ def run_v8(args, rank, world, local_rank):
                 ring.launch(pipes_dev[i_last % R].fused.out, i_last % R)
             if use_ring:
                 ring.join()
+            if peer is not None and not peer.fused and group_replay is not None:
+                # the pushes are pipelined by one group: deliver the detections of the last G steps inside the timed region
+                for j in range(i_last - G + 1, i_last + 1):
+                    peer.push(pipes_dev[j % R].fused.out, MAX_OUT, 0)
 
         def step_e2e(i):
             # public API call with HOST frames: H2D (copy stream, double-buffered) + pre-process + decode + NMS + D2H
