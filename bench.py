@@ -614,7 +614,7 @@ def run_v8(args, rank, world, local_rank):
         #      ramps / tails and the latency-bound NMS hide under the other chain's HBM traffic.
         G = 1 if (use_ring or args.no_overlap) else max(1, min(args.graph_steps, R))
         chain_b = torch.cuda.Stream(dev, priority=-1)
-        chain_c = torch.cuda.Stream(dev)  # N > 1: the gather's push + wait kernels, off the scan -> NMS chain
+        chain_c = torch.cuda.Stream(dev, priority=-1)  # N > 1: the gather's push + wait kernels (tiny: dispatched ahead of the streaming grids)
 
         def make_step(j):   # single step (serial / NCCL-ring modes)
             p, h, prev = pipes_dev[j], head_sets[j], pipes_dev[(j - 1) % R]
