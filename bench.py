@@ -593,7 +593,7 @@ def run_v8(args, rank, world, local_rank):
         peer, ring, gather_mode = None, GatherRing(world, BATCH, pipe.fused.out.shape[1], dev, slots=R), "none"
         if world > 1 and not args.nccl_gather and not args.no_gather:
             try:
-                peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=4)
+                peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=2 * max(1, min(args.graph_steps, R)))
                 peer.fused = bool(args.fused_gather)
                 gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
                                "gather_push_kernel (8 CTAs: NVLink peer stores + flags + wait) on a third graph chain, pipelined by one group of steps; no collective kernel")
@@ -612,7 +612,7 @@ def run_v8(args, rank, world, local_rank):
         #      as TWO concurrent chains: chain A = their G letterbox launches, chain B (high priority) = their G x (scan -> NMS
         #      [-> gather wait]) launches.  Exactly one letterbox, one scan and one NMS launch per step; per-launch gaps, kernel
         #      ramps / tails and the latency-bound NMS hide under the other chain's HBM traffic.
-        G = 1 if (use_ring or args.no_overlap) else max(1, min(args.graph_steps, R))
+        G = 1 if (use_ring or (args.no_overlap and peer is None)) else max(1, min(args.graph_steps, R))
         chain_b = torch.cuda.Stream(dev, priority=-1)
         chain_c = torch.cuda.Stream(dev, priority=-1)  # N > 1: the gather's push + wait kernels (tiny: dispatched ahead of the streaming grids)
 
@@ -627,35 +627,39 @@ def run_v8(args, rank, world, local_rank):
                     ring.join()
             return f
 
-        def make_group(j0, n):   # steps j0 .. j0+n-1 (input sets mod R) as two chains
+        def make_group(j0, n, half=0):   # steps j0 .. j0+n-1 (input sets mod R) as two (N > 1: three) concurrent chains
             def f():
                 cur = torch.cuda.current_stream(dev)
                 chain_b.wait_stream(cur)                     # fork
-                third = peer is not None and not peer.fused
                 evp = {}
-                if third:
-                    # chain C: the gather's push + wait kernels, software-pipelined by one group -- this graph pushes the
-                    # detections the PREVIOUS replay of the same group left in pipes_dev[j].fused.out (the first replay
-                    # pushes an unused buffer, bench's flush pushes the last group); NMS(j) below overwrites that buffer,
-                    # so it waits for push(j) -- which ran long before.  Nothing of the gather is on the scan -> NMS chain.
+                if peer is not None and not peer.fused:
+                    # chain C: the gather, software-pipelined by one group -- this graph PUBLISHES the detections that the
+                    # previous replay of the group left in pipes_dev[j].fused.out (the first replay publishes an unused buffer,
+                    # flush_dev() publishes the last group) into the G slots of one half of the gathered buffers, then WAITS
+                    # for every rank's publish of those slots.  NMS(j) below overwrites the buffer push(j) reads, so it waits
+                    # for push(j) -- a local copy that ran long before; nothing on the scan -> NMS chain waits for a peer.
                     chain_c.wait_stream(cur)
                     with torch.cuda.stream(chain_c):
                         for j in range(j0, j0 + n):
-                            peer.push(pipes_dev[j % R].fused.out, MAX_OUT, 0)
+                            peer.push(pipes_dev[j % R].fused.out, half * G + (j - j0), MAX_OUT, 0)
                             evp[j] = torch.cuda.Event()
                             evp[j].record(chain_c)
+                        for j in range(j0, j0 + n):
+                            peer.wait(half * G + (j - j0))
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
-                        if third:
+                        if peer is None:
+                            pipes_dev[j % R].decode_nms_gather(head_sets[j % R], None)
+                        elif peer.fused:   # publish from inside nms_kernel, wait on the same chain
+                            pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer, None, half * G + (j - j0), fused_gather=True)
+                        else:
                             pipes_dev[j % R].fused.enqueue_scan(BATCH, head_sets[j % R])
                             chain_b.wait_event(evp[j])
                             pipes_dev[j % R].fused.enqueue_nms(BATCH, head_sets[j % R])
-                        else:
-                            pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer)
                 for j in range(j0, j0 + n):
                     pipes_dev[j % R].pre.enqueue()
                 cur.wait_stream(chain_b)                     # join
-                if third:
+                if evp:
                     cur.wait_stream(chain_c)
             return f
 
@@ -668,15 +672,21 @@ def run_v8(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()  # ranks enter the (eager warm-up + capture) steps together: the gather's wait kernel gives up after ~2 s
         group_replay, tail_replay = None, {}
-        if args.no_graph:
+        if args.no_graph and peer is None:
             dev_steps = [make_step(j) for j in range(R)]
-        elif G > 1:
+        elif G > 1 or peer is not None:
             assert R % G == 0 or G == R
             mode = "thread_local" if world > 1 else "global"
-            groups = [pipe.capture(make_group(j0, G), mode) for j0 in range(0, R, G)]
-            singles = [pipe.capture(make_group(j, 1), mode) for j in range(R)]
-            dev_steps = [g.replay for g in singles]
-            group_replay = [g.replay for g in groups]
+            halves = 2 if peer is not None else 1   # the gather alternates between the two halves of its slots from replay to replay
+            groups = [[pipe.capture(make_group(j0, G, h), mode) for h in range(halves)] for j0 in range(0, R, G)]
+            singles = [pipe.capture(make_group(j, 1), mode) for j in range(R)] if peer is None else None
+            dev_steps = [g.replay for g in singles] if singles else None
+            replays = [0]
+
+            def replay_group(k):
+                groups[k][replays[0] % halves].replay()
+                replays[0] += 1
+            group_replay = [lambda k=k: replay_group(k) for k in range(len(groups))]
         else:
             try:
                 dg = [pipe.capture(make_step(j), "thread_local" if world > 1 else "global") for j in range(R)]
@@ -699,6 +709,8 @@ def run_v8(args, rank, world, local_rank):
                 dev_steps = [make_eager(j) for j in range(R)]
 
         def step_dev(i):
+            if dev_steps is None:
+                raise SystemExit("--steps and --warmup must be multiples of --graph-steps when N > 1 (the gather works on whole groups)")
             dev_steps[i % R]()
 
         def run_dev(first, n):
@@ -721,15 +733,19 @@ def run_v8(args, rank, world, local_rank):
             if use_ring:
                 ring.join()
             if peer is not None and not peer.fused and group_replay is not None:
-                # the pushes are pipelined by one group: deliver the detections of the last G steps inside the timed region
+                # the publishes are pipelined by one group: deliver the detections of the last G steps inside the timed region
+                h = replays[0] % 2
                 for j in range(i_last - G + 1, i_last + 1):
-                    peer.push(pipes_dev[j % R].fused.out, MAX_OUT, 0)
+                    peer.push(pipes_dev[j % R].fused.out, h * G + (j % G), MAX_OUT, 0)
+                for j in range(i_last - G + 1, i_last + 1):
+                    peer.wait(h * G + (j % G))
+                replays[0] += 1
 
         def step_e2e(i):
             # public API call with HOST frames: H2D (copy stream, double-buffered) + pre-process + decode + NMS + D2H
             if use_ring:
                 ring.join()
-            pipe.submit(frame_sets_host[i % R], head_sets[i % R], peer_gather=peer)
+            pipe.submit(frame_sets_host[i % R], head_sets[i % R], peer_gather=peer, gather_slot=i % (2 * G) if peer is not None else 0)
             if use_ring:
                 ring.launch(pipe.fused.out, i % R)
 
@@ -738,6 +754,8 @@ def run_v8(args, rank, world, local_rank):
             sampler.start()
             time.sleep(0.25)
         K, W = args.steps, args.warmup
+        if peer is not None:   # whole groups only
+            K, W = max(G, K // G * G), max(G, (W + G - 1) // G * G)
         ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev, run_many=run_dev)
         ms_e2e, win_e2e, nb_e2e = timed_blocks(step_e2e, K, W, stream, dev, world, dist, (lambda i: ring.join()) if use_ring else None)
         gather_err = peer.error() if peer is not None else 0
@@ -752,7 +770,7 @@ def run_v8(args, rank, world, local_rank):
         if peer is not None:   # scan + NMS with the peer stores + wait, ranks in lockstep
             dist.barrier()
             def _sg(i):
-                pipe.decode_nms_gather(head_sets[i % R], peer)
+                pipe.decode_nms_gather(head_sets[i % R], peer, None, i % (2 * G), fused_gather=peer.fused)
             nms_gather_ms = time_kernel_loop(_sg, n_iso, stream, dev)
         lb_ms = time_kernel_loop(lambda i: pipes_dev[i % R].pre.enqueue(), n_iso, stream, dev)
         # the same scan launches inside ONE CUDA graph (how the step runs them): launch gaps are the graph's, not Python's
@@ -772,7 +790,8 @@ def run_v8(args, rank, world, local_rank):
         t.daemon = True
         t.start()
         torch.cuda.synchronize(dev)
-        dev_steps.clear()
+        if dev_steps:
+            dev_steps.clear()
         dist.barrier()
         torch.cuda.synchronize(dev)
         sys.stdout.flush()

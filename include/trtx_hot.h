@@ -202,23 +202,29 @@ TRTX_API int trtx_yolo_nms_after_scan_enqueue(const trtx_yolo_params* p, const t
                                               int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
                                               trtx_stream_t stream);
 
-/* Multi-GPU gather fused into the NMS kernel (images shard by batch, the only exchange is the gather of the
- * compact detections).  One process per GPU on one NVSwitch node; every rank owns
+/* Multi-GPU gather of the compact detections over NVLink peer memory (images shard by batch, the only exchange is
+ * this gather).  One process per GPU on one NVSwitch node; every rank owns
  *   out   : [slots][world*batch][1 + max_det*R] fp32  -- the gathered detections (rank r's images at [r*batch, (r+1)*batch))
- *   flags : [world][slots] uint32, zero-initialised
- *   ctrl  : [4] uint32, zero-initialised, local only: step counter, CTAs done, error (1 = a wait timed out), spare
+ *   flags : [world][slots] uint32, zero-initialised   -- flags[r][s] = how often rank r has published slot s
+ *   ctrl  : [4] uint32, zero-initialised, local only  -- [1] scratch counter, [2] error (1 = a wait timed out)
  * allocated with trtx_peer_alloc (cudaMalloc + CUDA IPC handle) and mapped into the other ranks with trtx_peer_open, so
- * that out_dev[] / flags_dev[] hold, on every rank, the addresses of all ranks' buffers ([rank] = its own).
- * trtx_yolo_decode_nms_gather_enqueue = trtx_yolo_decode_nms_enqueue whose NMS kernel additionally stores every emitted
- * row and the per-image count into slot (step % slots) of EVERY rank's `out` over NVLink (no collective kernel, no extra
- * launch, no SMs beyond the NMS CTAs), then publishes flag[rank][slot] = step + 1 on every rank with system-scope release.
- * Rows past `count` are not cleared in the gathered buffer.  trtx_gather_wait_enqueue (one warp) completes the step on
- * the stream: it waits until all `world` flags of the slot carry the step, then advances the local step counter; work
- * enqueued after it may read slot (step % slots) of the local `out`.  A slot is rewritten `slots` steps later (slots >= 2:
- * a peer can only be that far ahead after this rank finished the step in between).  Every rank must enqueue the same
- * sequence of steps.  world <= 8. */
+ * that out_dev[] / flags_dev[] hold, on every rank, the addresses of all ranks' buffers ([rank] = its own).  `slot` is chosen
+ * by the caller per call (plain data: calls captured into CUDA graphs keep their slot).
+ *   PUBLISH  trtx_gather_push_enqueue: a small kernel (8 CTAs) copies the live part [count, rows] of every image of a local
+ *            compact output into `slot` of EVERY rank's `out` (lane-consecutive NVLink stores) and then raises this rank's
+ *            counter of the slot on every rank with ONE system-scope release store.  It waits for nobody.
+ *            trtx_yolo_decode_nms_gather_enqueue does the same from inside nms_kernel (no extra launch; but the NMS CTAs'
+ *            32 whole SMs stay occupied during the copy and the release -- measured in DESIGN.md section 5).
+ *   WAIT     trtx_gather_wait_enqueue (one warp): returns on the stream once every rank's counter of `slot` has reached this
+ *            rank's own, i.e. all ranks' rows of this round are in the local out[slot]; work enqueued after it may read them.
+ *            Rows past an image's `count` are stale.  Gives up after ~2 s (ctrl[2] = 1) instead of hanging the GPU.
+ * Reusing a slot overwrites it on every rank: a rank may publish into a slot again only after all ranks have finished
+ * reading the previous round.  The pattern that guarantees it without further handshakes: 2*G slots used in halves; the G
+ * publishes of a round go to one half, then the G waits, all on the streams of the round; the next round uses the other half.
+ * (A rank cannot get two rounds ahead of a peer: its own waits need the peer's publishes of the round in between.)
+ * Every rank must enqueue the same sequence.  world <= 8. */
 typedef struct trtx_gather {
-    int32_t world, rank, slots, reserved;
+    int32_t world, rank, slots, slot;
     float* out_dev[8];
     uint32_t* flags_dev[8];
     uint32_t* ctrl_dev;
@@ -227,15 +233,9 @@ TRTX_API int trtx_yolo_decode_nms_gather_enqueue(const trtx_yolo_params* p, cons
                                                  const void* const* inputs_dev, float* compact_out_dev,
                                                  int32_t* keep_index_dev, void* workspace_dev, size_t workspace_bytes,
                                                  const trtx_gather* gather, trtx_stream_t stream);
-TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream);
-/* The same step as ONE separate small kernel after a plain trtx_yolo_decode_nms_enqueue / trtx_nms_enqueue (8 CTAs of 256
- * threads that co-reside with the streaming kernels of the step): copies the live part [count, rows] of every image of
- * compact_out_dev [batch, 1 + max_det*(7+extra_floats)] into slot (step % slots) of every rank, publishes the flags, waits
- * for the peers' and advances the step counter (push + wait; do NOT also call trtx_gather_wait_enqueue).  Same buffers,
- * same contract.  Preferred when the step is HBM-bound: the fused variant holds the NMS CTAs' 32 whole SMs during the
- * NVLink round trips (measured in DESIGN.md section 5). */
 TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,
                                       int extra_floats, trtx_stream_t stream);
+TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream);
 /* Peer-mappable device memory (zero-initialised) + its 64-byte CUDA IPC handle; open / close a peer's handle; free. */
 TRTX_API int trtx_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
 TRTX_API int trtx_peer_open(const unsigned char handle[64], void** dev_ptr);

@@ -69,7 +69,7 @@ class NmsParams(C.Structure):
 
 
 class Gather(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("slots", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("slots", C.c_int32), ("slot", C.c_int32),
                 ("out_dev", C.c_void_p * 8), ("flags_dev", C.c_void_p * 8), ("ctrl_dev", C.c_void_p)]
 
 

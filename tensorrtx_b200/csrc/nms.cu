@@ -78,8 +78,8 @@ struct NmsArgs {
     struct Gather {
         float* out[8];
         unsigned* flags[8];
-        unsigned* ctrl;  // local: [0] step counter, [1] CTAs done, [2] error
-        int world, rank, slots;
+        unsigned* ctrl;  // local: [1] CTAs done, [2] error ([0], [3] unused)
+        int world, rank, slots, slot;
     } g;
 };
 
@@ -640,10 +640,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     int32_t* oidx = a.keep_index ? a.keep_index + (size_t)b * a.max_det : nullptr;
     // gathered buffers: [slots][world*B][1 + max_det*R]; this image's block on every rank
     const int gworld = a.g.world;
-    const unsigned gstep = gworld ? *reinterpret_cast<volatile unsigned*>(a.g.ctrl) : 0u;
-    const size_t goff = gworld ? ((size_t)(gstep % (unsigned)a.g.slots) * gworld * gridDim.x + (size_t)a.g.rank * gridDim.x + b) *
-                                         (1 + (size_t)a.max_det * R)
-                               : 0;
+    const size_t goff = gworld ? ((size_t)a.g.slot * gworld * gridDim.x + (size_t)a.g.rank * gridDim.x + b) * (1 + (size_t)a.max_det * R) : 0;
 
     if (greedy) {
         // ---------------- E: class segments ----------------
@@ -886,24 +883,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             if (atomicAdd(&a.g.ctrl[1], 1u) == gridDim.x - 1) {  // last CTA of the launch: publish
                 a.g.ctrl[1] = 0u;
                 __threadfence();
-                for (int p = 0; p < gworld; ++p)
-                    st_release_sys(a.g.flags[p] + (size_t)a.g.rank * a.g.slots + gstep % (unsigned)a.g.slots, gstep + 1u);
+                const size_t fi = (size_t)a.g.rank * a.g.slots + a.g.slot;  // this rank's publish counter of the slot, on every rank
+                const unsigned v = *reinterpret_cast<volatile unsigned*>(a.g.flags[a.g.rank] + fi) + 1u;
+                for (int p = 0; p < gworld; ++p) st_release_sys(a.g.flags[p] + fi, v);
             }
         }
     }
     TRTX_STAMP(6);
 }
 
-// Completes a gather step: spins (acquire, system scope) until every rank's flag for the current slot carries this step,
-// then advances the local step counter.  One warp; gives up after ~2 s of SM clocks (ctrl[2] = 1) instead of hanging the GPU.
+// Completes a gather of one slot on this rank: spins (acquire, system scope) until every rank's publish counter of the slot
+// has reached this rank's own (its own publish precedes this kernel in stream order).  One warp; gives up after ~2 s of SM
+// clocks (ctrl[2] = 1) instead of hanging the GPU.
 __global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
-    const unsigned s = g.ctrl[0], slot = s % (unsigned)g.slots;
     const int lane = threadIdx.x;
+    const unsigned* fl = g.flags[g.rank];
+    const unsigned expected = ld_acquire_sys(fl + (size_t)g.rank * g.slots + g.slot);
     bool ok = true;
     if (lane < g.world) {
-        const unsigned* f = g.flags[g.rank] + (size_t)lane * g.slots + slot;
+        const unsigned* f = fl + (size_t)lane * g.slots + g.slot;
         const long long t0 = clock64();
-        while (ld_acquire_sys(f) != s + 1u) {
+        while ((int)(ld_acquire_sys(f) - expected) < 0) {
             __nanosleep(100);
             if (clock64() - t0 > 4000000000ll) {
                 ok = false;
@@ -912,26 +912,21 @@ __global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
         }
     }
     ok = __all_sync(0xffffffffu, ok);  // (the acquire loads above order the peers' rows before everything that follows)
-    if (lane == 0) {
-        if (!ok) g.ctrl[2] = 1u;
-        g.ctrl[0] = s + 1u;
-    }
+    if (lane == 0 && !ok) g.ctrl[2] = 1u;
 }
 
-// The same gather as a SEPARATE small kernel (a few 256-thread CTAs that co-reside with the step's streaming kernels): copies
-// the live part of every image's block of the local compact output to every rank, publishes the flags, and its last CTA
-// then waits for the peers' flags and advances the step counter -- push and wait in one launch.  Measured at N = 2
-// (profiles/r02d_*): the variant fused into nms_kernel keeps 32 whole SMs (1024 threads x 64 registers per CTA) occupied for
-// the NVLink round trips of its system-scope fence, which slows the HBM-bound kernels of the other chain; this one does not.
+// The same publish as a SEPARATE small kernel (a few 256-thread CTAs that co-reside with the step's streaming kernels): copies
+// the live part of every image's block of the local compact output into the slot on every rank and publishes the slot's
+// counter.  It does not wait for anybody.  (Measured, DESIGN.md section 5: the variant fused into nms_kernel keeps the NMS
+// CTAs' 32 whole SMs busy during the copy and the release, and everything that follows the NMS on its stream behind it.)
 __global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, const float* __restrict__ local, int batch, int cols,
                                                           int max_det, int R) {
-    const unsigned s = *reinterpret_cast<volatile unsigned*>(g.ctrl), slot = s % (unsigned)g.slots;
     const int tid = threadIdx.x;
     for (int b = blockIdx.x; b < batch; b += gridDim.x) {
         const float* src = local + (size_t)b * cols;
         const int n = min(max((int)src[0], 0), max_det);
         const int live = 1 + n * R;
-        const size_t off = (((size_t)slot * g.world + g.rank) * batch + b) * cols;
+        const size_t off = (((size_t)g.slot * g.world + g.rank) * batch + b) * cols;
         for (int p = 0; p < g.world; ++p) {
             float* dst = g.out[p] + off;
             for (int i = tid; i < live; i += 256) dst[i] = src[i];
@@ -943,21 +938,9 @@ __global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, con
     if (atomicAdd(&g.ctrl[1], 1u) != gridDim.x - 1) return;
     g.ctrl[1] = 0u;
     __threadfence();
-    for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + (size_t)g.rank * g.slots + slot, s + 1u);  // the system-scope release
-    bool ok = true;
-    const long long t0 = clock64();
-    for (int p = 0; p < g.world && ok; ++p) {
-        const unsigned* f = g.flags[g.rank] + (size_t)p * g.slots + slot;
-        while (ld_acquire_sys(f) != s + 1u) {
-            __nanosleep(100);
-            if (clock64() - t0 > 4000000000ll) {
-                ok = false;
-                break;
-            }
-        }
-    }
-    if (!ok) g.ctrl[2] = 1u;
-    g.ctrl[0] = s + 1u;
+    const size_t fi = (size_t)g.rank * g.slots + g.slot;
+    const unsigned v = *reinterpret_cast<volatile unsigned*>(g.flags[g.rank] + fi) + 1u;
+    for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + fi, v);  // the one system-scope release
 }
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
@@ -1044,7 +1027,9 @@ TRTX_API int trtx_nms_enqueue(const trtx_nms_params* p, int batch, const float* 
 static int fill_gather(const trtx_gather* g, NmsArgs::Gather* o) {
     memset(o, 0, sizeof(*o));
     if (!g) return TRTX_OK;
-    if (g->world < 1 || g->world > 8 || g->rank < 0 || g->rank >= g->world || g->slots < 2 || !g->ctrl_dev) return TRTX_ERR_INVALID;
+    if (g->world < 1 || g->world > 8 || g->rank < 0 || g->rank >= g->world || g->slots < 1 || g->slot < 0 || g->slot >= g->slots ||
+        !g->ctrl_dev)
+        return TRTX_ERR_INVALID;
     for (int r = 0; r < g->world; ++r) {
         if (!g->out_dev[r] || !g->flags_dev[r]) return TRTX_ERR_INVALID;
         o->out[r] = g->out_dev[r];
@@ -1054,6 +1039,7 @@ static int fill_gather(const trtx_gather* g, NmsArgs::Gather* o) {
     o->world = g->world;
     o->rank = g->rank;
     o->slots = g->slots;
+    o->slot = g->slot;
     return TRTX_OK;
 }
 

@@ -53,7 +53,7 @@ class DetectionPipeline:
         return self.out_host
 
     def run_device(self, heads: Sequence[torch.Tensor], stream=None, overlap: bool = True,
-                   peer_gather: "PeerGather | None" = None) -> torch.Tensor:
+                   peer_gather: "PeerGather | None" = None, slot: int = 0) -> torch.Tensor:
         """Device-resident step: pre-process the frames already in HBM + decode + NMS (no host copies).
 
         The letterbox of this batch does not depend on the decode/NMS of the head tensors (with a real backbone the heads
@@ -64,27 +64,29 @@ class DetectionPipeline:
         after it."""
         if not overlap or self._side is None or stream is not None:
             self.pre.enqueue(stream)
-            out = self.decode_nms_gather(heads, peer_gather, stream)
+            out = self.decode_nms_gather(heads, peer_gather, stream, slot)
             return out
         cur = torch.cuda.current_stream(self.device)
         self._side.wait_stream(cur)                  # fork
         with torch.cuda.stream(self._side):
-            out = self.decode_nms_gather(heads, peer_gather)
+            out = self.decode_nms_gather(heads, peer_gather, None, slot)
         self.pre.enqueue()
         cur.wait_stream(self._side)                  # join
         return out
 
-    def decode_nms_gather(self, heads, peer_gather: "PeerGather | None" = None, stream=None, fused_gather: bool = False) -> torch.Tensor:
-        """scan -> NMS (-> the multi-GPU gather).  Default gather = one small push + wait kernel after the NMS
-        (PeerGather.push); fused_gather=True stores from inside nms_kernel and waits with the one-warp kernel."""
+    def decode_nms_gather(self, heads, peer_gather: "PeerGather | None" = None, stream=None, slot: int = 0, fused_gather: bool = False,
+                          wait: bool = True) -> torch.Tensor:
+        """scan -> NMS (-> the multi-GPU gather into `slot`: push kernel after the NMS by default, from inside nms_kernel with
+        fused_gather=True; then the wait kernel unless wait=False)."""
         if peer_gather is None:
             return self.fused.enqueue(self.batch, heads, stream)[0]
-        if fused_gather or getattr(peer_gather, "fused", False):
-            out, _ = self.fused.enqueue(self.batch, heads, stream, gather=peer_gather.desc)
-            peer_gather.wait(stream)
-            return out
-        out, _ = self.fused.enqueue(self.batch, heads, stream)
-        peer_gather.push(out, self.fused.max_det, 0, stream)
+        if fused_gather:
+            out, _ = self.fused.enqueue(self.batch, heads, stream, gather=peer_gather.desc(slot))
+        else:
+            out, _ = self.fused.enqueue(self.batch, heads, stream)
+            peer_gather.push(out, slot, self.fused.max_det, 0, stream)
+        if wait:
+            peer_gather.wait(slot, stream)
         return out
 
     # ---- overlapped host pipeline: H2D of batch i+1 runs on a copy stream while batch i is decoded ----
@@ -103,7 +105,7 @@ class DetectionPipeline:
         self._next = 0
 
     def submit(self, frames_host: torch.Tensor, heads: Sequence[torch.Tensor] | None = None, slots: int = 2,
-               peer_gather: "PeerGather | None" = None):
+               peer_gather: "PeerGather | None" = None, gather_slot: int = 0):
         """Asynchronous step with double buffering: returns (pinned host result, event); the result is valid
         once the event has completed.  The H2D copy is issued on a dedicated copy stream so that it overlaps
         the kernels of the previous submit() (the reference serialises memcpy -> H2D -> kernel -> sync per
@@ -121,7 +123,7 @@ class DetectionPipeline:
         sl["pre"].enqueue()
         if self.backbone is not None:
             heads = self.backbone(self.net_input)
-        out = self.decode_nms_gather(heads, peer_gather)
+        out = self.decode_nms_gather(heads, peer_gather, None, gather_slot)
         sl["out_host"].copy_(out, non_blocking=True)
         sl["done"].record(compute)
         return sl["out_host"], sl["done"]
@@ -241,16 +243,19 @@ class _RawCuda:
 
 
 class PeerGather:
-    """The gather of the compact detections FUSED into the NMS kernel (trtx_gather, include/trtx_hot.h): every rank's
-    nms_kernel stores its kept rows straight into the gathered buffer of every rank over NVLink peer memory and raises a
-    flag; `wait()` enqueues the one-warp kernel that completes the step.  No NCCL kernel competes with the step for SMs
-    (the NCCL all-gather of round 1 stretched the step by 8-20 %).
+    """The gather of the compact detections over NVLink peer memory (trtx_gather, include/trtx_hot.h): `push(out, slot)`
+    enqueues the small kernel that copies this rank's kept rows into `slot` of the gathered buffer of EVERY rank and
+    publishes the slot (it waits for nobody); `wait(slot)` enqueues the one-warp kernel that returns once every rank's rows
+    of the round are in the local buffer.  No NCCL kernel competes with the step for SMs (the NCCL all-gather of round 1
+    stretched the step by 8-20 %).  `desc(slot)` is the descriptor for the variant fused into
+    nms_kernel (FusedYoloDecodeNms.enqueue(gather=...)).
 
     Buffers are cudaMalloc'ed by the library and exchanged between the processes of the node as CUDA IPC handles through
     torch.distributed (object all-gather); torch is plumbing only.  `result(slot)` views this rank's gathered buffer
-    [world*batch, 1 + max_det*7]; rows past each image's count are stale."""
+    [world*batch, 1 + max_det*7]; rows past each image's count are stale.  Slot reuse: see trtx_hot.h (use 2*G slots in
+    halves, a round's pushes then its waits)."""
 
-    def __init__(self, world: int, rank: int, batch: int, cols: int, device, slots: int = 4):
+    def __init__(self, world: int, rank: int, batch: int, cols: int, device, slots: int = 8):
         import ctypes as C
 
         import torch.distributed as dist
@@ -267,48 +272,62 @@ class PeerGather:
             self._own.append(ptr.value)
             handles.append(bytes(h))
         every = [None] * world
-        dist.all_gather_object(every, (rank, handles[0], handles[1]))
-        g = L.Gather()
-        g.world, g.rank, g.slots = world, rank, slots
+        if world > 1:
+            dist.all_gather_object(every, (rank, handles[0], handles[1]))
+        else:
+            every = [(rank, handles[0], handles[1])]
+        self._out_ptrs, self._flag_ptrs = [0] * world, [0] * world
         self._opened = []
         for r, h_out, h_flags in every:
             if r == rank:
-                g.out_dev[r], g.flags_dev[r] = self._own[0], self._own[1]
+                self._out_ptrs[r], self._flag_ptrs[r] = self._own[0], self._own[1]
                 continue
             for k, h in ((0, h_out), (1, h_flags)):
                 ptr = C.c_void_p()
                 buf = (C.c_ubyte * 64).from_buffer_copy(h)
                 L.check(self._lib.trtx_peer_open(buf, C.byref(ptr)), "trtx_peer_open")
                 self._opened.append(ptr.value)
-                (g.out_dev if k == 0 else g.flags_dev)[r] = ptr.value
-        g.ctrl_dev = self._own[2]
-        self.desc = g
+                (self._out_ptrs if k == 0 else self._flag_ptrs)[r] = ptr.value
+        self._descs = [self._make_desc(s) for s in range(slots)]
         self._out = torch.as_tensor(_RawCuda(self._own[0], (slots, world * batch, cols), "<f4"), device=self.device)
         self._ctrl = torch.as_tensor(_RawCuda(self._own[2], (4,), "<u4"), device=self.device)
-        dist.barrier()  # every rank has mapped every buffer before anyone stores into them
+        self._flags = torch.as_tensor(_RawCuda(self._own[1], (world, slots), "<u4"), device=self.device)
+        if world > 1:
+            dist.barrier()  # every rank has mapped every buffer before anyone stores into them
+
+    def _make_desc(self, slot: int):
+        g = L.Gather()
+        g.world, g.rank, g.slots, g.slot = self.world, self.rank, self.slots, slot
+        for r in range(self.world):
+            g.out_dev[r], g.flags_dev[r] = self._out_ptrs[r], self._flag_ptrs[r]
+        g.ctrl_dev = self._own[2]
+        return g
+
+    def desc(self, slot: int):
+        return self._descs[slot]
 
     def result(self, slot: int) -> torch.Tensor:
         return self._out[slot]
 
-    def step_counter(self) -> int:
-        return int(self._ctrl[0].item())
+    def published(self) -> torch.Tensor:
+        """[world, slots] publish counters as seen by this rank."""
+        return self._flags
 
     def error(self) -> int:
         return int(self._ctrl[2].item())
 
-    def wait(self, stream=None) -> None:
-        import ctypes as C
-
-        from .plugins import _stream
-        L.check(self._lib.trtx_gather_wait_enqueue(C.byref(self.desc), _stream(stream)), "trtx_gather_wait_enqueue")
-
-    def push(self, local_out: torch.Tensor, max_det: int, extra_floats: int = 0, stream=None) -> None:
-        """Push + wait as ONE small kernel after a plain (non-gather) decode + NMS: trtx_gather_push_enqueue."""
+    def push(self, local_out: torch.Tensor, slot: int, max_det: int, extra_floats: int = 0, stream=None) -> None:
         import ctypes as C
 
         from .plugins import _ptr, _stream
-        L.check(self._lib.trtx_gather_push_enqueue(C.byref(self.desc), _ptr(local_out), int(local_out.shape[0]), int(max_det),
+        L.check(self._lib.trtx_gather_push_enqueue(C.byref(self._descs[slot]), _ptr(local_out), int(local_out.shape[0]), int(max_det),
                                                    int(extra_floats), _stream(stream)), "trtx_gather_push_enqueue")
+
+    def wait(self, slot: int, stream=None) -> None:
+        import ctypes as C
+
+        from .plugins import _stream
+        L.check(self._lib.trtx_gather_wait_enqueue(C.byref(self._descs[slot]), _stream(stream)), "trtx_gather_wait_enqueue")
 
     def close(self) -> None:
         for p in self._opened:

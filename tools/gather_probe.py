@@ -21,9 +21,12 @@ cols = 1 + K * 7
 out = torch.zeros((4, B, cols), device=dev)
 flags = torch.zeros((1, 4), dtype=torch.int32, device=dev)
 ctrl = torch.zeros(4, dtype=torch.int32, device=dev)
-g = L.Gather()
-g.world, g.rank, g.slots = 1, 0, 4
-g.out_dev[0], g.flags_dev[0], g.ctrl_dev = out.data_ptr(), flags.data_ptr(), ctrl.data_ptr()
+gs = []
+for sl in range(4):
+    g = L.Gather()
+    g.world, g.rank, g.slots, g.slot = 1, 0, 4, sl
+    g.out_dev[0], g.flags_dev[0], g.ctrl_dev = out.data_ptr(), flags.data_ptr(), ctrl.data_ptr()
+    gs.append(g)
 chain_b = torch.cuda.Stream(dev, priority=-1)
 chain_c = torch.cuda.Stream(dev)
 
@@ -36,6 +39,7 @@ def group(mode):
             chain_c.wait_stream(cur)
         with torch.cuda.stream(chain_b):
             for j in range(R):
+                g = gs[j]
                 if mode == "fused":
                     pipes[j].fused.enqueue(B, heads[j], gather=g)
                     L.check(lib.trtx_gather_wait_enqueue(C.byref(g), chain_b.cuda_stream), "wait")
@@ -43,11 +47,13 @@ def group(mode):
                     o, _ = pipes[j].fused.enqueue(B, heads[j])
                     if mode == "push":
                         L.check(lib.trtx_gather_push_enqueue(C.byref(g), o.data_ptr(), B, K, 0, chain_b.cuda_stream), "push")
+                        L.check(lib.trtx_gather_wait_enqueue(C.byref(g), chain_b.cuda_stream), "wait")
                     elif mode == "push_c":      # the push + wait kernel on a third chain: off the scan -> NMS critical path
                         ev = torch.cuda.Event()
                         ev.record(chain_b)
                         chain_c.wait_event(ev)
                         L.check(lib.trtx_gather_push_enqueue(C.byref(g), o.data_ptr(), B, K, 0, chain_c.cuda_stream), "push")
+                        L.check(lib.trtx_gather_wait_enqueue(C.byref(g), chain_c.cuda_stream), "wait")
         for j in range(R):
             pipes[j].pre.enqueue()
         cur.wait_stream(chain_b)

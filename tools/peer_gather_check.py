@@ -19,19 +19,20 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-B, K, SLOTS, STEPS = 8, 1000, 3, 7
+B, K, SLOTS, STEPS = 8, 1000, 4, 11
 plug = P.YoloLayerPlugin(80, 17, 0.0, 640, 640, K, False, False, False, (8, 16, 32))
 fused = P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev)
 pg = PeerGather(world, rank, B, 1 + K * 7, dev, slots=SLOTS)
 bad = 0
 for step in range(STEPS):
     heads = [torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=100 * step + rank, n_obj=20)]
-    if step % 2 == 0:                     # alternate the two forms of the gather: fused into nms_kernel / push kernel
-        out, _ = fused.enqueue(B, heads, gather=pg.desc)
-        pg.wait()
+    slot = step % SLOTS
+    if step % 2 == 0:                     # alternate the two forms of the publish: from inside nms_kernel / push kernel
+        out, _ = fused.enqueue(B, heads, gather=pg.desc(slot))
     else:
         out, _ = fused.enqueue(B, heads)
-        pg.push(out, K)
+        pg.push(out, slot, K)
+    pg.wait(slot)
     torch.cuda.synchronize()
     ref = torch.empty((world * B, 1 + K * 7), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(ref, out.contiguous())
@@ -41,7 +42,7 @@ for step in range(STEPS):
         n = int(ref[i, 0])
         if got[i, 0] != n or not np.array_equal(got[i, 1:1 + n * 7], ref[i, 1:1 + n * 7]) or n < 3:
             bad += 1
-    assert pg.step_counter() == step + 1 and pg.error() == 0, (pg.step_counter(), pg.error())
+    assert pg.error() == 0 and pg.published()[:, step % SLOTS].cpu().tolist() == [step // SLOTS + 1] * world, pg.published().cpu().tolist()
     dist.barrier()
 t = torch.tensor([bad], device=dev)
 dist.all_reduce(t)
