@@ -596,7 +596,7 @@ def run_v8(args, rank, world, local_rank):
                 peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=2 * max(1, min(args.graph_steps, R)))
                 peer.fused = bool(args.fused_gather)
                 gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
-                               "gather_push_kernel (8 CTAs: NVLink peer stores + flags + wait) on a third graph chain, pipelined by one group of steps; no collective kernel")
+                               "one gather_push_kernel (8 CTAs: NVLink peer stores + one release) + one gather_wait_kernel per group of steps on a third graph chain, pipelined by one group; no collective kernel")
             except Exception as e:
                 print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
                 peer = None
@@ -639,13 +639,13 @@ def run_v8(args, rank, world, local_rank):
                     # for every rank's publish of those slots.  NMS(j) below overwrites the buffer push(j) reads, so it waits
                     # for push(j) -- a local copy that ran long before; nothing on the scan -> NMS chain waits for a peer.
                     chain_c.wait_stream(cur)
-                    with torch.cuda.stream(chain_c):
+                    with torch.cuda.stream(chain_c):   # ONE publish kernel and ONE wait kernel for the group's n slots
+                        peer.push_many([pipes_dev[j % R].fused.out for j in range(j0, j0 + n)], half * G, MAX_OUT, 0)
+                        ev = torch.cuda.Event()
+                        ev.record(chain_c)
                         for j in range(j0, j0 + n):
-                            peer.push(pipes_dev[j % R].fused.out, half * G + (j - j0), MAX_OUT, 0)
-                            evp[j] = torch.cuda.Event()
-                            evp[j].record(chain_c)
-                        for j in range(j0, j0 + n):
-                            peer.wait(half * G + (j - j0))
+                            evp[j] = ev
+                        peer.wait(half * G, n=n)
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
                         if peer is None:
@@ -735,10 +735,8 @@ def run_v8(args, rank, world, local_rank):
             if peer is not None and not peer.fused and group_replay is not None:
                 # the publishes are pipelined by one group: deliver the detections of the last G steps inside the timed region
                 h = replays[0] % 2
-                for j in range(i_last - G + 1, i_last + 1):
-                    peer.push(pipes_dev[j % R].fused.out, h * G + (j % G), MAX_OUT, 0)
-                for j in range(i_last - G + 1, i_last + 1):
-                    peer.wait(h * G + (j % G))
+                peer.push_many([pipes_dev[j % R].fused.out for j in range(i_last - G + 1, i_last + 1)], h * G, MAX_OUT, 0)
+                peer.wait(h * G, n=G)
                 replays[0] += 1
 
         def step_e2e(i):

@@ -236,6 +236,12 @@ TRTX_API int trtx_yolo_decode_nms_gather_enqueue(const trtx_yolo_params* p, cons
 TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,
                                       int extra_floats, trtx_stream_t stream);
 TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream);
+/* The same for n <= 8 consecutive slots slot .. slot+n-1 in ONE launch each (a round of n steps: one push kernel publishing
+ * the n local outputs compact_outs_dev[0..n) -- a HOST array of device pointers -- with a single expensive release, one wait
+ * kernel for the n slots; world * n <= 64). */
+TRTX_API int trtx_gather_push_many_enqueue(const trtx_gather* gather, const float* const* compact_outs_dev, int n, int batch,
+                                           int max_det, int extra_floats, trtx_stream_t stream);
+TRTX_API int trtx_gather_wait_many_enqueue(const trtx_gather* gather, int nslots, trtx_stream_t stream);
 /* Peer-mappable device memory (zero-initialised) + its 64-byte CUDA IPC handle; open / close a peer's handle; free. */
 TRTX_API int trtx_peer_alloc(size_t bytes, void** dev_ptr, unsigned char handle[64]);
 TRTX_API int trtx_peer_open(const unsigned char handle[64], void** dev_ptr);

@@ -895,13 +895,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 // Completes a gather of one slot on this rank: spins (acquire, system scope) until every rank's publish counter of the slot
 // has reached this rank's own (its own publish precedes this kernel in stream order).  One warp; gives up after ~2 s of SM
 // clocks (ctrl[2] = 1) instead of hanging the GPU.
-__global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(64) gather_wait_kernel(NmsArgs::Gather g, int nslots) {
+    const int lane = threadIdx.x;  // one thread per (rank, slot): world * nslots <= 64
     const unsigned* fl = g.flags[g.rank];
-    const unsigned expected = ld_acquire_sys(fl + (size_t)g.rank * g.slots + g.slot);
     bool ok = true;
-    if (lane < g.world) {
-        const unsigned* f = fl + (size_t)lane * g.slots + g.slot;
+    if (lane < g.world * nslots) {
+        const int r = lane / nslots, sl = g.slot + lane - r * nslots;
+        const unsigned expected = ld_acquire_sys(fl + (size_t)g.rank * g.slots + sl);
+        const unsigned* f = fl + (size_t)r * g.slots + sl;
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(f) - expected) < 0) {
             __nanosleep(100);
@@ -911,22 +912,25 @@ __global__ void __launch_bounds__(32) gather_wait_kernel(NmsArgs::Gather g) {
             }
         }
     }
-    ok = __all_sync(0xffffffffu, ok);  // (the acquire loads above order the peers' rows before everything that follows)
-    if (lane == 0 && !ok) g.ctrl[2] = 1u;
+    if (!ok) g.ctrl[2] = 1u;  // (the acquire loads above order the peers' rows before everything that follows)
 }
 
 // The same publish as a SEPARATE small kernel (a few 256-thread CTAs that co-reside with the step's streaming kernels): copies
 // the live part of every image's block of the local compact output into the slot on every rank and publishes the slot's
 // counter.  It does not wait for anybody.  (Measured, DESIGN.md section 5: the variant fused into nms_kernel keeps the NMS
 // CTAs' 32 whole SMs busy during the copy and the release, and everything that follows the NMS on its stream behind it.)
-__global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, const float* __restrict__ local, int batch, int cols,
-                                                          int max_det, int R) {
+struct PushSrc {
+    const float* src[8];  // local compact outputs of n consecutive steps -> slots slot .. slot+n-1
+    int n;
+};
+__global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, PushSrc ps, int batch, int cols, int max_det, int R) {
     const int tid = threadIdx.x;
-    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-        const float* src = local + (size_t)b * cols;
+    for (int w = blockIdx.x; w < ps.n * batch; w += gridDim.x) {
+        const int k = w / batch, b = w - k * batch;
+        const float* src = ps.src[k] + (size_t)b * cols;
         const int n = min(max((int)src[0], 0), max_det);
         const int live = 1 + n * R;
-        const size_t off = (((size_t)g.slot * g.world + g.rank) * batch + b) * cols;
+        const size_t off = (((size_t)(g.slot + k) * g.world + g.rank) * batch + b) * cols;
         for (int p = 0; p < g.world; ++p) {
             float* dst = g.out[p] + off;
             for (int i = tid; i < live; i += 256) dst[i] = src[i];
@@ -938,9 +942,11 @@ __global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, con
     if (atomicAdd(&g.ctrl[1], 1u) != gridDim.x - 1) return;
     g.ctrl[1] = 0u;
     __threadfence();
-    const size_t fi = (size_t)g.rank * g.slots + g.slot;
-    const unsigned v = *reinterpret_cast<volatile unsigned*>(g.flags[g.rank] + fi) + 1u;
-    for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + fi, v);  // the one system-scope release
+    for (int k = 0; k < ps.n; ++k) {  // the system-scope releases: the first one orders every store above, the rest are cheap
+        const size_t fi = (size_t)g.rank * g.slots + g.slot + k;
+        const unsigned v = *reinterpret_cast<volatile unsigned*>(g.flags[g.rank] + fi) + 1u;
+        for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + fi, v);
+    }
 }
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
@@ -1114,23 +1120,38 @@ TRTX_API int trtx_yolo_decode_nms_gather_enqueue(const trtx_yolo_params* p, cons
     return yolo_nms_tiles(p, q, batch, ya, L, compact_out_dev, keep_index_dev, workspace_dev, st, gather);
 }
 
-TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream) {
+TRTX_API int trtx_gather_wait_many_enqueue(const trtx_gather* gather, int nslots, trtx_stream_t stream) {
     NmsArgs::Gather g;
     int rc = fill_gather(gather, &g);
     if (rc || !gather) return rc ? rc : TRTX_ERR_INVALID;
-    gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(g);
+    if (nslots < 1 || nslots > 8 || gather->slot + nslots > gather->slots) return TRTX_ERR_INVALID;
+    gather_wait_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(g, nslots);
     return check_launch();
 }
+TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream) {
+    return trtx_gather_wait_many_enqueue(gather, 1, stream);
+}
 
-TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,
-                                      int extra_floats, trtx_stream_t stream) {
+TRTX_API int trtx_gather_push_many_enqueue(const trtx_gather* gather, const float* const* compact_outs_dev, int n, int batch, int max_det,
+                                           int extra_floats, trtx_stream_t stream) {
     NmsArgs::Gather g;
     int rc = fill_gather(gather, &g);
-    if (rc || !gather || !compact_out_dev || batch <= 0 || max_det <= 0 || extra_floats < 0) return rc ? rc : TRTX_ERR_INVALID;
+    if (rc || !gather || !compact_outs_dev || batch <= 0 || max_det <= 0 || extra_floats < 0) return rc ? rc : TRTX_ERR_INVALID;
+    if (n < 1 || n > 8 || gather->slot + n > gather->slots) return TRTX_ERR_INVALID;
+    PushSrc ps{};
+    ps.n = n;
+    for (int k = 0; k < n; ++k) {
+        if (!compact_outs_dev[k]) return TRTX_ERR_INVALID;
+        ps.src[k] = compact_outs_dev[k];
+    }
     const int R = 7 + extra_floats;
-    gather_push_kernel<<<batch < 8 ? batch : 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, compact_out_dev, batch, 1 + max_det * R,
-                                                                                          max_det, R);
+    const int work = n * batch;
+    gather_push_kernel<<<work < 8 ? work : 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, ps, batch, 1 + max_det * R, max_det, R);
     return check_launch();
+}
+TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,
+                                      int extra_floats, trtx_stream_t stream) {
+    return trtx_gather_push_many_enqueue(gather, &compact_out_dev, 1, batch, max_det, extra_floats, stream);
 }
 
 // ---- peer memory for the gather: cudaMalloc + CUDA IPC (one process per GPU on one NVSwitch node) ----

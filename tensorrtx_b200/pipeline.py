@@ -323,11 +323,21 @@ class PeerGather:
         L.check(self._lib.trtx_gather_push_enqueue(C.byref(self._descs[slot]), _ptr(local_out), int(local_out.shape[0]), int(max_det),
                                                    int(extra_floats), _stream(stream)), "trtx_gather_push_enqueue")
 
-    def wait(self, slot: int, stream=None) -> None:
+    def wait(self, slot: int, stream=None, n: int = 1) -> None:
+        """Wait for slots slot .. slot+n-1 (one launch)."""
         import ctypes as C
 
         from .plugins import _stream
-        L.check(self._lib.trtx_gather_wait_enqueue(C.byref(self._descs[slot]), _stream(stream)), "trtx_gather_wait_enqueue")
+        L.check(self._lib.trtx_gather_wait_many_enqueue(C.byref(self._descs[slot]), int(n), _stream(stream)), "trtx_gather_wait_many_enqueue")
+
+    def push_many(self, local_outs, slot: int, max_det: int, extra_floats: int = 0, stream=None) -> None:
+        """Publish len(local_outs) local outputs into slots slot .. in ONE launch (one system-scope release for the round)."""
+        import ctypes as C
+
+        from .plugins import _ptr, _stream
+        ptrs = L.ptr_array([_ptr(t) for t in local_outs])
+        L.check(self._lib.trtx_gather_push_many_enqueue(C.byref(self._descs[slot]), ptrs, len(local_outs), int(local_outs[0].shape[0]),
+                                                        int(max_det), int(extra_floats), _stream(stream)), "trtx_gather_push_many_enqueue")
 
     def close(self) -> None:
         for p in self._opened:

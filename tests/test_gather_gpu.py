@@ -64,6 +64,29 @@ def test_peer_gather_protocol_two_logical_ranks(oracle, dev):
                     res, _ = oracle.nms(0, ref[b], K, 90, 0.5, 0.45)
                     assert n == len(res) and n > 3 and got[b, 0] == n
                     assert np.array_equal(got[b, 1:1 + n * 7], loc[b, 1:1 + n * 7])   # same bytes as the local output
+    # a round of two steps published by ONE kernel into slots 2, 3 and awaited by ONE kernel (trtx_gather_push_many / wait_many)
+    outs2 = []
+    for r in range(W):
+        with torch.cuda.stream(streams[r]):
+            pair = []
+            for k in range(2):
+                hd = [torch.from_numpy(h).to(dev) for h in synth.yolov8_heads(B, seed=990 + 2 * r + k, n_obj=10)]
+                f = P.FusedYoloDecodeNms(plug, B, 0.5, 0.45, device=dev)
+                pair.append(f.enqueue(B, hd)[0])
+            g = desc(r, 2)
+            ptrs = L.ptr_array([t.data_ptr() for t in pair])
+            L.check(lib.trtx_gather_push_many_enqueue(C.byref(g), ptrs, 2, B, K, 0, streams[r].cuda_stream), "push_many")
+            L.check(lib.trtx_gather_wait_many_enqueue(C.byref(g), 2, streams[r].cuda_stream), "wait_many")
+            outs2.append(pair)
+    torch.cuda.synchronize()
+    for r in range(W):
+        for k in range(2):
+            loc = outs2[r][k].cpu().numpy()
+            for p in range(W):
+                got = outs[p][2 + k, r * B:(r + 1) * B].cpu().numpy()
+                for b in range(B):
+                    n = int(loc[b, 0])
+                    assert got[b, 0] == n and n > 2 and np.array_equal(got[b, 1:1 + n * 7], loc[b, 1:1 + n * 7])
     # a rank whose peer never publishes gives up instead of hanging the GPU: error flag set
     f2 = torch.zeros((2, SLOTS), dtype=torch.int32, device=dev)
     f2[0, 1] = 5                                            # own counter of slot 1 is ahead of the silent peer's
