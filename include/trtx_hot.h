@@ -347,6 +347,15 @@ TRTX_API int trtx_scale_mask_enqueue(const float* masks_dev, int n, int net_w, i
 TRTX_API int trtx_roi_align(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
                             float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
                             int feature_w, trtx_stream_t stream);
+/* The same with the kernel chosen by the caller (both are bit-identical to the reference's roiAlign):
+ * TRTX_ROI_WINDOW (what trtx_roi_align uses) stages each proposal's feature-map window in shared memory and takes the
+ * bilinear taps from there; TRTX_ROI_DIRECT takes every tap from global memory (the round-1 kernel; also what
+ * TRTX_ROI_WINDOW falls back to when a channel of the map does not fit the window buffer, feature_h * feature_w > 20480). */
+#define TRTX_ROI_WINDOW 0
+#define TRTX_ROI_DIRECT 1
+TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
+                               float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
+                               int feature_w, int mode, trtx_stream_t stream);
 /* indices_dev [batch, detections_per_im] class index as float; masks_dev [batch, detections_per_im, num_classes, S, S];
  * out_dev [batch, detections_per_im, S, S] = sigmoid of the predicted class' mask (rows with an index outside
  * [0, num_classes) are left untouched, as in the reference). */

@@ -55,14 +55,15 @@ __device__ __forceinline__ AxisTap axis_tap(float y, int size) {
     return t;
 }
 
-__global__ void __launch_bounds__(256) roi_align_kernel(const __grid_constant__ RoiArgs a) {
-    __shared__ AxisTap s_y[kRoiMaxTable], s_x[kRoiMaxTable];
-    const int n = blockIdx.x, b = blockIdx.z;
-    const int c_begin = blockIdx.y * kRoiChannelsPerCta, c_end = min(a.C, c_begin + kRoiChannelsPerCta);
-    const int P = a.P, PP = P * P;
-    const float4 roi = a.rois[(size_t)b * a.N + n];
+// Geometry of one proposal (RoiAlign.cu:104-127 -- "Do not using rounding; this implementation detail is critical")
+struct RoiGeom {
+    float start_w, start_h, bin_h, bin_w, count;
+    int grid_h, grid_w;
+    bool tabled;
+};
 
-    // RoiAlign.cu:104-127 -- "Do not using rounding; this implementation detail is critical"
+__device__ __forceinline__ RoiGeom roi_geom(const RoiArgs& a, const float4 roi) {
+    RoiGeom q;
     float roi_offset = 0.5f;
     float roi_start_w = roi.x * a.spatial_scale - roi_offset;
     float roi_start_h = roi.y * a.spatial_scale - roi_offset;
@@ -70,29 +71,27 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const __grid_constant__ 
     float roi_end_h = roi.w * a.spatial_scale - roi_offset;
     float roi_width = roi_end_w - roi_start_w;
     float roi_height = roi_end_h - roi_start_h;
-    float bin_size_h = static_cast<float>(roi_height) / static_cast<float>(P);
-    float bin_size_w = static_cast<float>(roi_width) / static_cast<float>(P);
-    int roi_bin_grid_h = (a.sampling_ratio > 0) ? a.sampling_ratio : ceil(roi_height / P);
-    int roi_bin_grid_w = (a.sampling_ratio > 0) ? a.sampling_ratio : ceil(roi_width / P);
-    const float count = roi_bin_grid_h * roi_bin_grid_w;
-    const bool tabled = roi_bin_grid_h > 0 && roi_bin_grid_w > 0 && P * roi_bin_grid_h <= kRoiMaxTable &&
-                        P * roi_bin_grid_w <= kRoiMaxTable;
-    if (tabled) {
-        for (int i = threadIdx.x; i < P * roi_bin_grid_h; i += blockDim.x) {
-            const int ph = i / roi_bin_grid_h, iy = i - ph * roi_bin_grid_h;
-            const float y = roi_start_h + ph * bin_size_h +
-                            static_cast<float>(iy + .5f) * bin_size_h / static_cast<float>(roi_bin_grid_h);  // :133-135
-            s_y[i] = axis_tap(y, a.H);
-        }
-        for (int i = threadIdx.x; i < P * roi_bin_grid_w; i += blockDim.x) {
-            const int pw = i / roi_bin_grid_w, ix = i - pw * roi_bin_grid_w;
-            const float x = roi_start_w + pw * bin_size_w +
-                            static_cast<float>(ix + .5f) * bin_size_w / static_cast<float>(roi_bin_grid_w);  // :137-139
-            s_x[i] = axis_tap(x, a.W);
-        }
-    }
-    __syncthreads();
+    q.start_w = roi_start_w;
+    q.start_h = roi_start_h;
+    q.bin_h = static_cast<float>(roi_height) / static_cast<float>(a.P);
+    q.bin_w = static_cast<float>(roi_width) / static_cast<float>(a.P);
+    q.grid_h = (a.sampling_ratio > 0) ? a.sampling_ratio : ceil(roi_height / a.P);
+    q.grid_w = (a.sampling_ratio > 0) ? a.sampling_ratio : ceil(roi_width / a.P);
+    q.count = q.grid_h * q.grid_w;
+    q.tabled = q.grid_h > 0 && q.grid_w > 0 && a.P * q.grid_h <= kRoiMaxTable && a.P * q.grid_w <= kRoiMaxTable;
+    return q;
+}
 
+// the sample coordinates of one axis (RoiAlign.cu:133-139)
+__device__ __forceinline__ float roi_sample(float start, float bin, int p, int i, int grid) {
+    return start + p * bin + static_cast<float>(i + .5f) * bin / static_cast<float>(grid);
+}
+
+// Direct form: taps straight from the (L2-resident) feature map.  One thread per output bin, CU channels per pass.
+// `off_y(t)` / `off_x(t)`: how a tabulated tap turns into an offset -- absolute rows of the feature map here.
+__device__ __forceinline__ void roi_align_direct(const RoiArgs& a, const RoiGeom& q, const AxisTap* s_y, const AxisTap* s_x, int n, int b,
+                                                 int c_begin, int c_end) {
+    const int P = a.P, PP = P * P;
     // thread = (bin, channel lane): bins are the fast index, so a warp writes consecutive floats
     const int nsub = max(1, (int)blockDim.x / PP);
     const int bin = threadIdx.x % PP, csub = threadIdx.x / PP;
@@ -108,24 +107,11 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const __grid_constant__ 
         for (int k = 0; k < CU; ++k) output_val[k] = 0.f;
         const float* fm = fb + (size_t)c0 * plane;
         const int nch = min(CU, c_end - c0);
-        for (int iy = 0; iy < roi_bin_grid_h; iy++) {
-            AxisTap ty;
-            if (tabled) {
-                ty = s_y[ph * roi_bin_grid_h + iy];
-            } else {  // degenerate or huge sampling grids: coordinates on the fly, as the reference does
-                const float y = roi_start_h + ph * bin_size_h +
-                                static_cast<float>(iy + .5f) * bin_size_h / static_cast<float>(roi_bin_grid_h);
-                ty = axis_tap(y, a.H);
-            }
-            for (int ix = 0; ix < roi_bin_grid_w; ix++) {
-                AxisTap tx;
-                if (tabled) {
-                    tx = s_x[pw * roi_bin_grid_w + ix];
-                } else {
-                    const float x = roi_start_w + pw * bin_size_w +
-                                    static_cast<float>(ix + .5f) * bin_size_w / static_cast<float>(roi_bin_grid_w);
-                    tx = axis_tap(x, a.W);
-                }
+        for (int iy = 0; iy < q.grid_h; iy++) {
+            // degenerate or huge sampling grids: coordinates on the fly, as the reference does
+            const AxisTap ty = q.tabled ? s_y[ph * q.grid_h + iy] : axis_tap(roi_sample(q.start_h, q.bin_h, ph, iy, q.grid_h), a.H);
+            for (int ix = 0; ix < q.grid_w; ix++) {
+                const AxisTap tx = q.tabled ? s_x[pw * q.grid_w + ix] : axis_tap(roi_sample(q.start_w, q.bin_w, pw, ix, q.grid_w), a.W);
                 if (!(ty.valid && tx.valid)) continue;  // bilinear_interpolate returns 0: `output_val += 0`
                 const float ly = ty.l, hy = ty.h, lx = tx.l, hx = tx.h;
                 const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
@@ -144,7 +130,223 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const __grid_constant__ 
         }
 #pragma unroll
         for (int k = 0; k < CU; ++k)
-            if (k < nch) ob[(size_t)(c0 + k) * PP] = output_val[k] / count;  // :147 (NaN for a degenerate proposal, like the reference)
+            if (k < nch) ob[(size_t)(c0 + k) * PP] = output_val[k] / q.count;  // :147 (NaN for a degenerate proposal, like the reference)
+    }
+}
+
+__device__ __forceinline__ void roi_build_tables(const RoiArgs& a, const RoiGeom& q, AxisTap* s_y, AxisTap* s_x) {
+    for (int i = threadIdx.x; i < a.P * q.grid_h; i += blockDim.x) {
+        const int ph = i / q.grid_h, iy = i - ph * q.grid_h;
+        s_y[i] = axis_tap(roi_sample(q.start_h, q.bin_h, ph, iy, q.grid_h), a.H);
+    }
+    for (int i = threadIdx.x; i < a.P * q.grid_w; i += blockDim.x) {
+        const int pw = i / q.grid_w, ix = i - pw * q.grid_w;
+        s_x[i] = axis_tap(roi_sample(q.start_w, q.bin_w, pw, ix, q.grid_w), a.W);
+    }
+}
+
+// round-1 kernel: every tap is a global load (kept as `mode = 1` of trtx_roi_align_ex and for proposals the window
+// kernel does not tabulate)
+__global__ void __launch_bounds__(256) roi_align_kernel(const __grid_constant__ RoiArgs a) {
+    __shared__ AxisTap s_y[kRoiMaxTable], s_x[kRoiMaxTable];
+    const int n = blockIdx.x, b = blockIdx.z;
+    const int c_begin = blockIdx.y * kRoiChannelsPerCta, c_end = min(a.C, c_begin + kRoiChannelsPerCta);
+    const RoiGeom q = roi_geom(a, a.rois[(size_t)b * a.N + n]);
+    if (q.tabled) roi_build_tables(a, q, s_y, s_x);
+    __syncthreads();
+    roi_align_direct(a, q, s_y, s_x, n, b, c_begin, c_end);
+}
+
+// --------------------------------------------------------------------------------------------
+// Window kernel (round 2, default): the taps of a proposal touch only the feature-map window
+// [y0..y1] x [x0..x1] that its sample coordinates span -- 169 cells for a 13x13-cell proposal against 196 output bins that
+// each read 4..16 of them.  The CTA (one proposal, 64 channels) copies that window ONCE into shared memory, CHANNEL-MINOR
+// (cell-major rows of `pitch` floats), with cp.async (4 bytes per element, every copy of a pass in flight together: the L2
+// round trip is paid once per pass instead of once per dependent tap), and then takes every tap from shared memory: one
+// LDS.128 fetches a tap for FOUR channels, the offsets and weights of a sample are read once per 16 channels.  A thread
+// owns one output bin; per channel the samples are accumulated in the reference's order with the reference's expression,
+// so the results stay bit-identical (test_roi_align_and_mask_rcnn_inference_vs_reference_functions).
+//   fill: a warp item = 4 channels x 8 consecutive cells of a window row: four 32-byte global segments, 32 distinct banks;
+//   taps: pitch = channels + 4 floats (pitch / 4 odd), so the 8 lanes of a quarter-warp -- neighbouring bins, i.e.
+//         neighbouring or identical cells -- hit distinct 16-byte bank groups or broadcast.
+// Shared memory: 2 tables (8 KB) + kRoiWindowFloats floats of window; 2 CTAs per SM.
+// --------------------------------------------------------------------------------------------
+constexpr int kRoiWindowFloats = 20480;  // 80 KB
+constexpr int kRoiWindowThreads = 224;   // 7 warps: 196 bins of a 14x14 pooler + 28 idle lanes in the tap phase
+constexpr int kRoiCU = 16;               // channels per thread and tap round
+
+// one axis of a sample, window-relative: BYTE offsets of the low / high row (or column) in the window, the two fractions;
+// lo < 0: the reference's bilinear_interpolate returns 0 for this coordinate
+struct __align__(16) WinTap {
+    int lo, hi;
+    float l, h;
+};
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// exact n / d for n * d < 2^32, m = ceil(2^32 / d) (d = 1 has no 32-bit multiplier)
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned m, unsigned d) { return d == 1 ? n : __umulhi(n, m); }
+__device__ __forceinline__ unsigned fast_div_magic(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
+
+// taps of one bin for channels k0 .. k0 + kRoiCU - 1 of the pass (FULL: all of them exist)
+template <bool FULL>
+__device__ __forceinline__ void roi_window_taps(const char* win, const WinTap* ty_row, const WinTap* tx_row, int grid_h, int grid_w, int nch,
+                                                float count, float* ob, int PP) {
+    float output_val[kRoiCU];
+#pragma unroll
+    for (int k = 0; k < kRoiCU; ++k) output_val[k] = 0.f;
+    for (int iy = 0; iy < grid_h; iy++) {
+        const WinTap ty = ty_row[iy];
+        if (ty.lo < 0) continue;  // bilinear_interpolate returns 0: `output_val += 0`
+        for (int ix = 0; ix < grid_w; ix++) {
+            const WinTap tx = tx_row[ix];
+            if (tx.lo < 0) continue;
+            const float ly = ty.l, hy = ty.h, lx = tx.l, hx = tx.h;
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const char *p1 = win + (ty.lo + tx.lo), *p2 = win + (ty.lo + tx.hi), *p3 = win + (ty.hi + tx.lo), *p4 = win + (ty.hi + tx.hi);
+#pragma unroll
+            for (int g = 0; g < kRoiCU / 4; ++g) {
+                if (FULL || 4 * g < nch) {
+                    const float4 a1 = *reinterpret_cast<const float4*>(p1 + 16 * g), a2 = *reinterpret_cast<const float4*>(p2 + 16 * g);
+                    const float4 a3 = *reinterpret_cast<const float4*>(p3 + 16 * g), a4 = *reinterpret_cast<const float4*>(p4 + 16 * g);
+                    {
+                        const float v1 = a1.x, v2 = a2.x, v3 = a3.x, v4 = a4.x;
+                        const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;  // :76
+                        output_val[4 * g + 0] += val;
+                    }
+                    {
+                        const float v1 = a1.y, v2 = a2.y, v3 = a3.y, v4 = a4.y;
+                        const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+                        output_val[4 * g + 1] += val;
+                    }
+                    {
+                        const float v1 = a1.z, v2 = a2.z, v3 = a3.z, v4 = a4.z;
+                        const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+                        output_val[4 * g + 2] += val;
+                    }
+                    {
+                        const float v1 = a1.w, v2 = a2.w, v3 = a3.w, v4 = a4.w;
+                        const float val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+                        output_val[4 * g + 3] += val;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kRoiCU; ++k)
+        if (FULL || k < nch) ob[(size_t)k * PP] = output_val[k] / count;  // :147
+}
+
+__global__ void __launch_bounds__(kRoiWindowThreads, 2) roi_align_window_kernel(const __grid_constant__ RoiArgs a) {
+    __shared__ AxisTap s_y[kRoiMaxTable], s_x[kRoiMaxTable];   // 10 KB; rewritten in place as WinTap (16 of the 20 bytes)
+    __shared__ int s_box[4];  // y0, y1, x0, x1 of the window (over the valid taps)
+    extern __shared__ __align__(16) float s_win[];
+    const int n = blockIdx.x, b = blockIdx.z;
+    const int c_begin = blockIdx.y * kRoiChannelsPerCta, c_end = min(a.C, c_begin + kRoiChannelsPerCta);
+    const int P = a.P, PP = P * P;
+    const RoiGeom q = roi_geom(a, a.rois[(size_t)b * a.N + n]);
+    if (!q.tabled) {  // block-uniform
+        roi_align_direct(a, q, s_y, s_x, n, b, c_begin, c_end);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        s_box[0] = a.H;
+        s_box[1] = -1;
+        s_box[2] = a.W;
+        s_box[3] = -1;
+    }
+    roi_build_tables(a, q, s_y, s_x);
+    __syncthreads();
+    const int ny = P * q.grid_h, nx = P * q.grid_w;
+    {   // window = hull of the valid taps (a handful of shared-memory atomics per CTA)
+        int lo = a.H, hi = -1;
+        for (int i = threadIdx.x; i < ny; i += blockDim.x)
+            if (s_y[i].valid) lo = min(lo, s_y[i].low), hi = max(hi, s_y[i].high);
+        if (hi >= 0) atomicMin(&s_box[0], lo), atomicMax(&s_box[1], hi);
+        lo = a.W, hi = -1;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x)
+            if (s_x[i].valid) lo = min(lo, s_x[i].low), hi = max(hi, s_x[i].high);
+        if (hi >= 0) atomicMin(&s_box[2], lo), atomicMax(&s_box[3], hi);
+    }
+    __syncthreads();
+    const int y0 = s_box[0], y1 = s_box[1], x0 = s_box[2], x1 = s_box[3];
+    const int bin = threadIdx.x;
+    const bool has_bin = bin < PP;
+    const int ph = has_bin ? bin / P : 0, pw = has_bin ? bin - ph * P : 0;
+    float* ob = a.out + (((size_t)b * a.N + n) * a.C) * PP + bin;
+    if (y1 < 0 || x1 < 0) {  // every sample is outside the map: the reference adds zeros
+        if (has_bin)
+            for (int c = c_begin; c < c_end; ++c) ob[(size_t)c * PP] = 0.f / q.count;
+        return;
+    }
+    const int wh = y1 - y0 + 1, ww = x1 - x0 + 1, cells = wh * ww;
+    // channels per pass: as many as fit, a multiple of 8 (pitch = channels + 4 floats, pitch / 4 odd) -- or 4 with pitch 4
+    // for windows of more than 20480 / 12 cells (a whole 50 x 67 map: 3350 cells)
+    int cpass = min(kRoiChannelsPerCta, (kRoiWindowFloats / cells - 4) & ~7);
+    int pitch = cpass + 4;
+    if (cpass < 8) cpass = 4, pitch = 4;
+    // tables become window-relative byte offsets (AxisTap -> WinTap in place: each thread converts its own entries)
+    WinTap* w_y = reinterpret_cast<WinTap*>(s_y);
+    WinTap* w_x = reinterpret_cast<WinTap*>(s_x);
+    {
+        AxisTap ty[2], tx[2];  // P * grid <= 256 entries per axis, 224 threads: at most 2 each
+        int k = 0;
+        for (int i = threadIdx.x; i < ny; i += blockDim.x) ty[k++] = s_y[i];
+        k = 0;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) tx[k++] = s_x[i];
+        __syncthreads();
+        k = 0;
+        for (int i = threadIdx.x; i < ny; i += blockDim.x, ++k) {
+            WinTap t;
+            t.lo = ty[k].valid ? (ty[k].low - y0) * ww * pitch * 4 : -1;
+            t.hi = (ty[k].high - y0) * ww * pitch * 4;
+            t.l = ty[k].l, t.h = ty[k].h;
+            w_y[i] = t;
+        }
+        k = 0;
+        for (int i = threadIdx.x; i < nx; i += blockDim.x, ++k) {
+            WinTap t;
+            t.lo = tx[k].valid ? (tx[k].low - x0) * pitch * 4 : -1;
+            t.hi = (tx[k].high - x0) * pitch * 4;
+            t.l = tx[k].l, t.h = tx[k].h;
+            w_x[i] = t;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nxc = (ww + 7) >> 3, per_quad = wh * nxc;  // fill items per channel quad
+    const unsigned m_quad = fast_div_magic(per_quad), m_nxc = fast_div_magic(nxc);
+    const size_t plane = (size_t)a.H * a.W;
+    const float* fwin = a.feat + (size_t)b * a.C * plane + (size_t)y0 * a.W + x0;
+    const int fx = lane & 7, fc = lane >> 3;
+    for (int cb = c_begin; cb < c_end; cb += cpass) {
+        const int nc = min(cpass, c_end - cb);
+        __syncthreads();  // tables rewritten (first pass) / previous pass' taps done
+        const float* fsrc = fwin + (size_t)(cb + fc) * plane + fx;
+        float* fdst = s_win + fx * pitch + fc;
+        const int items = ((nc + 3) >> 2) * per_quad;
+        for (int it = warp; it < items; it += kRoiWindowThreads / 32) {
+            const unsigned cq = fast_div(it, m_quad, per_quad), r = it - cq * per_quad;
+            const unsigned y = fast_div(r, m_nxc, nxc), xc = r - y * nxc;
+            if ((int)(cq * 4) + fc < nc && (int)(xc * 8) + fx < ww)
+                cp_async_4(fdst + (size_t)((y * ww + xc * 8) * pitch + cq * 4), fsrc + (size_t)(cq * 4) * plane + y * a.W + xc * 8);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (!has_bin) continue;
+        for (int k0 = 0; k0 < nc; k0 += kRoiCU) {
+            const int nch = nc - k0;
+            const char* win = reinterpret_cast<const char*>(s_win + k0);
+            float* o = ob + (size_t)(cb + k0) * PP;
+            if (nch >= kRoiCU)
+                roi_window_taps<true>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, kRoiCU, q.count, o, PP);
+            else
+                roi_window_taps<false>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, nch, q.count, o, PP);
+        }
     }
 }
 
@@ -168,13 +370,14 @@ using namespace trtx;
 
 extern "C" {
 
-TRTX_API int trtx_roi_align(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
-                            float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
-                            int feature_w, trtx_stream_t stream) {
+TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
+                               float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
+                               int feature_w, int mode, trtx_stream_t stream) {
     if (batch <= 0 || !rois_dev || !features_dev || !out_dev) return TRTX_ERR_INVALID;
     if (pooler_resolution <= 0 || num_proposals <= 0 || out_channels <= 0 || feature_h <= 0 || feature_w <= 0) return TRTX_ERR_INVALID;
     if (pooler_resolution > kRoiMaxPooled || pooler_resolution * pooler_resolution > 256) return TRTX_ERR_UNSUPPORTED;
     if (batch > 65535) return TRTX_ERR_UNSUPPORTED;
+    if (mode != TRTX_ROI_WINDOW && mode != TRTX_ROI_DIRECT) return TRTX_ERR_INVALID;
     RoiArgs a;
     a.rois = reinterpret_cast<const float4*>(rois_dev);
     a.feat = features_dev;
@@ -188,8 +391,28 @@ TRTX_API int trtx_roi_align(int batch, const float* rois_dev, const float* featu
     a.spatial_scale = spatial_scale;
     dim3 grid(num_proposals, (out_channels + kRoiChannelsPerCta - 1) / kRoiChannelsPerCta, batch);
     if (grid.y > 65535) return TRTX_ERR_UNSUPPORTED;
-    roi_align_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    // the window kernel needs one bin per thread and a map whose single-channel window fits its shared memory
+    const bool window_ok = pooler_resolution * pooler_resolution <= kRoiWindowThreads &&
+                           (long long)feature_h * feature_w <= kRoiWindowFloats;
+    if (mode == TRTX_ROI_DIRECT || !window_ok) {
+        roi_align_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+        return check_launch();
+    }
+    constexpr int smem = kRoiWindowFloats * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(roi_align_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return TRTX_ERR_CUDA;
+    }
+    roi_align_window_kernel<<<grid, kRoiWindowThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch();
+}
+
+TRTX_API int trtx_roi_align(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,
+                            float spatial_scale, int sampling_ratio, int num_proposals, int out_channels, int feature_h,
+                            int feature_w, trtx_stream_t stream) {
+    return trtx_roi_align_ex(batch, rois_dev, features_dev, out_dev, pooler_resolution, spatial_scale, sampling_ratio, num_proposals,
+                             out_channels, feature_h, feature_w, TRTX_ROI_WINDOW, stream);
 }
 
 TRTX_API int trtx_mask_rcnn_inference(int batch, const float* indices_dev, const float* masks_dev, float* out_dev,

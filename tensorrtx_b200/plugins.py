@@ -847,10 +847,15 @@ class RoiAlignPlugin:
     def getWorkspaceSize(self, maxBatchSize: int) -> int:
         return 0
 
-    def enqueue(self, batchSize, inputs, outputs, workspace=None, stream=None) -> int:
-        return int(self._lib.trtx_roi_align(batchSize, _ptr(inputs[0]), _ptr(inputs[1]), _ptr(outputs[0]), self._pooler_resolution,
-                                            self._spatial_scale, self._sampling_ratio, self._num_proposals, self._out_channels,
-                                            self._feature_h, self._feature_w, _stream(stream)))
+    def enqueue(self, batchSize, inputs, outputs, workspace=None, stream=None, mode: int | None = None) -> int:
+        """mode: None = trtx_roi_align (the window kernel); L.ROI_WINDOW / L.ROI_DIRECT pick the kernel (trtx_roi_align_ex)."""
+        if mode is None:
+            return int(self._lib.trtx_roi_align(batchSize, _ptr(inputs[0]), _ptr(inputs[1]), _ptr(outputs[0]), self._pooler_resolution,
+                                                self._spatial_scale, self._sampling_ratio, self._num_proposals, self._out_channels,
+                                                self._feature_h, self._feature_w, _stream(stream)))
+        return int(self._lib.trtx_roi_align_ex(batchSize, _ptr(inputs[0]), _ptr(inputs[1]), _ptr(outputs[0]), self._pooler_resolution,
+                                               self._spatial_scale, self._sampling_ratio, self._num_proposals, self._out_channels,
+                                               self._feature_h, self._feature_w, int(mode), _stream(stream)))
 
 
 class MaskRcnnInferencePlugin:

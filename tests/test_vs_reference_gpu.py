@@ -296,18 +296,25 @@ def test_roi_align_and_mask_rcnn_inference_vs_reference_functions(dev, oracle):
     wi = np.exp(rng.uniform(np.log(8), np.log(300), N)); hi = np.exp(rng.uniform(np.log(8), np.log(250), N))
     rois_in = np.stack([xi, yi, xi + wi, yi + hi], -1).astype(np.float32)
     fd, rd = torch.from_numpy(feat).to(dev), torch.from_numpy(rois).to(dev)
-    for sampling in (0, 2):
+    rois[1, 1] = [0, 0, 1067, 800]           # the whole map: the window of a channel is 50 x 67 cells (several passes)
+    rois[1, 2] = [5, 5, 9, 9]                # a fraction of one cell
+    rois[1, 3] = [1060, 790, 1200, 900]      # hangs over the bottom-right corner
+    for sampling in (0, 2, 5, 19):           # 19: 14 * 19 = 266 table entries per axis > 256 -> coordinates on the fly
         ref = torch.zeros((B, N, Cc, Pp, Pp), device=dev)
         assert lib.ref_roi_align(B, C.c_void_p(rd.data_ptr()), C.c_void_p(fd.data_ptr()), C.c_void_p(ref.data_ptr()), Pp,
                                  C.c_float(1 / 16), sampling, N, Cc, H, W) == 0
-        got = torch.full((B, N, Cc, Pp, Pp), -3.0, device=dev)
         plug = P.RoiAlignPlugin(Pp, 1 / 16, sampling, N, Cc)
         plug.configurePlugin([(N, 4), (Cc, H, W)])
-        assert plug.enqueue(B, [rd, fd], [got]) == 0
-        torch.cuda.synchronize()
-        r, g = ref.cpu().numpy(), got.cpu().numpy()
-        assert np.array_equal(np.isnan(r), np.isnan(g))
-        assert np.array_equal(r[~np.isnan(r)], g[~np.isnan(g)])          # bit-identical
+        r = ref.cpu().numpy()
+        for mode in (None, L.ROI_WINDOW, L.ROI_DIRECT):  # the shared-memory window kernel (default) and the round-1 kernel
+            got = torch.full((B, N, Cc, Pp, Pp), -3.0, device=dev)
+            assert plug.enqueue(B, [rd, fd], [got], mode=mode) == 0
+            torch.cuda.synchronize()
+            g = got.cpu().numpy()
+            assert np.array_equal(np.isnan(r), np.isnan(g)), (sampling, mode)
+            assert np.array_equal(r[~np.isnan(r)], g[~np.isnan(g)]), (sampling, mode)          # bit-identical
+        if sampling > 2:
+            continue
         # CPU restatement (no FMA contraction) on proposals inside the feature map: at the `x > width -> 0` border of
         # bilinear_interpolate a 1-ulp difference in a sample coordinate flips a whole tap, which only the same-compiler
         # comparison above can pin
