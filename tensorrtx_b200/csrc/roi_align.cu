@@ -186,16 +186,16 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_4s(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// exact n / d for n * d < 2^32, m = ceil(2^32 / d) (d = 1 has no 32-bit multiplier)
-__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned m, unsigned d) { return d == 1 ? n : __umulhi(n, m); }
-__device__ __forceinline__ unsigned fast_div_magic(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
-
-// taps of one bin for channels k0 .. k0 + kRoiCU - 1 of the pass (FULL: all of them exist)
-template <bool FULL>
+// POW2: the sample count is a power of two (1 for proposals of up to 14 x 14 cells), so `output_val / count` (:147) equals
+// `output_val * (1 / count)` bit for bit (scaling by 2^-k is exact, or rounds the same real number once when it underflows)
+template <bool FULL, bool POW2>
 __device__ __forceinline__ void roi_window_taps(const char* win, const WinTap* ty_row, const WinTap* tx_row, int grid_h, int grid_w, int nch,
-                                                float count, float* ob, int PP) {
+                                                float count, float* ob, const int PP) {
     float output_val[kRoiCU];
 #pragma unroll
     for (int k = 0; k < kRoiCU; ++k) output_val[k] = 0.f;
@@ -239,16 +239,20 @@ __device__ __forceinline__ void roi_window_taps(const char* win, const WinTap* t
     }
 #pragma unroll
     for (int k = 0; k < kRoiCU; ++k)
-        if (FULL || k < nch) ob[(size_t)k * PP] = output_val[k] / count;  // :147
+        if (FULL || k < nch) ob[(size_t)k * PP] = POW2 ? output_val[k] * (1.0f / count) : output_val[k] / count;  // :147
 }
 
+// PT: the pooler resolution when it is the 14 of the Faster / Mask R-CNN heads (rcnn.cpp:44 POOLER_RESOLUTION) -- store offsets
+// become immediates and a thread row of 16 owns one row of 14 bins, so that the 8 lanes of a quarter-warp read neighbouring
+// cells of ONE window row (no shared-memory bank conflicts between bins of different rows); 0: any resolution, bin = thread.
+template <int PT>
 __global__ void __launch_bounds__(kRoiWindowThreads, 2) roi_align_window_kernel(const __grid_constant__ RoiArgs a) {
     __shared__ AxisTap s_y[kRoiMaxTable], s_x[kRoiMaxTable];   // 10 KB; rewritten in place as WinTap (16 of the 20 bytes)
     __shared__ int s_box[4];  // y0, y1, x0, x1 of the window (over the valid taps)
     extern __shared__ __align__(16) float s_win[];
     const int n = blockIdx.x, b = blockIdx.z;
     const int c_begin = blockIdx.y * kRoiChannelsPerCta, c_end = min(a.C, c_begin + kRoiChannelsPerCta);
-    const int P = a.P, PP = P * P;
+    const int P = PT ? PT : a.P, PP = P * P;
     const RoiGeom q = roi_geom(a, a.rois[(size_t)b * a.N + n]);
     if (!q.tabled) {  // block-uniform
         roi_align_direct(a, q, s_y, s_x, n, b, c_begin, c_end);
@@ -275,10 +279,17 @@ __global__ void __launch_bounds__(kRoiWindowThreads, 2) roi_align_window_kernel(
     }
     __syncthreads();
     const int y0 = s_box[0], y1 = s_box[1], x0 = s_box[2], x1 = s_box[3];
-    const int bin = threadIdx.x;
-    const bool has_bin = bin < PP;
-    const int ph = has_bin ? bin / P : 0, pw = has_bin ? bin - ph * P : 0;
-    float* ob = a.out + (((size_t)b * a.N + n) * a.C) * PP + bin;
+    int ph, pw;
+    bool has_bin;
+    if (PT) {  // 16 threads per row of bins (kRoiWindowThreads = 14 * 16)
+        ph = threadIdx.x >> 4, pw = threadIdx.x & 15;
+        has_bin = pw < PT;
+        if (!has_bin) pw = 0;
+    } else {
+        has_bin = (int)threadIdx.x < PP;
+        ph = has_bin ? threadIdx.x / P : 0, pw = has_bin ? threadIdx.x - ph * P : 0;
+    }
+    float* ob = a.out + (((size_t)b * a.N + n) * a.C) * PP + (ph * P + pw);
     if (y1 < 0 || x1 < 0) {  // every sample is outside the map: the reference adds zeros
         if (has_bin)
             for (int c = c_begin; c < c_end; ++c) ob[(size_t)c * PP] = 0.f / q.count;
@@ -293,47 +304,57 @@ __global__ void __launch_bounds__(kRoiWindowThreads, 2) roi_align_window_kernel(
     // tables become window-relative byte offsets (AxisTap -> WinTap in place: each thread converts its own entries)
     WinTap* w_y = reinterpret_cast<WinTap*>(s_y);
     WinTap* w_x = reinterpret_cast<WinTap*>(s_x);
-    {
-        AxisTap ty[2], tx[2];  // P * grid <= 256 entries per axis, 224 threads: at most 2 each
-        int k = 0;
-        for (int i = threadIdx.x; i < ny; i += blockDim.x) ty[k++] = s_y[i];
-        k = 0;
-        for (int i = threadIdx.x; i < nx; i += blockDim.x) tx[k++] = s_x[i];
+    {   // P * grid <= 256 entries per axis, 224 threads: at most 2 each (slots tid and tid + 224)
+        const int i0 = threadIdx.x, i1 = threadIdx.x + kRoiWindowThreads;
+        AxisTap ty0, ty1, tx0, tx1;
+        if (i0 < ny) ty0 = s_y[i0];
+        if (i1 < ny) ty1 = s_y[i1];
+        if (i0 < nx) tx0 = s_x[i0];
+        if (i1 < nx) tx1 = s_x[i1];
         __syncthreads();
-        k = 0;
-        for (int i = threadIdx.x; i < ny; i += blockDim.x, ++k) {
-            WinTap t;
-            t.lo = ty[k].valid ? (ty[k].low - y0) * ww * pitch * 4 : -1;
-            t.hi = (ty[k].high - y0) * ww * pitch * 4;
-            t.l = ty[k].l, t.h = ty[k].h;
-            w_y[i] = t;
-        }
-        k = 0;
-        for (int i = threadIdx.x; i < nx; i += blockDim.x, ++k) {
-            WinTap t;
-            t.lo = tx[k].valid ? (tx[k].low - x0) * pitch * 4 : -1;
-            t.hi = (tx[k].high - x0) * pitch * 4;
-            t.l = tx[k].l, t.h = tx[k].h;
-            w_x[i] = t;
-        }
+        const int ymul = ww * pitch * 4, xmul = pitch * 4;
+        auto conv = [](const AxisTap& t, int origin, int mul) {
+            WinTap w;
+            w.lo = t.valid ? (t.low - origin) * mul : -1;
+            w.hi = (t.high - origin) * mul;
+            w.l = t.l, w.h = t.h;
+            return w;
+        };
+        if (i0 < ny) w_y[i0] = conv(ty0, y0, ymul);
+        if (i1 < ny) w_y[i1] = conv(ty1, y0, ymul);
+        if (i0 < nx) w_x[i0] = conv(tx0, x0, xmul);
+        if (i1 < nx) w_x[i1] = conv(tx1, x0, xmul);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nxc = (ww + 7) >> 3, per_quad = wh * nxc;  // fill items per channel quad
-    const unsigned m_quad = fast_div_magic(per_quad), m_nxc = fast_div_magic(nxc);
     const size_t plane = (size_t)a.H * a.W;
+    const int plane4 = 4 * a.H * a.W;
+    const unsigned ngroups = (cells + 7) >> 3, m_ww = (65536 + ww - 1) / ww;
     const float* fwin = a.feat + (size_t)b * a.C * plane + (size_t)y0 * a.W + x0;
     const int fx = lane & 7, fc = lane >> 3;
+    const int nsamp = q.grid_h * q.grid_w;
+    const bool pow2 = (nsamp & (nsamp - 1)) == 0;
     for (int cb = c_begin; cb < c_end; cb += cpass) {
         const int nc = min(cpass, c_end - cb);
         __syncthreads();  // tables rewritten (first pass) / previous pass' taps done
-        const float* fsrc = fwin + (size_t)(cb + fc) * plane + fx;
-        float* fdst = s_win + fx * pitch + fc;
-        const int items = ((nc + 3) >> 2) * per_quad;
-        for (int it = warp; it < items; it += kRoiWindowThreads / 32) {
-            const unsigned cq = fast_div(it, m_quad, per_quad), r = it - cq * per_quad;
-            const unsigned y = fast_div(r, m_nxc, nxc), xc = r - y * nxc;
-            if ((int)(cq * 4) + fc < nc && (int)(xc * 8) + fx < ww)
-                cp_async_4(fdst + (size_t)((y * ww + xc * 8) * pitch + cq * 4), fsrc + (size_t)(cq * 4) * plane + y * a.W + xc * 8);
+        // Fill.  An item = (cell, channel % 4): the lanes of a warp are 4 channels x 8 consecutive cells (four 32-byte global
+        // segments unless the 8 cells wrap to the next window row; 32 distinct banks).  The item's source and destination are
+        // worked out once, then one cp.async per channel quad with both addresses stepping by constants.
+        const int nq = nc >> 2, ntail = nc & 3;
+        const float* fsrc = fwin + (size_t)(cb + fc) * plane;
+        const uint32_t fdst = (uint32_t)__cvta_generic_to_shared(s_win + fc);
+        for (unsigned e = threadIdx.x; e < ngroups * 32; e += kRoiWindowThreads) {
+            const unsigned cell = (e >> 5) * 8 + fx;
+            if (cell >= (unsigned)cells) continue;
+            const unsigned y = cells < 960 ? (cell * m_ww) >> 16 : cell / ww, x = cell - y * ww;  // exact: cell * (m_ww * ww - 2^16) < 2^16
+            const float* src = fsrc + (y * a.W + x);
+            uint32_t dst = fdst + cell * pitch * 4;
+#pragma unroll 4
+            for (int cq = 0; cq < nq; ++cq) {
+                cp_async_4s(dst, src);
+                dst += 16;
+                src += plane4;
+            }
+            if (fc < ntail) cp_async_4s(dst, src);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -342,10 +363,12 @@ __global__ void __launch_bounds__(kRoiWindowThreads, 2) roi_align_window_kernel(
             const int nch = nc - k0;
             const char* win = reinterpret_cast<const char*>(s_win + k0);
             float* o = ob + (size_t)(cb + k0) * PP;
-            if (nch >= kRoiCU)
-                roi_window_taps<true>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, kRoiCU, q.count, o, PP);
+            if (nch >= kRoiCU && pow2)
+                roi_window_taps<true, true>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, kRoiCU, q.count, o, PP);
+            else if (nch >= kRoiCU)
+                roi_window_taps<true, false>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, kRoiCU, q.count, o, PP);
             else
-                roi_window_taps<false>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, nch, q.count, o, PP);
+                roi_window_taps<false, false>(win, w_y + ph * q.grid_h, w_x + pw * q.grid_w, q.grid_h, q.grid_w, nch, q.count, o, PP);
         }
     }
 }
@@ -399,12 +422,13 @@ TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* fe
         return check_launch();
     }
     constexpr int smem = kRoiWindowFloats * (int)sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(roi_align_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
+    auto kernel = pooler_resolution == 14 ? roi_align_window_kernel<14> : roi_align_window_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
     if (e != cudaSuccess) {
         g_last_cuda_error = (int)e;
         return TRTX_ERR_CUDA;
     }
-    roi_align_window_kernel<<<grid, kRoiWindowThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    kernel<<<grid, kRoiWindowThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     return check_launch();
 }
 
