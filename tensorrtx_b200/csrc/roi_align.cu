@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const __grid_constant__ 
 //         neighbouring or identical cells -- hit distinct 16-byte bank groups or broadcast.
 // Shared memory: 2 tables (8 KB) + kRoiWindowFloats floats of window; 2 CTAs per SM.
 // --------------------------------------------------------------------------------------------
-constexpr int kRoiWindowFloats = 20480;  // 80 KB
+constexpr int kRoiWindowFloats = 16384;  // 64 KB
 constexpr int kRoiWindowThreads = 224;   // 7 warps: 196 bins of a 14x14 pooler + 28 idle lanes in the tap phase
-constexpr int kRoiCU = 16;               // channels per thread and tap round
+constexpr int kRoiCU = 8;               // channels per thread and tap round
 
 // one axis of a sample, window-relative: BYTE offsets of the low / high row (or column) in the window, the two fractions;
 // lo < 0: the reference's bilinear_interpolate returns 0 for this coordinate
@@ -246,7 +246,7 @@ __device__ __forceinline__ void roi_window_taps(const char* win, const WinTap* t
 // become immediates and a thread row of 16 owns one row of 14 bins, so that the 8 lanes of a quarter-warp read neighbouring
 // cells of ONE window row (no shared-memory bank conflicts between bins of different rows); 0: any resolution, bin = thread.
 template <int PT>
-__global__ void __launch_bounds__(kRoiWindowThreads, 2) roi_align_window_kernel(const __grid_constant__ RoiArgs a) {
+__global__ void __launch_bounds__(kRoiWindowThreads, 3) roi_align_window_kernel(const __grid_constant__ RoiArgs a) {
     __shared__ AxisTap s_y[kRoiMaxTable], s_x[kRoiMaxTable];   // 10 KB; rewritten in place as WinTap (16 of the 20 bytes)
     __shared__ int s_box[4];  // y0, y1, x0, x1 of the window (over the valid taps)
     extern __shared__ __align__(16) float s_win[];
