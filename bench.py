@@ -464,7 +464,7 @@ def scan_traffic():
         h = hashlib.sha256()
         for f in ("yolo_decode.cu", "yolo_layout.cuh", "common.cuh"):
             h.update((ROOT / "tensorrtx_b200" / "csrc" / f).read_bytes())
-        if j.get("src_sha256") == h.hexdigest():
+        if j.get("src_sha256") == h.hexdigest() and isinstance(j.get("dram_bytes_per_launch"), int) and isinstance(j.get("capture"), str):
             return j
     except Exception:
         pass

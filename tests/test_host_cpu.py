@@ -264,3 +264,23 @@ def test_abi_header_is_plain_c(tmp_path):
                         str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
 
+
+
+def test_committed_scan_traffic_summary_matches_what_bench_reads():
+    """profiles/scan_traffic.json feeds `roofline.traffic`: either it describes the CURRENT scan-kernel sources with the keys
+    bench.py prints, or bench.scan_traffic() returns None (never a KeyError in the middle of the JSON line)."""
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.scan_traffic()
+    f = ROOT / "profiles" / "scan_traffic.json"
+    if f.exists():
+        j = json.loads(f.read_text())
+        for k in ("dram_bytes_per_launch", "capture", "src_sha256"):
+            assert k in j, k
+    if t is not None:
+        assert 0.9 * 90316800 < t["dram_bytes_per_launch"] < 1.3 * 90316800      # every head byte read once (SURVEY 8d)
+        assert isinstance(t["capture"], str)
