@@ -591,17 +591,20 @@ def run_v8(args, rank, world, local_rank):
         # ---- N > 1: the gather.  Preferred: fused into the NMS kernel over NVLink peer memory (no collective kernel);
         #      fallback: one NCCL all-gather per step on a side stream as a parallel graph branch (round 1).
         peer, ring, gather_mode = None, GatherRing(world, BATCH, pipe.fused.out.shape[1], dev, slots=R), "none"
-        if world > 1 and not args.nccl_gather and not args.no_gather:
+        if (world > 1 or args.force_gather) and not args.nccl_gather and not args.no_gather:
             try:
-                peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=2 * max(1, min(args.graph_steps, R)))
+                gdepth = 1 if args.fused_gather else max(1, args.gather_depth)
+                peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=2 * gdepth * max(1, min(args.graph_steps, R)))
                 peer.fused = bool(args.fused_gather)
                 gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
-                               "one gather_push_kernel (8 CTAs: NVLink peer stores + one release) + one gather_wait_kernel per group of steps on a third graph chain, pipelined by one group; no collective kernel")
+                               f"one gather_copy_kernel (8 CTAs: plain NVLink peer stores) + one gather_publish_kernel (counters, relaxed stores; the kernel boundary orders them) + one gather_wait_kernel per group of steps on a third graph chain, no system-scope fence anywhere; a group is published one replay after it was computed and awaited {gdepth - 1} replay(s) later (ring of {2 * gdepth} slot groups); no collective kernel"
+                               + (" [EXPERIMENT: no in-graph waits]" if args.gather_no_wait else ""))
             except Exception as e:
                 print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
                 peer = None
             ok = torch.tensor([1 if peer is not None else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
             if int(ok.item()) == 0 and peer is not None:
                 peer.close()
                 peer = None
@@ -627,6 +630,10 @@ def run_v8(args, rank, world, local_rank):
                     ring.join()
             return f
 
+        NG = 2 * gdepth if peer is not None else 1   # slot groups of the gather ring (trtx_hot.h: a slot is reused 2*depth replays later)
+        # compact outputs, double-buffered by replay parity when the peer gather publishes them one replay later
+        outs2 = [[p.fused.out, torch.zeros_like(p.fused.out)] for p in pipes_dev] if peer is not None else None
+
         def make_group(j0, n, half=0):   # steps j0 .. j0+n-1 (input sets mod R) as two (N > 1: three) concurrent chains
             def f():
                 cur = torch.cuda.current_stream(dev)
@@ -634,18 +641,18 @@ def run_v8(args, rank, world, local_rank):
                 evp = {}
                 if peer is not None and not peer.fused:
                     # chain C: the gather, software-pipelined by one group -- this graph PUBLISHES the detections that the
-                    # previous replay of the group left in pipes_dev[j].fused.out (the first replay publishes an unused buffer,
-                    # flush_dev() publishes the last group) into the G slots of one half of the gathered buffers, then WAITS
-                    # for every rank's publish of those slots.  NMS(j) below overwrites the buffer push(j) reads, so it waits
-                    # for push(j) -- a local copy that ran long before; nothing on the scan -> NMS chain waits for a peer.
+                    # previous replay left in the OTHER half of the double-buffered compact outputs (outs2[j][1 - half % 2]; the
+                    # first replay publishes an unused buffer, flush_dev() publishes the last group) into slot group `half` of
+                    # the gathered buffers, then WAITS for every rank's publish of the group published gdepth - 1 replays ago.
+                    # The NMS of this replay writes outs2[j][half % 2], which the previous replay's publish had finished reading
+                    # before this graph started: nothing on the scan -> NMS chain waits for the gather, let alone for a peer
+                    # (with a single output buffer the NMS had to wait for the publish kernel: +2.7 us per step, r02e_gather.log).
                     chain_c.wait_stream(cur)
-                    with torch.cuda.stream(chain_c):   # ONE publish kernel and ONE wait kernel for the group's n slots
-                        peer.push_many([pipes_dev[j % R].fused.out for j in range(j0, j0 + n)], half * G, MAX_OUT, 0)
-                        ev = torch.cuda.Event()
-                        ev.record(chain_c)
-                        for j in range(j0, j0 + n):
-                            evp[j] = ev
-                        peer.wait(half * G, n=n)
+                    with torch.cuda.stream(chain_c):   # ONE copy + ONE publish kernel and ONE wait kernel for the group's n slots
+                        peer.push_many([outs2[j % R][1 - half % 2] for j in range(j0, j0 + n)], half * G, MAX_OUT, 0)
+                        if not args.gather_no_wait:   # the group published gdepth - 1 replays ago (gdepth = 1: the one just published)
+                            peer.wait(((half - (gdepth - 1)) % NG) * G, n=n)
+                        evp[0] = True
                 with torch.cuda.stream(chain_b):
                     for j in range(j0, j0 + n):
                         if peer is None:
@@ -654,8 +661,7 @@ def run_v8(args, rank, world, local_rank):
                             pipes_dev[j % R].decode_nms_gather(head_sets[j % R], peer, None, half * G + (j - j0), fused_gather=True)
                         else:
                             pipes_dev[j % R].fused.enqueue_scan(BATCH, head_sets[j % R])
-                            chain_b.wait_event(evp[j])
-                            pipes_dev[j % R].fused.enqueue_nms(BATCH, head_sets[j % R])
+                            pipes_dev[j % R].fused.enqueue_nms(BATCH, head_sets[j % R], out=outs2[j % R][half % 2])
                 for j in range(j0, j0 + n):
                     pipes_dev[j % R].pre.enqueue()
                 cur.wait_stream(chain_b)                     # join
@@ -677,7 +683,7 @@ def run_v8(args, rank, world, local_rank):
         elif G > 1 or peer is not None:
             assert R % G == 0 or G == R
             mode = "thread_local" if world > 1 else "global"
-            halves = 2 if peer is not None else 1   # the gather alternates between the two halves of its slots from replay to replay
+            halves = NG   # the gather walks round its ring of slot groups from replay to replay
             groups = [[pipe.capture(make_group(j0, G, h), mode) for h in range(halves)] for j0 in range(0, R, G)]
             singles = [pipe.capture(make_group(j, 1), mode) for j in range(R)] if peer is None else None
             dev_steps = [g.replay for g in singles] if singles else None
@@ -734,9 +740,10 @@ def run_v8(args, rank, world, local_rank):
                 ring.join()
             if peer is not None and not peer.fused and group_replay is not None:
                 # the publishes are pipelined by one group: deliver the detections of the last G steps inside the timed region
-                h = replays[0] % 2
-                peer.push_many([pipes_dev[j % R].fused.out for j in range(i_last - G + 1, i_last + 1)], h * G, MAX_OUT, 0)
-                peer.wait(h * G, n=G)
+                h = replays[0] % NG
+                peer.push_many([outs2[j % R][1 - h % 2] for j in range(i_last - G + 1, i_last + 1)], h * G, MAX_OUT, 0)
+                for d in range(NG if args.gather_no_wait else gdepth):   # everything still in flight
+                    peer.wait(((h - d) % NG) * G, n=G)
                 replays[0] += 1
 
         def step_e2e(i):
@@ -755,6 +762,34 @@ def run_v8(args, rank, world, local_rank):
         if peer is not None:   # whole groups only
             K, W = max(G, K // G * G), max(G, (W + G - 1) // G * G)
         ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev, run_many=run_dev)
+        gather_verified = None
+        if peer is not None and not peer.fused and group_replay is not None and not args.gather_no_wait:
+            # self-check outside the timed region: after one more group + flush, every rank's gathered buffer must hold every
+            # rank's detections of that group (count + live rows; rows past the count are not cleared on the peers) -- the
+            # reference copy travels through an NCCL all-gather of the local outputs
+            if world > 1:
+                dist.barrier()
+            run_dev(0, G)
+            flush_dev(G - 1)
+            torch.cuda.synchronize(dev)
+            h = (replays[0] - 1) % NG
+            cols = pipe.fused.out.shape[1]
+            gather_verified = True
+            for k in range(G):
+                local = outs2[k % R][1 - h % 2]
+                ref = torch.empty((world * BATCH, cols), dtype=local.dtype, device=dev)
+                if world > 1:
+                    dist.all_gather_into_tensor(ref, local.contiguous())
+                else:
+                    ref.copy_(local)
+                got = peer.result(h * G + k)
+                live = torch.arange(cols, device=dev)[None, :] < (1 + ref[:, :1].long() * 7)
+                if not (torch.equal(got[:, 0], ref[:, 0]) and torch.equal(got[live], ref[live]) and float(ref[:, 0].sum()) > 0):
+                    gather_verified = False
+            if world > 1:   # every rank's view
+                okt = torch.tensor([1 if gather_verified else 0], device=dev)
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                gather_verified = bool(int(okt.item()))
         ms_e2e, win_e2e, nb_e2e = timed_blocks(step_e2e, K, W, stream, dev, world, dist, (lambda i: ring.join()) if use_ring else None)
         gather_err = peer.error() if peer is not None else 0
 
@@ -766,7 +801,8 @@ def run_v8(args, rank, world, local_rank):
         nms_ms = time_kernel_loop(lambda i: fused.enqueue_nms(BATCH, head_sets[0]), n_iso, stream, dev)
         nms_gather_ms = None
         if peer is not None:   # scan + NMS with the peer stores + wait, ranks in lockstep
-            dist.barrier()
+            if world > 1:
+                dist.barrier()
             def _sg(i):
                 pipe.decode_nms_gather(head_sets[i % R], peer, None, i % (2 * G), fused_gather=peer.fused)
             nms_gather_ms = time_kernel_loop(_sg, n_iso, stream, dev)
@@ -820,7 +856,7 @@ def run_v8(args, rank, world, local_rank):
                 "overlap": (f"{G} steps per graph as two concurrent chains: letterbox launches || (scan -> NMS) launches" if G > 1 else
                             ("letterbox || (scan -> NMS) as parallel graph branches" if not args.no_overlap else "serial")),
                 "timed_blocks": {"device": nb_dev, "e2e": nb_e2e, "steps_per_block": K, "min_timed_s": MIN_TIMED_S},
-                "gather_timeouts": gather_err,
+                "gather_timeouts": gather_err, "gather_verified": gather_verified,
                 "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
         "clocks": sampler.summary(win_dev + win_e2e),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
@@ -979,6 +1015,9 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=4, help="consecutive steps captured into one CUDA graph (two concurrent chains)")
     ap.add_argument("--nccl-gather", action="store_true", help="N > 1: NCCL all-gather instead of the gather fused into nms_kernel")
     ap.add_argument("--no-gather", action="store_true", help="experiment: N > 1 without any gather (upper bound of the scaling)")
+    ap.add_argument("--gather-depth", type=int, default=1, help="N > 1: replays between the publish of a group and the wait for it, plus one (1 = wait in the same replay); ring of 2*depth slot groups")
+    ap.add_argument("--force-gather", action="store_true", help="experiment: run the peer gather's publish + wait kernels at N = 1 too (this rank is its only peer)")
+    ap.add_argument("--gather-no-wait", action="store_true", help="experiment: N > 1, publish only; the waits happen once at the end of a timed block (no flow control)")
     ap.add_argument("--fused-gather", action="store_true", help="N > 1: gather stores from inside nms_kernel + one-warp wait kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -91,6 +91,14 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ---- IoU variants -------------------------------------------------------------------------
 // Host IoUs restated by to_corners / box_area / overlaps below:
@@ -882,71 +890,86 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
             __threadfence();
             if (atomicAdd(&a.g.ctrl[1], 1u) == gridDim.x - 1) {  // last CTA of the launch: publish
                 a.g.ctrl[1] = 0u;
-                __threadfence();
+                __threadfence_system();  // the ONE system-scope fence of the launch; the counters follow as relaxed stores
                 const size_t fi = (size_t)a.g.rank * a.g.slots + a.g.slot;  // this rank's publish counter of the slot, on every rank
                 const unsigned v = *reinterpret_cast<volatile unsigned*>(a.g.flags[a.g.rank] + fi) + 1u;
-                for (int p = 0; p < gworld; ++p) st_release_sys(a.g.flags[p] + fi, v);
+                for (int p = 0; p < gworld; ++p) st_relaxed_sys(a.g.flags[p] + fi, v);
             }
         }
     }
     TRTX_STAMP(6);
 }
 
-// Completes a gather of one slot on this rank: spins (acquire, system scope) until every rank's publish counter of the slot
-// has reached this rank's own (its own publish precedes this kernel in stream order).  One warp; gives up after ~2 s of SM
-// clocks (ctrl[2] = 1) instead of hanging the GPU.
+// Completes a gather of `nslots` slots on this rank: spins until every rank's publish counter of each slot has reached this
+// rank's own (its own publish precedes this kernel in stream order).  One warp; gives up after ~2 s of SM clocks (ctrl[2] = 1)
+// instead of hanging the GPU.  The polls are RELAXED system-scope loads and there is no fence: whatever reads the gathered rows
+// is a later kernel (or copy) of the stream, and the kernel boundary orders it after these loads.  (Measured, tools/
+// gather_probe.py and profiles/r02e_gather.log: every system-scope fence or release / acquire executed while the step's
+// kernels stream at ~6 TB/s stalls the whole step by several microseconds.)
 __global__ void __launch_bounds__(64) gather_wait_kernel(NmsArgs::Gather g, int nslots) {
     const int lane = threadIdx.x;  // one thread per (rank, slot): world * nslots <= 64
     const unsigned* fl = g.flags[g.rank];
     bool ok = true;
     if (lane < g.world * nslots) {
         const int r = lane / nslots, sl = g.slot + lane - r * nslots;
-        const unsigned expected = ld_acquire_sys(fl + (size_t)g.rank * g.slots + sl);
+        const unsigned expected = ld_relaxed_sys(fl + (size_t)g.rank * g.slots + sl);
         const unsigned* f = fl + (size_t)r * g.slots + sl;
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - expected) < 0) {
-            __nanosleep(100);
+        while ((int)(ld_relaxed_sys(f) - expected) < 0) {
+            __nanosleep(200);
             if (clock64() - t0 > 4000000000ll) {
                 ok = false;
                 break;
             }
         }
     }
-    if (!ok) g.ctrl[2] = 1u;  // (the acquire loads above order the peers' rows before everything that follows)
+    if (!ok) g.ctrl[2] = 1u;
 }
 
-// The same publish as a SEPARATE small kernel (a few 256-thread CTAs that co-reside with the step's streaming kernels): copies
-// the live part of every image's block of the local compact output into the slot on every rank and publishes the slot's
-// counter.  It does not wait for anybody.  (Measured, DESIGN.md section 5: the variant fused into nms_kernel keeps the NMS
-// CTAs' 32 whole SMs busy during the copy and the release, and everything that follows the NMS on its stream behind it.)
+// The publish as SEPARATE small kernels (default of PeerGather.push): (1) gather_copy_kernel -- a few 256-thread CTAs that
+// co-reside with the step's streaming kernels -- copies the live part of every image's block of the local compact outputs
+// into the slots on every rank: plain stores, no fence, no flag; (2) gather_publish_kernel -- one warp -- bumps this rank's
+// publish counter of every slot on every rank with relaxed system-scope stores.  The ordering "rows before counter" is the
+// KERNEL BOUNDARY between the two (a grid's writes, peer writes included, are performed at system scope before a dependent
+// grid of the stream starts), so no thread ever executes a system-scope fence.  Neither kernel waits for anybody.
 struct PushSrc {
     const float* src[8];  // local compact outputs of n consecutive steps -> slots slot .. slot+n-1
     int n;
 };
-__global__ void __launch_bounds__(256) gather_push_kernel(NmsArgs::Gather g, PushSrc ps, int batch, int cols, int max_det, int R) {
+__global__ void __launch_bounds__(256) gather_copy_kernel(NmsArgs::Gather g, PushSrc ps, int batch, int cols, int max_det, int R) {
+    // one CTA per (step, image): the kernel is a chain of dependent latencies (count -> rows -> stores), so its duration is one
+    // such chain, not their sum (8 CTAs walking 16 blocks each took ~40 us under the step's traffic and, because the NMS that
+    // overwrites a block has to wait for this copy, stalled the scan -> NMS chain by that much: profiles/r02e_gather.log)
     const int tid = threadIdx.x;
-    for (int w = blockIdx.x; w < ps.n * batch; w += gridDim.x) {
-        const int k = w / batch, b = w - k * batch;
-        const float* src = ps.src[k] + (size_t)b * cols;
-        const int n = min(max((int)src[0], 0), max_det);
-        const int live = 1 + n * R;
-        const size_t off = (((size_t)(g.slot + k) * g.world + g.rank) * batch + b) * cols;
+    const int w = blockIdx.x;
+    const int k = w / batch, b = w - k * batch;
+    const float* src = ps.src[k] + (size_t)b * cols;
+    const int n = min(max((int)src[0], 0), max_det);
+    const int live = 1 + n * R;
+    const size_t off = (((size_t)(g.slot + k) * g.world + g.rank) * batch + b) * cols;
+    constexpr int U = 4;  // rows in flight per thread: all loads first, then the stores to every rank
+    for (int i0 = tid; i0 < live; i0 += 256 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (i0 + u * 256 < live) ? src[i0 + u * 256] : 0.0f;
         for (int p = 0; p < g.world; ++p) {
             float* dst = g.out[p] + off;
-            for (int i = tid; i < live; i += 256) dst[i] = src[i];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u * 256 < live) dst[i0 + u * 256] = v[u];
         }
     }
+}
+__global__ void __launch_bounds__(64) gather_publish_kernel(NmsArgs::Gather g, int nslots) {
+    const int lane = threadIdx.x;  // one thread per (destination rank, slot): world * nslots <= 64
+    if (lane >= g.world * nslots) return;
+    const int p = lane / nslots, k = lane - p * nslots;
+    const size_t fi = (size_t)g.rank * g.slots + g.slot + k;  // this rank's publish counter of the slot, on every rank
+    // the local copy of the counter is only ever written by this rank's publishes, which are stream-ordered
+    const unsigned v = ld_relaxed_sys(g.flags[g.rank] + fi) + 1u;
+    __syncwarp();  // (every lane has read the old local value before lane p == rank overwrites it)
     __syncthreads();
-    if (tid != 0) return;
-    __threadfence();  // gpu scope: this CTA's stores before its count (see nms_kernel's gather block)
-    if (atomicAdd(&g.ctrl[1], 1u) != gridDim.x - 1) return;
-    g.ctrl[1] = 0u;
-    __threadfence();
-    for (int k = 0; k < ps.n; ++k) {  // the system-scope releases: the first one orders every store above, the rest are cheap
-        const size_t fi = (size_t)g.rank * g.slots + g.slot + k;
-        const unsigned v = *reinterpret_cast<volatile unsigned*>(g.flags[g.rank] + fi) + 1u;
-        for (int p = 0; p < g.world; ++p) st_release_sys(g.flags[p] + fi, v);
-    }
+    st_relaxed_sys(g.flags[p] + fi, v);
 }
 
 static size_t nms_smem_bytes(int pre_topk, int tiles = 0) {
@@ -1144,9 +1167,11 @@ TRTX_API int trtx_gather_push_many_enqueue(const trtx_gather* gather, const floa
         if (!compact_outs_dev[k]) return TRTX_ERR_INVALID;
         ps.src[k] = compact_outs_dev[k];
     }
+    if (n * g.world > 64) return TRTX_ERR_UNSUPPORTED;
     const int R = 7 + extra_floats;
     const int work = n * batch;
-    gather_push_kernel<<<work < 8 ? work : 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, ps, batch, 1 + max_det * R, max_det, R);
+    gather_copy_kernel<<<work, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, ps, batch, 1 + max_det * R, max_det, R);
+    gather_publish_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(g, n);
     return check_launch();
 }
 TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* compact_out_dev, int batch, int max_det,

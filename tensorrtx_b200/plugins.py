@@ -635,14 +635,16 @@ class FusedYoloDecodeNms:
         L.check(self._lib.trtx_yolo_scan_enqueue(C.byref(self.plugin.params), int(batch), ptrs, _ptr(self.ws),
                                                  self.ws_bytes, _stream(stream)), "trtx_yolo_scan_enqueue")
 
-    def enqueue_nms(self, batch: int, inputs, stream=None):
-        """Split form, second half: NMS over the tiles left by enqueue_scan."""
+    def enqueue_nms(self, batch: int, inputs, stream=None, out=None):
+        """Split form, second half: NMS over the tiles left by enqueue_scan (out: another [max_batch, 1 + max_det*7] buffer,
+        e.g. the second of a double buffer whose first half is still being gathered)."""
         ptrs = L.ptr_array([_ptr(t) for t in inputs])
+        out = self.out if out is None else out
         L.check(self._lib.trtx_yolo_nms_after_scan_enqueue(C.byref(self.plugin.params), C.byref(self.q), int(batch), ptrs,
-                                                           _ptr(self.out), _ptr(self.idx) if self.idx is not None else None,
+                                                           _ptr(out), _ptr(self.idx) if self.idx is not None else None,
                                                            _ptr(self.ws), self.ws_bytes, _stream(stream)),
                 "trtx_yolo_nms_after_scan_enqueue")
-        return self.out[:batch], (self.idx[:batch] if self.idx is not None else None)
+        return out[:batch], (self.idx[:batch] if self.idx is not None else None)
 
 
 # --------------------------------------------------------------------------------------------------
