@@ -471,6 +471,9 @@ def scan_traffic():
     return None
 
 
+PER_RANK_MS = []   # N > 1: one list per timed block with every rank's own block time (the reported time is their maximum)
+
+
 def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None, run_many=None):
     """W warm-up steps, then blocks of exactly K steps; returns (mean ms per block, [(t0, t1) wall windows], n_blocks)."""
     import torch
@@ -499,8 +502,11 @@ def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None, run
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
+            every = torch.empty(world, dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(every, t)          # per-rank block times (reported, see PER_RANK_MS)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+            PER_RANK_MS.append(every.tolist())
         return ms, (t0, t1)
 
     if run_many is not None:
@@ -597,7 +603,7 @@ def run_v8(args, rank, world, local_rank):
                 peer = PeerGather(world, rank, BATCH, pipe.fused.out.shape[1], dev, slots=2 * gdepth * max(1, min(args.graph_steps, R)))
                 peer.fused = bool(args.fused_gather)
                 gather_mode = ("fused into nms_kernel: NVLink peer stores + flags (trtx_gather), no collective kernel" if args.fused_gather else
-                               f"one gather_copy_kernel (8 CTAs: plain NVLink peer stores) + one gather_publish_kernel (counters, relaxed stores; the kernel boundary orders them) + one gather_wait_kernel per group of steps on a third graph chain, no system-scope fence anywhere; a group is published one replay after it was computed and awaited {gdepth - 1} replay(s) later (ring of {2 * gdepth} slot groups); no collective kernel"
+                               f"one gather_copy_kernel (one CTA per image block: plain NVLink peer stores) + one gather_publish_kernel (counters, relaxed stores; the kernel boundary orders them) + one gather_wait_kernel per group of steps on a third graph chain, no system-scope fence anywhere; a group is published one replay after it was computed and awaited {gdepth - 1} replay(s) later (ring of {2 * gdepth} slot groups); no collective kernel"
                                + (" [EXPERIMENT: no in-graph waits]" if args.gather_no_wait else ""))
             except Exception as e:
                 print(f"[bench] rank {rank}: peer gather unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
@@ -762,6 +768,13 @@ def run_v8(args, rank, world, local_rank):
         if peer is not None:   # whole groups only
             K, W = max(G, K // G * G), max(G, (W + G - 1) // G * G)
         ms_dev, win_dev, nb_dev = timed_blocks(step_dev, K, W, stream, dev, world, dist, flush_dev, run_many=run_dev)
+        per_rank_ms = None   # N > 1: every rank's own mean ms per step over the timed blocks (ms_per_step is built from the per-block maxima)
+        try:
+            if PER_RANK_MS:
+                per_rank_ms = [round(sum(blk[r] for blk in PER_RANK_MS) / len(PER_RANK_MS) / K, 6) for r in range(world)]
+        except Exception:
+            per_rank_ms = None
+        PER_RANK_MS.clear()
         gather_verified = None
         if peer is not None and not peer.fused and group_replay is not None and not args.gather_no_wait:
             # self-check outside the timed region: after one more group + flush, every rank's gathered buffer must hold every
@@ -856,6 +869,7 @@ def run_v8(args, rank, world, local_rank):
                 "overlap": (f"{G} steps per graph as two concurrent chains: letterbox launches || (scan -> NMS) launches" if G > 1 else
                             ("letterbox || (scan -> NMS) as parallel graph branches" if not args.no_overlap else "serial")),
                 "timed_blocks": {"device": nb_dev, "e2e": nb_e2e, "steps_per_block": K, "min_timed_s": MIN_TIMED_S},
+                "per_rank_ms_per_step": per_rank_ms,
                 "gather_timeouts": gather_err, "gather_verified": gather_verified,
                 "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
         "clocks": sampler.summary(win_dev + win_e2e),

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kRoiWindowThreads, 3) roi_align_window_kernel(
         for (unsigned e = threadIdx.x; e < ngroups * 32; e += kRoiWindowThreads) {
             const unsigned cell = (e >> 5) * 8 + fx;
             if (cell >= (unsigned)cells) continue;
-            const unsigned y = cells < 960 ? (cell * m_ww) >> 16 : cell / ww, x = cell - y * ww;  // exact: cell * (m_ww * ww - 2^16) < 2^16
+            const unsigned y = cells * ww <= 65536 ? (cell * m_ww) >> 16 : cell / ww, x = cell - y * ww;  // exact: cell * (m_ww * ww - 2^16) < cells * ww <= 2^16
             const float* src = fsrc + (y * a.W + x);
             uint32_t dst = fdst + cell * pitch * 4;
 #pragma unroll 4
@@ -414,15 +414,15 @@ TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* fe
     a.spatial_scale = spatial_scale;
     dim3 grid(num_proposals, (out_channels + kRoiChannelsPerCta - 1) / kRoiChannelsPerCta, batch);
     if (grid.y > 65535) return TRTX_ERR_UNSUPPORTED;
-    // the window kernel needs one bin per thread and a map whose single-channel window fits its shared memory
-    const bool window_ok = pooler_resolution * pooler_resolution <= kRoiWindowThreads &&
-                           (long long)feature_h * feature_w <= kRoiWindowFloats;
+    // the window kernel is built (and was validated on hardware) for the 14 x 14 pooler of the reference's heads (rcnn.cpp:43) and
+    // needs a map whose single-channel window fits its shared memory; every other shape takes the direct kernel
+    const bool window_ok = pooler_resolution == 14 && (long long)feature_h * feature_w <= kRoiWindowFloats / 4;
     if (mode == TRTX_ROI_DIRECT || !window_ok) {
         roi_align_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
         return check_launch();
     }
     constexpr int smem = kRoiWindowFloats * (int)sizeof(float);
-    auto kernel = pooler_resolution == 14 ? roi_align_window_kernel<14> : roi_align_window_kernel<0>;
+    auto kernel = roi_align_window_kernel<14>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
     if (e != cudaSuccess) {
         g_last_cuda_error = (int)e;
