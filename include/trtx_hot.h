@@ -210,14 +210,17 @@ TRTX_API int trtx_yolo_nms_after_scan_enqueue(const trtx_yolo_params* p, const t
  * allocated with trtx_peer_alloc (cudaMalloc + CUDA IPC handle) and mapped into the other ranks with trtx_peer_open, so
  * that out_dev[] / flags_dev[] hold, on every rank, the addresses of all ranks' buffers ([rank] = its own).  `slot` is chosen
  * by the caller per call (plain data: calls captured into CUDA graphs keep their slot).
- *   PUBLISH  trtx_gather_push_enqueue: a small kernel (8 CTAs) copies the live part [count, rows] of every image of a local
- *            compact output into `slot` of EVERY rank's `out` (lane-consecutive NVLink stores) and then raises this rank's
- *            counter of the slot on every rank with ONE system-scope release store.  It waits for nobody.
- *            trtx_yolo_decode_nms_gather_enqueue does the same from inside nms_kernel (no extra launch; but the NMS CTAs'
- *            32 whole SMs stay occupied during the copy and the release -- measured in DESIGN.md section 5).
- *   WAIT     trtx_gather_wait_enqueue (one warp): returns on the stream once every rank's counter of `slot` has reached this
- *            rank's own, i.e. all ranks' rows of this round are in the local out[slot]; work enqueued after it may read them.
- *            Rows past an image's `count` are stale.  Gives up after ~2 s (ctrl[2] = 1) instead of hanging the GPU.
+ *   PUBLISH  trtx_gather_push_enqueue: gather_copy_kernel (one CTA per image) copies the live part [count, rows] of every image
+ *            of a local compact output into `slot` of EVERY rank's `out` (lane-consecutive NVLink stores; no fence, no flag), then
+ *            gather_publish_kernel (one warp) raises this rank's counter of the slot on every rank with relaxed system-scope
+ *            stores: the kernel boundary between the two orders the rows before the counter, so no thread executes a system-scope
+ *            fence.  Neither kernel waits for anybody.
+ *            trtx_yolo_decode_nms_gather_enqueue publishes from inside nms_kernel instead (no extra launch; ONE system-scope
+ *            fence by the last CTA; the NMS CTAs' 32 whole SMs stay occupied during the copy -- measured in DESIGN.md section 5).
+ *   WAIT     trtx_gather_wait_enqueue (one warp, relaxed polls): returns on the stream once every rank's counter of `slot` has
+ *            reached this rank's own, i.e. all ranks' rows of this round are in the local out[slot]; LATER work of the stream
+ *            (kernels, copies) may read them.  Rows past an image's `count` are stale.  Gives up after ~2 s (ctrl[2] = 1) instead
+ *            of hanging the GPU.
  * Reusing a slot overwrites it on every rank: a rank may publish into a slot again only after all ranks have finished
  * reading the previous round.  The pattern that guarantees it without further handshakes: 2*G slots used in halves; the G
  * publishes of a round go to one half, then the G waits, all on the streams of the round; the next round uses the other half.
@@ -238,7 +241,8 @@ TRTX_API int trtx_gather_push_enqueue(const trtx_gather* gather, const float* co
 TRTX_API int trtx_gather_wait_enqueue(const trtx_gather* gather, trtx_stream_t stream);
 /* The same for n <= 8 consecutive slots slot .. slot+n-1 in ONE launch each (a round of n steps: one push kernel publishing
  * the n local outputs compact_outs_dev[0..n) -- a HOST array of device pointers -- with a single expensive release, one wait
- * kernel for the n slots; world * n <= 64). */
+ * kernel for the n slots; world * n <= 64).  A publish reads its sources when it runs: keep them unchanged until then (bench.py
+ * double-buffers the compact outputs so that the next NMS never has to wait for the publish of the previous one). */
 TRTX_API int trtx_gather_push_many_enqueue(const trtx_gather* gather, const float* const* compact_outs_dev, int n, int batch,
                                            int max_det, int extra_floats, trtx_stream_t stream);
 TRTX_API int trtx_gather_wait_many_enqueue(const trtx_gather* gather, int nslots, trtx_stream_t stream);
