@@ -484,7 +484,7 @@ def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None, run
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True, blocking=True)
         t0 = time.time()
         e0.record(stream)
         if run_many is not None:
@@ -495,8 +495,9 @@ def timed_blocks(step, K, W, stream, dev, world, dist, flush=None, pre=None, run
         if flush is not None:
             flush(first + K - 1)
         e1.record(stream)
-        torch.cuda.synchronize(dev)
-        t1 = time.time()
+        e1.synchronize()             # blocking-sync event: the host thread SLEEPS until the block is done instead of spinning -- with 8
+        torch.cuda.synchronize(dev)  # ranks spinning, the container's CPU quota (~10 cores on the GPU boxes) runs out and the launching
+        t1 = time.time()             # threads get descheduled (N = 8 without any gather: 61 us per step against 55 at N = 1, 2)
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -532,11 +533,12 @@ def time_kernel_loop(fn, n, stream, dev):
     for i in range(5):
         fn(i)
     torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True, blocking=True)
     e0.record(stream)
     for i in range(n):
         fn(i)
     e1.record(stream)
+    e1.synchronize()   # sleep, do not spin (see timed_blocks)
     torch.cuda.synchronize(dev)
     return e0.elapsed_time(e1) / n
 
