@@ -39,6 +39,13 @@ struct Builder : IExprBuilder {
 
 int main(int argc, char** argv) {
     const bool gpu = argc > 1 && std::string(argv[1]) == "--gpu";
+    const bool dump = argc > 1 && std::string(argv[1]) == "--dump";  // print every serialized blob as hex (compared with plugins.py)
+    auto hex = [&](const char* name, const std::vector<char>& b) {
+        if (!dump) return;
+        std::printf("blob %s ", name);
+        for (unsigned char c : b) std::printf("%02x", c);
+        std::printf("\n");
+    };
     // ---- what yolov8/src/block.cpp:262-296 does ----
     IPluginCreator* creator = getPluginRegistry()->getPluginCreator("YoloLayer_TRT", "1");
     CHECK(creator != nullptr);
@@ -72,6 +79,7 @@ int main(int argc, char** argv) {
     std::vector<char> blob2(blob.size());
     back->serialize(blob2.data());
     CHECK(blob == blob2);
+    hex("yolov8", blob);
     CHECK(creator->deserializePlugin("yololayer", blob.data(), blob.size() - 1) == nullptr);  // malformed -> refused, no assert
     IPluginV2* cl = obj->clone();
     CHECK(cl != nullptr && cl != obj);
@@ -109,6 +117,7 @@ int main(int argc, char** argv) {
     std::vector<char> b5(v5->getSerializationSize());
     v5->serialize(b5.data());
     CHECK(legacy.deserializePlugin("yololayer", b5.data(), b5.size()) != nullptr);
+    hex("yolov5", b5);
 
     // ---- Decode_TRT and the rcnn plugins ----
     IPluginCreator* dc = getPluginRegistry()->getPluginCreator("Decode_TRT", "1");
@@ -116,17 +125,44 @@ int main(int argc, char** argv) {
     PluginFieldCollection none{0, nullptr};
     IPluginV2* dec = dc->createPlugin("decode", &none);
     CHECK(dec != nullptr && std::string(dec->getPluginType()) == "Decode_TRT");
+    {
+        std::vector<char> db(dec->getSerializationSize());
+        dec->serialize(db.data());
+        hex("decode", db);
+    }
     trtx::RpnDecodePlugin rpn(6000, std::vector<float>(60, 1.f), 16.f, 50, 67, 800, 1067);
     CHECK(rpn.getNbOutputs() == 2 && rpn.getOutputDimensions(1, nullptr, 2).d[1] == 4 && rpn.getWorkspaceSize(8) > 0);
     std::vector<char> rb(rpn.getSerializationSize());
     rpn.serialize(rb.data());
     trtx::RpnDecodePlugin rpn2(rb.data(), rb.size());
+    hex("rpn_decode", rb);
+    {
+        trtx::RpnNmsPlugin rn(0.7f, 1000);
+        Dims nd[2];
+        nd[0].nbDims = 2; nd[0].d[0] = 6000; nd[0].d[1] = 1; nd[1] = nd[0];
+        rn.configurePlugin(nd, 2, nullptr, 1, nullptr, nullptr, nullptr, nullptr, PluginFormat::kLINEAR, 8);
+        std::vector<char> nb(rn.getSerializationSize());
+        rn.serialize(nb.data());
+        hex("rpn_nms", nb);
+        trtx::PredictorDecodePlugin pd(1000, 800, 1067, std::vector<float>{10.f, 10.f, 5.f, 5.f});
+        Dims pdm[3];
+        pdm[0].nbDims = 4; pdm[0].d[0] = 1000; pdm[0].d[1] = 80; pdm[0].d[2] = 1; pdm[0].d[3] = 1; pdm[1] = pdm[0]; pdm[2] = pdm[0];
+        pd.configurePlugin(pdm, 3, nullptr, 3, nullptr, nullptr, nullptr, nullptr, PluginFormat::kLINEAR, 8);
+        std::vector<char> pb(pd.getSerializationSize());
+        pd.serialize(pb.data());
+        hex("predictor_decode", pb);
+    }
     CHECK(rpn2.getSerializationSize() == rb.size());
     trtx::BatchedNmsPlugin bn(1, 0.5f, 100);
     Dims cd[3];
     cd[0].nbDims = 2; cd[0].d[0] = 1000; cd[0].d[1] = 1; cd[1] = cd[0]; cd[2] = cd[0];
     bn.configurePlugin(cd, 3, nullptr, 3, nullptr, nullptr, nullptr, nullptr, PluginFormat::kLINEAR, 8);
     CHECK(bn.getSerializationSize() == 4 + 4 + 4 + sizeof(size_t) && bn.getWorkspaceSize(8) > 0);
+    {
+        std::vector<char> bb(bn.getSerializationSize());
+        bn.serialize(bb.data());
+        hex("batched_nms", bb);
+    }
     CHECK(getPluginRegistry()->getPluginCreator("BatchedNms", "1") != nullptr && getPluginRegistry()->getPluginCreator("RpnNms", "1") != nullptr);
     trtx::RoiAlignPlugin ra(14, 1.f / 16, 0, 1000, 1024);
     Dims rd[2];
@@ -136,11 +172,17 @@ int main(int argc, char** argv) {
     std::vector<char> rab(ra.getSerializationSize());
     ra.serialize(rab.data());
     trtx::RoiAlignPlugin ra2(rab.data(), rab.size());
+    hex("roi_align", rab);
     CHECK(rab.size() == 28 && ra2.getOutputDimensions(0, nullptr, 2).d[3] == 14 && ra2.getWorkspaceSize(8) == 0);
     CHECK(std::string(ra2.getPluginType()) == "RoiAlign" && getPluginRegistry()->getPluginCreator("RoiAlign", "1") != nullptr);
     trtx::MaskRcnnInferencePlugin mi(100, 14);
     CHECK(mi.getSerializationSize() == 12 && mi.getOutputDimensions(0, nullptr, 2).d[0] == 100 &&
           getPluginRegistry()->getPluginCreator("MaskRcnnInference", "1") != nullptr);
+    {
+        std::vector<char> mb(mi.getSerializationSize());
+        mi.serialize(mb.data());
+        hex("mask_rcnn_inference", mb);
+    }
 
     if (gpu) {
         // ---- enqueue through both YOLO adapters on the same synthetic heads; outputs must be identical ----
