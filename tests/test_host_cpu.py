@@ -305,3 +305,40 @@ def test_roi_align_window_kernel_arithmetic_shortcuts_are_exact(tmp_path):
         assert np.array_equal((cell * m) >> 16, cell // ww), ww
     src = (ROOT / "tensorrtx_b200" / "csrc" / "roi_align.cu").read_text()
     assert "cells * ww <= 65536 ? (cell * m_ww) >> 16 : cell / ww" in src and "kRoiWindowFloats / 4" in src
+
+
+def test_gather_ring_schedule_never_overwrites_an_unread_slot_group():
+    """bench.py's multi-GPU step: replay k of a rank PUBLISHES group k-1 into slot group k mod 2D of every
+    rank and WAITS for every rank's publish of group k-D (D = --gather-depth; D = 1: the group just published); consumers of a
+    group run in the replay that waited for it.  Claim: with a ring of 2D slot groups no rank ever overwrites a slot group a
+    peer has not finished reading, whatever the ranks' relative speeds.  Event-driven replay of the schedule with random
+    per-replay durations (a wait blocks until the peers' publishes exist); the publish of replay k lands at the replay's start,
+    the read of the awaited group lasts until the replay's end."""
+    rng = np.random.default_rng(7)
+    for D in (1, 2, 3):
+        NG = 2 * D
+        for world in (2, 3, 8):
+            for trial in range(20):
+                n_replays = 60
+                dur = rng.uniform(0.2, 3.0, (world, n_replays)) * rng.uniform(0.5, 2.0, (world, 1))  # some ranks are slower overall
+                start = np.zeros((world, n_replays)); end = np.zeros((world, n_replays))
+                pub = np.full((world, n_replays), np.inf)   # time at which rank r published group g (g = replay index - 1)
+                # iterate to the fixed point of the dependency graph (replay k of r starts after replay k-1 of r ended; it ends
+                # after its own work AND after every peer has published group k-D, i.e. started replay k-D+1)
+                for k in range(n_replays):
+                    for r in range(world):
+                        start[r, k] = end[r, k - 1] if k else 0.0
+                        if k >= 1:
+                            pub[r, k - 1] = start[r, k]                     # group k-1 published at the start of replay k
+                    for r in range(world):
+                        need = k - D
+                        t_wait = max(pub[p, need] for p in range(world)) if need >= 0 else 0.0
+                        assert np.isfinite(t_wait), "a wait for a group that nobody can have published yet: deadlock"
+                        end[r, k] = max(start[r, k] + dur[r, k], t_wait)
+                # safety: group g occupies slot group (g+1) mod NG on every rank from pub[., g] on; it is overwritten by group
+                # g + NG, published by rank p at pub[p, g + NG]; rank q reads group g during the replay that waited for it
+                # (replay g + D), i.e. until end[q, g + D]
+                for g in range(n_replays - NG - 1):
+                    for p in range(world):
+                        for q in range(world):
+                            assert pub[p, g + NG] >= end[q, g + D] - 1e-12, (D, world, trial, g, p, q)
