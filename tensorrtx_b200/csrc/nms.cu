@@ -83,14 +83,8 @@ struct NmsArgs {
     } g;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+// system-scope RELAXED accesses of the gather's publish counters: the ordering comes from kernel boundaries (or, in the variant
+// fused into nms_kernel, from one __threadfence_system()), never from per-access acquire / release -- see gather_wait_kernel
 __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
     unsigned v;
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
