@@ -342,3 +342,38 @@ def test_gather_ring_schedule_never_overwrites_an_unread_slot_group():
                     for p in range(world):
                         for q in range(world):
                             assert pub[p, g + NG] >= end[q, g + D] - 1e-12, (D, world, trial, g, p, q)
+
+
+def test_no_undefined_global_names_in_bench_and_package():
+    """bench.py's GPU legs cannot run here; at least every global name its functions (and the package's) load must exist --
+    a cheap guard against a typo that would only surface at the end of a GPU run."""
+    import builtins
+    import dis
+    import importlib.util
+    import types
+
+    for rel in ("bench.py", "__graft_entry__.py", "tensorrtx_b200/pipeline.py", "tensorrtx_b200/plugins.py", "tensorrtx_b200/_lib.py",
+                "tensorrtx_b200/synth.py", "tensorrtx_b200/build.py"):
+        path = ROOT / rel
+        name = "chk_" + rel.replace("/", "_").replace(".py", "")
+        if rel.startswith("tensorrtx_b200/"):
+            name = "tensorrtx_b200." + name      # relative imports of the package modules resolve
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        try:
+            spec.loader.exec_module(mod)
+            missing = set()
+
+            def walk(co):
+                for ins in dis.get_instructions(co):
+                    if ins.opname in ("LOAD_GLOBAL", "LOAD_NAME") and isinstance(ins.argval, str):
+                        if not hasattr(mod, ins.argval) and not hasattr(builtins, ins.argval):
+                            missing.add((co.co_name, ins.argval))
+                for c in co.co_consts:
+                    if isinstance(c, types.CodeType):
+                        walk(c)
+            walk(compile(path.read_text(), str(path), "exec"))
+            assert not missing, (rel, sorted(missing))
+        finally:
+            sys.modules.pop(name, None)
