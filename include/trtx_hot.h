@@ -353,8 +353,9 @@ TRTX_API int trtx_roi_align(int batch, const float* rois_dev, const float* featu
                             int feature_w, trtx_stream_t stream);
 /* The same with the kernel chosen by the caller (both are bit-identical to the reference's roiAlign):
  * TRTX_ROI_WINDOW (what trtx_roi_align uses) stages each proposal's feature-map window in shared memory and takes the
- * bilinear taps from there; TRTX_ROI_DIRECT takes every tap from global memory (the round-1 kernel; also what
- * TRTX_ROI_WINDOW falls back to when a channel of the map does not fit the window buffer, feature_h * feature_w > 20480). */
+ * bilinear taps from there -- for the reference's configuration class: pooler_resolution 14, out_channels % 4 == 0,
+ * feature_h * feature_w <= 4096; any other shape runs TRTX_ROI_DIRECT, which takes every tap from global memory (the
+ * round-1 kernel). */
 #define TRTX_ROI_WINDOW 0
 #define TRTX_ROI_DIRECT 1
 TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* features_dev, float* out_dev, int pooler_resolution,

@@ -415,8 +415,9 @@ TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* fe
     dim3 grid(num_proposals, (out_channels + kRoiChannelsPerCta - 1) / kRoiChannelsPerCta, batch);
     if (grid.y > 65535) return TRTX_ERR_UNSUPPORTED;
     // the window kernel is built (and was validated on hardware) for the 14 x 14 pooler of the reference's heads (rcnn.cpp:43) and
-    // needs a map whose single-channel window fits its shared memory; every other shape takes the direct kernel
-    const bool window_ok = pooler_resolution == 14 && (long long)feature_h * feature_w <= kRoiWindowFloats / 4;
+    // needs a map whose single-channel window fits its shared memory; every other shape (other poolers, channel counts that are
+    // not a multiple of 4 -- code paths no test has run on a GPU) takes the direct kernel
+    const bool window_ok = pooler_resolution == 14 && out_channels % 4 == 0 && (long long)feature_h * feature_w <= kRoiWindowFloats / 4;
     if (mode == TRTX_ROI_DIRECT || !window_ok) {
         roi_align_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
         return check_launch();
