@@ -367,6 +367,15 @@ TRTX_API int trtx_roi_align_ex(int batch, const float* rois_dev, const float* fe
 TRTX_API int trtx_mask_rcnn_inference(int batch, const float* indices_dev, const float* masks_dev, float* out_dev,
                                       int detections_per_im, int output_size, int num_classes, trtx_stream_t stream);
 
+/* The INT8 calibrator's host pre-process: Int8EntropyCalibrator2::getBatch, yolov8/src/calibrator.cpp:33-52
+ * = preprocess_img (yolov8/include/utils.h:6-26: cv::resize INTER_LINEAR of the 8-bit image into the letterbox rectangle, 128-grey
+ * canvas) + cv::dnn::blobFromImages(1 / 255.0, swapRB).  HOST code, like the reference's (calibration is not in the inference loop):
+ * bgr = 8-bit BGR rows of src_pitch bytes; out_chw = [3, net_h, net_w] fp32 RGB planes, ready for the cudaMemcpy of :48.  The
+ * OpenCV arithmetic is restated (fixed-point bilinear resize, float scale) and pinned bit for bit against cv2 4.13.
+ * trtx_calib_letterbox_rect: the rectangle {x, y, w, h} the resized image occupies. */
+TRTX_API int trtx_calib_letterbox_rect(int src_w, int src_h, int net_w, int net_h, int rect[4]);
+TRTX_API int trtx_calib_letterbox_host(const uint8_t* bgr, int src_w, int src_h, size_t src_pitch, int net_w, int net_h, float* out_chw);
+
 /* =====================================================================================
  * 6. Instance masks of the segmentation models
  *    replaces the HOST function process_mask(), yolov8/yolov8_seg.cpp:17-60 and

@@ -826,6 +826,34 @@ class BatchedNmsPlugin:
 # --------------------------------------------------------------------------------------------------
 # Pre-process (preprocess.h)
 # --------------------------------------------------------------------------------------------------
+class Int8CalibratorBatcher:
+    """The host pre-process of Int8EntropyCalibrator2::getBatch (yolov8/src/calibrator.cpp:33-52): every image goes through
+    preprocess_img (letterbox, cv::resize INTER_LINEAR) and cv::dnn::blobFromImages(1 / 255.0, swapRB); `get_batch(images)` returns
+    the [B, 3, input_h, input_w] fp32 batch the calibrator copies to the device.  HOST code (trtx_calib_letterbox_host), as in the
+    reference; bit-identical to OpenCV 4.13 (tests/test_calibrator_cpu.py)."""
+
+    def __init__(self, batchsize: int, input_w: int, input_h: int):
+        self._lib = L.load()
+        self.batchsize, self.input_w, self.input_h = int(batchsize), int(input_w), int(input_h)
+        self.input_count = 3 * self.input_w * self.input_h * self.batchsize     # calibrator.cpp:20
+
+    def getBatchSize(self) -> int:
+        return self.batchsize
+
+    def get_batch(self, images) -> "np.ndarray":
+        import numpy as np
+
+        if len(images) != self.batchsize:
+            raise L.TrtxError(f"Int8CalibratorBatcher: {len(images)} images for a batch of {self.batchsize}")
+        out = np.empty((self.batchsize, 3, self.input_h, self.input_w), np.float32)
+        for i, img in enumerate(images):
+            img = np.ascontiguousarray(img, np.uint8)
+            h, w = img.shape[:2]
+            L.check(self._lib.trtx_calib_letterbox_host(img.ctypes.data_as(C.c_void_p), w, h, img.strides[0], self.input_w, self.input_h,
+                                                        out[i].ctypes.data_as(C.c_void_p)), "trtx_calib_letterbox_host")
+        return out
+
+
 class RoiAlignPlugin:
     """rcnn/RoiAlignPlugin.h:27-170 (plugin "RoiAlign"): inputs proposals [B,N,4], features [B,C,H,W] ->
     [B, N, C, P, P].  No workspace, no device synchronisation (the reference syncs after every image)."""
