@@ -62,6 +62,17 @@ __attribute__((visibility("default"))) int ref_v8_process_decode_ptr_host(const 
     for (size_t i = 0; i < res.size(); ++i) memcpy(res_out + i * 6, &res[i], 6 * sizeof(float));
     return (int)res.size();
 }
+// process_decode_ptr_host_obb (postprocess.cpp:273-290): kept rows incl. the angle (Detection::angle is the struct's last float)
+__attribute__((visibility("default"))) int ref_v8_process_decode_ptr_host_obb(const float* decode_ptr_host, int bbox_elem, int count, float* res_out) {
+    std::vector<Detection> res;
+    cv::Mat img;
+    process_decode_ptr_host_obb(res, decode_ptr_host, bbox_elem, img, count);
+    for (size_t i = 0; i < res.size(); ++i) {
+        memcpy(res_out + i * 7, &res[i], 6 * sizeof(float));
+        res_out[i * 7 + 6] = res[i].angle;
+    }
+    return (int)res.size();
+}
 // get_rect (postprocess.cpp:4-36): box in network-input pixels -> cv::Rect in the original image (kInputW x kInputH = 640 x 640)
 __attribute__((visibility("default"))) void ref_v8_get_rect(int img_w, int img_h, float* bbox, int* rect_out) {
     cv::Mat img(img_h, img_w, CV_8UC3, nullptr);

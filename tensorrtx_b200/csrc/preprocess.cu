@@ -534,6 +534,22 @@ TRTX_API int trtx_process_decode_ptr_host(const float* decode_ptr_host, int bbox
     return n;
 }
 
+// process_decode_ptr_host_obb (yolov8/src/postprocess.cpp:273-290): the same for oriented boxes -- 7 floats per kept row, the angle
+// from column 7 of the 8-float rows cuda_decode_obb writes (postprocess.cu:31-39)
+TRTX_API int trtx_process_decode_ptr_host_obb(const float* decode_ptr_host, int bbox_element, int count, float* rows_out) {
+    if (!decode_ptr_host || !rows_out || bbox_element < 8 || count < 0) return -TRTX_ERR_INVALID;
+    int n = 0;
+    for (int i = 0; i < count; ++i) {
+        const float* p = decode_ptr_host + 1 + (size_t)i * bbox_element;
+        if ((int)p[6] == 1) {
+            for (int k = 0; k < 6; ++k) rows_out[(size_t)n * 7 + k] = p[k];
+            rows_out[(size_t)n * 7 + 6] = p[7];
+            ++n;
+        }
+    }
+    return n;
+}
+
 TRTX_API int trtx_preprocess_batch_enqueue(const trtx_image_desc* images_host, int batch, void* dst_dev, int dst_w,
                                            int dst_h, int out_dtype, trtx_stream_t stream) {
     if (!images_host || batch <= 0 || !dst_dev || dst_w <= 0 || dst_h <= 0) return TRTX_ERR_INVALID;

@@ -194,3 +194,26 @@ def test_scale_mask_rect_and_process_decode_rows_equal_reference():
     n_ref = ref.ref_v8_process_decode_ptr_host(buf.ctypes.data_as(C.c_void_p), 7, K, out_ref.ctypes.data_as(C.c_void_p))
     n = lib.trtx_process_decode_ptr_host(buf.ctypes.data_as(C.POINTER(C.c_float)), 7, K, out_mine.ctypes.data_as(C.POINTER(C.c_float)))
     assert n == n_ref == int(rows[:, 6].sum()) and np.array_equal(out_mine, out_ref)
+
+
+def test_process_decode_ptr_host_obb_equals_reference():
+    """process_decode_ptr_host_obb (yolov8/src/postprocess.cpp:273-290): kept rows of the oriented-box compact buffer (8-float rows,
+    angle in column 7) -- the library's host function against the reference's compiled code."""
+    from tensorrtx_b200 import _lib as L
+    ref = _load("libref_yolov8_host.so")
+    if not hasattr(ref, "ref_v8_process_decode_ptr_host_obb"):
+        pytest.skip("oracle/_ref predates the obb wrapper (run `make -C oracle` where /root/reference is mounted)")
+    lib = L.load()
+    rng = np.random.default_rng(72)
+    for elem in (8, 9):
+        K = 150
+        buf = np.zeros(1 + K * elem, np.float32)
+        buf[0] = K
+        rows = buf[1:].reshape(K, elem)
+        rows[:, :] = rng.uniform(-3, 640, (K, elem)).astype(np.float32)
+        rows[:, 6] = rng.integers(0, 3, K)                  # keep flags 0, 1, 2: only == 1 is kept
+        out_ref, out_mine = np.zeros((K, 7), np.float32), np.zeros((K, 7), np.float32)
+        n_ref = ref.ref_v8_process_decode_ptr_host_obb(buf.ctypes.data_as(C.c_void_p), elem, K, out_ref.ctypes.data_as(C.c_void_p))
+        n = lib.trtx_process_decode_ptr_host_obb(buf.ctypes.data_as(C.POINTER(C.c_float)), elem, K, out_mine.ctypes.data_as(C.POINTER(C.c_float)))
+        assert n == n_ref == int((rows[:, 6] == 1).sum()) and n > 20 and np.array_equal(out_mine, out_ref)
+    assert lib.trtx_process_decode_ptr_host_obb(buf.ctypes.data_as(C.POINTER(C.c_float)), 7, K, out_mine.ctypes.data_as(C.POINTER(C.c_float))) < 0
