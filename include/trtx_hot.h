@@ -333,6 +333,10 @@ TRTX_API int trtx_get_rect(int variant, int net_w, int net_h, int img_w, int img
  * a cv::Rect in the original image and the num_kpts keypoints (x, y, conf triplets, `lmk`) are mapped IN PLACE.  Host function. */
 TRTX_API int trtx_get_rect_adapt_landmark(int net_w, int net_h, int img_w, int img_h, const float bbox[4], float* lmk,
                                           int num_kpts, int rect[4]);
+/* RetinaFace's own get_rect_adapt_landmark (retinaface/common.hpp:65-89): 5 landmarks as x, y pairs, modified in place; the box
+ * corners are truncated to int and not clamped; rect = {x, y, w, h} in the original image. */
+TRTX_API int trtx_retina_get_rect_adapt_landmark(int input_w, int input_h, int img_w, int img_h, const float bbox[4], float lmk[10],
+                                                 int rect[4]);
 /* process_decode_ptr_host (yolov8/src/postprocess.cpp:131-147): rows of a compact buffer [1 + K*bbox_element] (the output
  * of the ONESHOT mode / cuda_decode+cuda_nms) whose keep flag is 1 -> 6-float rows l,t,r,b,conf,cls.  Returns the number
  * of rows written (<= count), or a negative TRTX_ERR_*.  Host function on HOST memory. */

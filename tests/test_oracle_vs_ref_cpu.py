@@ -217,3 +217,28 @@ def test_process_decode_ptr_host_obb_equals_reference():
         n = lib.trtx_process_decode_ptr_host_obb(buf.ctypes.data_as(C.POINTER(C.c_float)), elem, K, out_mine.ctypes.data_as(C.POINTER(C.c_float)))
         assert n == n_ref == int((rows[:, 6] == 1).sum()) and n > 20 and np.array_equal(out_mine, out_ref)
     assert lib.trtx_process_decode_ptr_host_obb(buf.ctypes.data_as(C.POINTER(C.c_float)), 7, K, out_mine.ctypes.data_as(C.POINTER(C.c_float))) < 0
+
+
+def test_retina_get_rect_adapt_landmark_equals_reference():
+    """RetinaFace's get_rect_adapt_landmark (retinaface/common.hpp:65-89: box corners truncated to int, 5 landmark pairs mapped in
+    place) -- the library's host function against the reference's compiled code: identical integers and landmark bits on 250 faces
+    x 8 image sizes, for the 640x640 network of BASELINE config 3 and the 480x640 one the reference compiles in."""
+    from tensorrtx_b200 import _lib as L
+    ref = _load("libref_retina_host.so")
+    if not hasattr(ref, "ref_retina_get_rect_adapt_landmark"):
+        pytest.skip("oracle/_ref predates this wrapper (run `make -C oracle` where /root/reference is mounted)")
+    lib = L.load()
+    rng = np.random.default_rng(73)
+    for (in_w, in_h) in ((640, 640), (640, 480)):
+        for (w, h) in SIZES:
+            for _ in range(250):
+                x1, y1 = rng.uniform(-30, in_w + 10), rng.uniform(-30, in_h + 10)
+                bb = np.array([x1, y1, x1 + rng.uniform(-5, 400), y1 + rng.uniform(-5, 400)], np.float32)
+                lmk = rng.uniform(-20, 660, 10).astype(np.float32)
+                l_ref, r_ref = lmk.copy(), np.zeros(4, np.int32)
+                ref.ref_retina_get_rect_adapt_landmark(w, h, in_w, in_h, bb.copy().ctypes.data_as(C.c_void_p), l_ref.ctypes.data_as(C.c_void_p),
+                                                       r_ref.ctypes.data_as(C.c_void_p))
+                l_mine, r_mine = lmk.copy(), (C.c_int * 4)()
+                assert lib.trtx_retina_get_rect_adapt_landmark(in_w, in_h, w, h, bb.ctypes.data_as(C.POINTER(C.c_float)),
+                                                               l_mine.ctypes.data_as(C.POINTER(C.c_float)), r_mine) == 0
+                assert list(r_mine) == r_ref.tolist() and np.array_equal(l_mine, l_ref)
