@@ -62,3 +62,27 @@ def test_get_rect_equals_golden(oracle, gold, variant):
     for bb, r, (w, h) in zip(boxes, rects, sizes):
         assert np.array_equal(oracle.get_rect(variant, int(w), int(h), bb), r)
         assert P.get_rect(int(w), int(h), bb, variant=variant) == tuple(int(v) for v in r)     # the library's host function
+
+
+def test_landmark_and_decode_ptr_host_functions_equal_golden(gold):
+    """get_rect_adapt_landmark (yolov8 and RetinaFace flavours) and process_decode_ptr_host(_obb): the library's host functions."""
+    import ctypes as C
+
+    from tensorrtx_b200 import _lib as L
+    from tensorrtx_b200 import plugins as P
+    lib = L.load()
+    for bb, li, lo, r, (w, h, in_w, in_h) in zip(gold["retina_lmk_boxes"], gold["retina_lmk_in"], gold["retina_lmk_out"], gold["retina_lmk_rects"],
+                                                 gold["retina_lmk_meta"]):
+        lm, rect = li.copy(), (C.c_int * 4)()
+        assert lib.trtx_retina_get_rect_adapt_landmark(int(in_w), int(in_h), int(w), int(h), np.ascontiguousarray(bb).ctypes.data_as(C.POINTER(C.c_float)),
+                                                       lm.ctypes.data_as(C.POINTER(C.c_float)), rect) == 0
+        assert list(rect) == r.tolist() and np.array_equal(lm, lo)
+    for bb, li, lo, r, (w, h) in zip(gold["v8_lmk_boxes"], gold["v8_lmk_in"], gold["v8_lmk_out"], gold["v8_lmk_rects"], gold["v8_lmk_meta"]):
+        rect, mapped = P.get_rect_adapt_landmark(int(w), int(h), bb, li)
+        assert rect == tuple(int(v) for v in r) and np.array_equal(np.asarray(mapped, np.float32), lo)
+    for key, elem, F, fn in (("pdh", 7, 6, lib.trtx_process_decode_ptr_host), ("pdh_obb", 8, 7, lib.trtx_process_decode_ptr_host_obb)):
+        buf, ref = np.ascontiguousarray(gold[key + "_in"]), gold[key + "_out"]
+        K = int(buf[0])
+        out = np.zeros((K, F), np.float32)
+        n = fn(buf.ctypes.data_as(C.POINTER(C.c_float)), elem, K, out.ctypes.data_as(C.POINTER(C.c_float)))
+        assert n == len(ref) and n > 10 and np.array_equal(out[:n], ref)

@@ -82,6 +82,43 @@ def main():
                 getattr(lib, fn)(w, h, bb.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p))
                 boxes.append(bb), rects.append(r), wh_.append((w, h))
         g[f"rect{variant}_boxes"], g[f"rect{variant}_rects"], g[f"rect{variant}_sizes"] = np.array(boxes), np.array(rects), np.array(wh_, np.int32)
+    # ---- RetinaFace get_rect_adapt_landmark (retinaface/common.hpp:65-89) and yolov8 get_rect_adapt_landmark (postprocess.cpp:38-69) ----
+    rng = np.random.default_rng(73)
+    boxes, lm_in, lm_out, rects, meta = [], [], [], [], []
+    for (in_w, in_h) in ((640, 640), (640, 480)):
+        for (w, h) in sizes:
+            for _ in range(25):
+                x1, y1 = rng.uniform(-30, in_w + 10), rng.uniform(-30, in_h + 10)
+                bb = np.array([x1, y1, x1 + rng.uniform(-5, 400), y1 + rng.uniform(-5, 400)], np.float32)
+                lmk = rng.uniform(-20, 660, 10).astype(np.float32)
+                lo, r = lmk.copy(), np.zeros(4, np.int32)
+                rt.ref_retina_get_rect_adapt_landmark(w, h, in_w, in_h, bb.copy().ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p),
+                                                      r.ctypes.data_as(C.c_void_p))
+                boxes.append(bb), lm_in.append(lmk), lm_out.append(lo), rects.append(r), meta.append((w, h, in_w, in_h))
+    g["retina_lmk_boxes"], g["retina_lmk_in"], g["retina_lmk_out"] = np.array(boxes), np.array(lm_in), np.array(lm_out)
+    g["retina_lmk_rects"], g["retina_lmk_meta"] = np.array(rects), np.array(meta, np.int32)
+    boxes, lm_in, lm_out, rects, meta = [], [], [], [], []
+    for (w, h) in sizes:
+        for _ in range(40):
+            x1, y1 = rng.uniform(-30, 650, 2)
+            bb = np.array([x1, y1, x1 + rng.uniform(-5, 400), y1 + rng.uniform(-5, 400)], np.float32)
+            lmk = rng.uniform(-20, 660, 51).astype(np.float32)
+            lo, r = lmk.copy(), np.zeros(4, np.int32)
+            v8.ref_v8_get_rect_adapt_landmark(w, h, bb.copy().ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p))
+            boxes.append(bb), lm_in.append(lmk), lm_out.append(lo), rects.append(r), meta.append((w, h))
+    g["v8_lmk_boxes"], g["v8_lmk_in"], g["v8_lmk_out"] = np.array(boxes), np.array(lm_in), np.array(lm_out)
+    g["v8_lmk_rects"], g["v8_lmk_meta"] = np.array(rects), np.array(meta, np.int32)
+    # ---- process_decode_ptr_host / _obb (postprocess.cpp:131-147, 273-290) ----
+    K = 120
+    for elem, fn, F, key in ((7, v8.ref_v8_process_decode_ptr_host, 6, "pdh"), (8, v8.ref_v8_process_decode_ptr_host_obb, 7, "pdh_obb")):
+        buf = np.zeros(1 + K * elem, np.float32)
+        buf[0] = K
+        rows = buf[1:].reshape(K, elem)
+        rows[:, :] = rng.uniform(-3, 640, (K, elem)).astype(np.float32)
+        rows[:, 6] = rng.integers(0, 3, K)
+        out = np.zeros((K, F), np.float32)
+        n = fn(buf.ctypes.data_as(C.c_void_p), elem, K, out.ctypes.data_as(C.c_void_p))
+        g[key + "_in"], g[key + "_out"] = buf, out[:n].copy()
     dst = ROOT / "tests" / "golden" / "ref_host.npz"
     np.savez_compressed(dst, **g)
     print(dst, dst.stat().st_size, "bytes;", {k: v.shape for k, v in g.items()})
