@@ -132,6 +132,68 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": inside, "sampled": "inside the timed windows only (100 ms period)"}
 
 
+class AllGpuSampler:
+    """N > 1, rank 0: every GPU of the box twice a second (SM / memory clocks, GPU / HBM temperatures, power, throttle reasons), so
+    that a rank that is slower than the others (run.per_rank_ms_per_step) can be told from a slow host.  Never raises."""
+    Q = "index,clocks.sm,clocks.mem,temperature.gpu,temperature.memory,power.draw,clocks_event_reasons.active"
+
+    def __init__(self):
+        self.proc, self.lines = None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        try:
+            for line in self.proc.stdout:
+                self.lines.append((time.time(), line.strip()))
+        except Exception:
+            pass
+
+    def stop(self):
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+                try:
+                    self.proc.wait(timeout=2)
+                except Exception:
+                    self.proc.kill()
+        except Exception:
+            pass
+
+    def summary(self, windows):
+        try:
+            per = {}
+            for ts, line in list(self.lines):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7 or not any(a <= ts <= b for a, b in windows):
+                    continue
+                per.setdefault(f[0], []).append(f[1:])
+            out = []
+            for idx in sorted(per, key=lambda s: int(s) if s.isdigit() else 0):
+                rows = per[idx]
+
+                def col(k, fn):
+                    v = []
+                    for r in rows:
+                        try:
+                            v.append(float(r[k]))
+                        except ValueError:
+                            pass
+                    return fn(v) if v else None
+                out.append({"gpu": int(idx) if idx.isdigit() else idx, "sm_mhz": col(0, statistics.median), "mem_mhz": col(1, statistics.median),
+                            "temp_c": col(2, max), "hbm_temp_c": col(3, max), "power_w": col(4, statistics.median),
+                            "reasons": sorted({r[5] for r in rows}), "samples": len(rows)})
+            return out or None
+        except Exception:
+            return None
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU side: the reference's own CPU code where it exists (oracle/_ref, compiled from /root/reference: host nms()),
 # the oracle's restatement where the reference only has a GPU kernel (decode), the reference's Python CPU pre-process
@@ -763,8 +825,11 @@ def run_v8(args, rank, world, local_rank):
                 ring.launch(pipe.fused.out, i % R)
 
         sampler = ClockSampler(local_rank)
+        all_gpus = AllGpuSampler() if (rank == 0 and world > 1) else None
         if rank == 0:
             sampler.start()
+            if all_gpus is not None:
+                all_gpus.start()
             time.sleep(0.25)
         K, W = args.steps, args.warmup
         if peer is not None:   # whole groups only
@@ -830,6 +895,8 @@ def run_v8(args, rank, world, local_rank):
         scan_ms_graph = time_kernel_loop(lambda i: g_scan.replay(), 10, stream, dev) / 20
         if rank == 0:
             sampler.stop()
+            if all_gpus is not None:
+                all_gpus.stop()
 
     def leave():
         if world == 1:
@@ -872,6 +939,7 @@ def run_v8(args, rank, world, local_rank):
                             ("letterbox || (scan -> NMS) as parallel graph branches" if not args.no_overlap else "serial")),
                 "timed_blocks": {"device": nb_dev, "e2e": nb_e2e, "steps_per_block": K, "min_timed_s": MIN_TIMED_S},
                 "per_rank_ms_per_step": per_rank_ms,
+                "gpus_during_device_blocks": all_gpus.summary(win_dev) if all_gpus is not None else None,
                 "gather_timeouts": gather_err, "gather_verified": gather_verified,
                 "backbone": "not on this path (TensorRT in the reference); head tensors are synthetic and HBM-resident"},
         "clocks": sampler.summary(win_dev + win_e2e),

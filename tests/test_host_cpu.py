@@ -380,3 +380,24 @@ def test_no_undefined_global_names_in_bench_and_package():
             assert not missing, (rel, sorted(missing))
         finally:
             sys.modules.pop(name, None)
+
+
+def test_all_gpu_sampler_summary_is_robust():
+    """bench.py's AllGpuSampler (N > 1: every GPU's clocks / temperatures during the timed blocks) must never raise: malformed
+    lines, [N/A] fields, samples outside the windows, no nvidia-smi at all."""
+    import importlib.util
+    import time
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.AllGpuSampler()
+    now = time.time()
+    s.lines = [(now, "0, 1965, 3996, 55, 62, 810.5, 0x0"), (now, "1, 1965, 3996, 61, 70, 820.1, 0x4"), (now, "1, [N/A], 3996, 63, 71, 825.1, 0x4"),
+               (now - 100, "2, 1, 1, 1, 1, 1, x"), (now, "garbage"), (now, "")]
+    out = s.summary([(now - 1, now + 1)])
+    assert [g["gpu"] for g in out] == [0, 1] and out[1]["samples"] == 2 and out[1]["hbm_temp_c"] == 71.0 and out[1]["sm_mhz"] == 1965.0
+    assert s.summary([]) is None and bench.AllGpuSampler().summary([(0, 1)]) is None
+    s2 = bench.AllGpuSampler()
+    s2.start()          # no nvidia-smi on the build container: must not raise
+    s2.stop()
