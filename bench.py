@@ -948,7 +948,9 @@ def run_v8(args, rank, world, local_rank):
                 "note": "DetectionPipeline.submit(): frames from pinned host memory (H2D on a copy stream, double-buffered) + "
                         "compact detections back to pinned host (D2H) every step; PCIe-bound",
                 "h2d_gbps": pipe.h2d_bytes * K / (ms_e2e * 1e-3) / 1e9},
-        "gpu_launches": (3 + (1 if peer is not None else 0)) * K,  # letterbox + scan + nms (+ gather_wait) per step
+        # our kernels inside one timed block: letterbox + scan + nms per step; the peer gather adds copy + publish + wait per group of G
+        # steps plus the same three for the flush of the last group (fused variant: the publish is inside nms_kernel, one wait per step)
+        "gpu_launches": 3 * K + (0 if peer is None else (K if peer.fused else 3 * (K // G) + 3)),
         "decode_nms_us_per_frame": ms_decnms * 1e3 / BATCH,
         "decode_nms_ms_per_batch": ms_decnms,
         "kernels_us": {"letterbox": lb_ms * 1e3, "scan": scan_ms_b2b * 1e3, "scan_in_graph": scan_ms_graph * 1e3, "nms": nms_ms * 1e3,
